@@ -1,0 +1,270 @@
+/*
+ * dbsp_b200.h — C ABI of the B200-native Z-set delta hot path.
+ *
+ * This is the drop-in boundary for the path BASELINE.json's north_star names:
+ * the reference's `Batch` / `Batcher` / `Builder` / `Merger` / `Trace` trait
+ * family (crates/dbsp/src/trace/mod.rs:86-396) and the `eval` bodies of the
+ * relational operators that consume it.  A Rust `dbsp-b200-sys` crate binds
+ * exactly these symbols; all arguments are plain
+ * pointers, sizes and POD structs — no torch / C++ types cross the boundary.
+ *
+ * Conventions (mirroring SURVEY.md §8b):
+ *   - every call returns int32 status, 0 = DBSP_OK; no exception crosses;
+ *   - a `dbsp_ctx` is bound to one GPU + one CUDA stream and must be used
+ *     from one host thread at a time (the reference confines a circuit
+ *     replica to its worker thread, circuit_builder.rs:1439-1450);
+ *   - batches are immutable, reference counted values (the reference's
+ *     batches are immutable values too, zset_batch.rs:27);
+ *   - every *_free is a no-op on NULL.
+ *
+ * Data model.  A row is `n_key_lanes + n_val_lanes` 64-bit lanes plus one
+ * int64 weight.  Lanes are u64 or i64 and compare lexicographically, which
+ * is Rust's derived `Ord` on tuples of integers.  `n_val_lanes == 0` is an
+ * `OrdZSet<K,R>` (zset_batch.rs:28-31); otherwise an
+ * `OrdIndexedZSet<K,V,R>` (indexed_zset_batch.rs:27-41).  On the device a
+ * batch is column-major: one contiguous u64 array per lane plus the weight
+ * array, rows sorted by (key lanes, val lanes), consolidated (no duplicate
+ * rows, no zero weights).  `dbsp_batch_download_csr` returns the
+ * reference's canonical `keys / offs / vals / diffs` vectors.
+ */
+#ifndef DBSP_B200_H
+#define DBSP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBSP_MAX_LANES 8
+#define DBSP_MAX_PREDS 4
+
+enum dbsp_status {
+  DBSP_OK = 0,
+  DBSP_ERR_INVALID = 1,   /* bad argument / schema mismatch                */
+  DBSP_ERR_CUDA = 2,      /* CUDA runtime error (see dbsp_last_error)      */
+  DBSP_ERR_NO_DEVICE = 3, /* no usable CUDA device: there is NO CPU fallback */
+  DBSP_ERR_UNSUPPORTED = 4
+};
+
+enum dbsp_lane_type { DBSP_U64 = 0, DBSP_I64 = 1 };
+
+/* Row schema.  Replaces the `K: DBData, V: DBData` type parameters of
+ * `Batch` (trace/mod.rs:49-76, 237-300) for the supported key/value set:
+ * tuples of <= 8 integer lanes in total. */
+typedef struct dbsp_schema {
+  uint8_t n_key_lanes;
+  uint8_t n_val_lanes;
+  uint8_t lane_types[DBSP_MAX_LANES]; /* key lanes first, then val lanes */
+} dbsp_schema;
+
+/* ---- declarative row expressions (replace the Rust closures passed to
+ * join / flat_map_index / map_index, join.rs:187, filter_map.rs:143-152) -- */
+enum dbsp_src_kind {
+  DBSP_SRC_KEY = 0,   /* lane `idx` of the (join) key                       */
+  DBSP_SRC_LVAL = 1,  /* lane `idx` of the left value (v1 of join_func);
+                         for map_index / raw tables: value lane / column    */
+  DBSP_SRC_RVAL = 2,  /* lane `idx` of the right value (v2 of join_func)    */
+  DBSP_SRC_CONST = 3  /* the constant `cst`                                 */
+};
+enum dbsp_expr_op {
+  DBSP_OP_COPY = 0, DBSP_OP_NEG = 1, DBSP_OP_ADD = 2, DBSP_OP_SUB = 3,
+  DBSP_OP_MUL = 4, DBSP_OP_DIV = 5 /* signed, truncating (Rust isize `/`) */
+};
+enum dbsp_cmp_op {
+  DBSP_CMP_EQ = 0, DBSP_CMP_NE = 1, DBSP_CMP_LT = 2, DBSP_CMP_LE = 3,
+  DBSP_CMP_GT = 4, DBSP_CMP_GE = 5,
+  DBSP_CMP_IN = 6 /* a < 64 && bit a of b is set: membership in a small code
+                     set, e.g. STATES_OF_INTEREST.contains (nexmark q3.rs:44) */
+};
+typedef struct dbsp_src {
+  uint8_t kind;
+  uint8_t idx;
+  uint8_t pad_[6];
+  int64_t cst;
+} dbsp_src;
+typedef struct dbsp_expr {
+  uint8_t op;
+  uint8_t pad_[7];
+  dbsp_src a, b;
+} dbsp_expr;
+typedef struct dbsp_pred {
+  uint8_t cmp;
+  uint8_t is_signed;
+  uint8_t pad_[6];
+  dbsp_src a, b;
+} dbsp_pred;
+/* Projection + filter: output row = (out[0..n_out_key+n_out_val)), kept iff
+ * every predicate holds. */
+typedef struct dbsp_proj {
+  dbsp_schema out_schema;
+  uint8_t n_pred;
+  uint8_t pad_[5];
+  dbsp_expr out[DBSP_MAX_LANES];
+  dbsp_pred pred[DBSP_MAX_PREDS];
+} dbsp_proj;
+
+/* Aggregators (operator/aggregate/{max,min,fold}.rs, mod.rs:129-156). */
+enum dbsp_agg_kind {
+  DBSP_AGG_MAX = 0,        /* Max over the value tuple  (max.rs:36-55)       */
+  DBSP_AGG_MIN = 1,        /* Min                       (min.rs:38-57)       */
+  DBSP_AGG_FOLD_COUNT = 2, /* Fold: # values with non-zero weight            */
+  DBSP_AGG_FOLD_SUM = 3,   /* Fold: sum of value lane 0 over such values     */
+  DBSP_AGG_WCOUNT = 4,     /* WeightedCount over OrdZSet<K> (mod.rs:129-156) */
+  DBSP_AGG_WCOUNT2 = 5     /* WeightedCount over the (sum,count) pair weight
+                              of `average` (average.rs:26-29): delta is
+                              OrdZSet<(K.., which)>, which in {0,1}          */
+};
+enum dbsp_weigh_mode {
+  DBSP_WEIGH_LINEAR = 0, /* weigh(f): weight_k = sum f(k,v)*w (mod.rs:297-323) */
+  DBSP_WEIGH_AVG = 1     /* f = Avg(value,1): rows (k,0)->sum v*w, (k,1)->sum w */
+};
+
+typedef struct dbsp_ctx dbsp_ctx;
+typedef struct dbsp_batch dbsp_batch;
+typedef struct dbsp_spine dbsp_spine;
+
+/* ---- context -------------------------------------------------------- */
+/* One context per GPU / circuit replica (runtime.rs:137-180: one worker =
+ * one replica).  Fails with DBSP_ERR_NO_DEVICE when no CUDA device is
+ * usable — there is no CPU path behind this ABI. */
+int32_t dbsp_ctx_create(int32_t device, dbsp_ctx** out);
+int32_t dbsp_ctx_destroy(dbsp_ctx* ctx);
+int32_t dbsp_ctx_sync(dbsp_ctx* ctx);
+const char* dbsp_last_error(void);
+/* Counters: kernels launched by this library and bytes it copied H2D/D2H
+ * since the last reset (bench.py's gpu_launches / e2e byte counts). */
+int32_t dbsp_ctx_stats(dbsp_ctx* ctx, uint64_t* kernel_launches,
+                       uint64_t* h2d_bytes, uint64_t* d2h_bytes, int32_t reset);
+/* CUDA stream the context launches on (cudaStream_t as void*), so a host
+ * can order its own work / CUDA events on it. */
+void* dbsp_ctx_stream(dbsp_ctx* ctx);
+
+/* ---- batches -------------------------------------------------------- */
+/* Batch::from_tuples (trace/mod.rs:259-263) = MergeBatcher + consolidate
+ * (merge_batcher/mod.rs:65-80,155-197; consolidation/mod.rs:32-52) + Builder
+ * (ordered/mod.rs:874-888): sort, sum equal rows, drop zero weights.
+ * `cols[l]` points to n u64 per lane (key lanes then val lanes); `weights`
+ * may be NULL (all +1).  `on_device` != 0: the pointers are device memory. */
+int32_t dbsp_batch_from_tuples(dbsp_ctx* ctx, const dbsp_schema* schema,
+                               const uint64_t* const* cols,
+                               const int64_t* weights, uint64_t n,
+                               int32_t on_device, dbsp_batch** out);
+/* flat_map_index over a raw (unsorted, column-major) event table followed by
+ * from_tuples (filter_map.rs:700-724): SRC_LVAL idx = column index. */
+int32_t dbsp_batch_from_table(dbsp_ctx* ctx, const uint64_t* const* cols,
+                              uint32_t n_cols, const int64_t* weights,
+                              uint64_t n, int32_t on_device,
+                              const dbsp_proj* proj, dbsp_batch** out);
+int32_t dbsp_batch_empty(dbsp_ctx* ctx, const dbsp_schema* schema,
+                         dbsp_batch** out);
+/* Batch::merge / Merger::work run to completion (trace/mod.rs:371-396;
+ * column_layer/builders.rs:98-169; ordered/mod.rs:344-396,806-834). */
+int32_t dbsp_batch_merge(dbsp_ctx* ctx, const dbsp_batch* a,
+                         const dbsp_batch* b, dbsp_batch** out);
+/* neg (column_layer/mod.rs:452-480). */
+int32_t dbsp_batch_neg(dbsp_ctx* ctx, const dbsp_batch* a, dbsp_batch** out);
+/* Same rows, different key/value split: `index()` (operator/index.rs:128-157)
+ * and its inverse are free in the flat column-major layout. */
+int32_t dbsp_batch_reindex(dbsp_ctx* ctx, const dbsp_batch* a,
+                           uint32_t n_key_lanes, dbsp_batch** out);
+/* BatchReader::len / key_count (trace/mod.rs:179-234). */
+int32_t dbsp_batch_len(const dbsp_batch* b, uint64_t* n_tuples);
+int32_t dbsp_batch_key_count(dbsp_ctx* ctx, const dbsp_batch* b,
+                             uint64_t* n_keys);
+int32_t dbsp_batch_schema(const dbsp_batch* b, dbsp_schema* out);
+/* Canonical vectors of the reference's batch structs.  Any pointer may be
+ * NULL (skipped).  keys[l]: n_keys u64 (n_tuples when n_val_lanes == 0);
+ * offs: n_keys+1 (only when n_val_lanes > 0); vals[l], diffs: n_tuples. */
+int32_t dbsp_batch_download_csr(dbsp_ctx* ctx, const dbsp_batch* b,
+                                uint64_t* const* keys, uint64_t* offs,
+                                uint64_t* const* vals, int64_t* diffs);
+/* Device pointers of the flat column-major rows (lane l, weights). */
+int32_t dbsp_batch_device_columns(const dbsp_batch* b, const uint64_t** cols,
+                                  const int64_t** weights);
+/* Largest key (first key lane set) of the batch — `fast_forward_keys` +
+ * `get_key` as used by watermark_monotonic (watermark.rs:38-45).
+ * *valid = 0 when the batch is empty. */
+int32_t dbsp_batch_last_key(dbsp_ctx* ctx, const dbsp_batch* b, uint64_t* key,
+                            int32_t* valid);
+int32_t dbsp_batch_clone(const dbsp_batch* b, dbsp_batch** out);
+int32_t dbsp_batch_free(dbsp_batch* b);
+
+/* ---- spine (trace) -------------------------------------------------- */
+/* Spine (trace/spine_fueled.rs:107-119): LSM of immutable batches. */
+int32_t dbsp_spine_new(dbsp_ctx* ctx, const dbsp_schema* schema,
+                       dbsp_spine** out);
+/* Trace::insert (spine_fueled.rs:605-634): the batch is shared, not copied. */
+int32_t dbsp_spine_insert(dbsp_ctx* ctx, dbsp_spine* s, const dbsp_batch* b);
+/* Trace::consolidate (spine_fueled.rs:583-600): merge everything. */
+int32_t dbsp_spine_consolidate(dbsp_ctx* ctx, dbsp_spine* s, dbsp_batch** out);
+/* truncate_keys_below (spine_fueled.rs:223-233); `key` = n_key_lanes u64. */
+int32_t dbsp_spine_truncate_keys_below(dbsp_ctx* ctx, dbsp_spine* s,
+                                       const uint64_t* key);
+int32_t dbsp_spine_len(const dbsp_spine* s, uint64_t* n_tuples,
+                       uint32_t* n_batches);
+int32_t dbsp_spine_free(dbsp_spine* s);
+
+/* ---- operators ------------------------------------------------------ */
+/* JoinTrace::eval (operator/join.rs:732-863), Time = (): delta joined with
+ * every batch of the trace, weights multiplied, join_func = proj, result
+ * consolidated.  `delta_is_left` != 0: delta rows feed SRC_LVAL and trace
+ * rows SRC_RVAL; 0: swapped (the flipped closure of join.rs:279-284). */
+int32_t dbsp_join_delta_trace(dbsp_ctx* ctx, const dbsp_batch* delta,
+                              const dbsp_spine* trace, const dbsp_proj* proj,
+                              int32_t delta_is_left, dbsp_batch** out);
+/* Join::eval (join.rs:436-473): stateless batch x batch. */
+int32_t dbsp_join_batches(dbsp_ctx* ctx, const dbsp_batch* left,
+                          const dbsp_batch* right, const dbsp_proj* proj,
+                          dbsp_batch** out);
+/* SemiJoinStream::eval (operator/semijoin.rs:100-142). */
+int32_t dbsp_semijoin(dbsp_ctx* ctx, const dbsp_batch* pairs,
+                      const dbsp_batch* keys, dbsp_batch** out);
+/* AggregateIncremental::eval (aggregate/mod.rs:600-684) fused with
+ * Upsert::eval (operator/upsert.rs:161-208): for every key of `delta`,
+ * aggregate the key's values in `in_trace` (which already contains delta),
+ * compare with the key's current value in `out_trace`, emit -1/+1 rows.
+ * The caller then inserts *out into out_trace (the TraceAppend of
+ * upsert.rs:69-107). */
+int32_t dbsp_aggregate_delta(dbsp_ctx* ctx, const dbsp_batch* delta,
+                             const dbsp_spine* in_trace,
+                             const dbsp_spine* out_trace, int32_t agg_kind,
+                             dbsp_batch** out);
+/* weigh (aggregate/mod.rs:297-323). `f` gives f(k,v) (SRC_KEY/SRC_LVAL). */
+int32_t dbsp_weigh(dbsp_ctx* ctx, const dbsp_batch* b, const dbsp_expr* f,
+                   int32_t mode, dbsp_batch** out);
+/* DistinctIncrementalTotal::eval (operator/distinct.rs:196-254). */
+int32_t dbsp_distinct_delta(dbsp_ctx* ctx, const dbsp_batch* delta,
+                            const dbsp_spine* delayed_integral,
+                            dbsp_batch** out);
+/* IndexedZSet::distinct (algebra/zset/mod.rs:14-38). */
+int32_t dbsp_stream_distinct(dbsp_ctx* ctx, const dbsp_batch* b,
+                             dbsp_batch** out);
+/* Window::eval (operator/time_series/window.rs:144-222).  Bounds are
+ * n_key_lanes u64 each; has_prev == 0 on the first step. */
+int32_t dbsp_window_delta(dbsp_ctx* ctx, const dbsp_spine* trace,
+                          const dbsp_batch* delta, int32_t has_prev,
+                          const uint64_t* start0, const uint64_t* end0,
+                          const uint64_t* start1, const uint64_t* end1,
+                          dbsp_batch** out);
+/* Map/FlatMap/Index::eval + from_tuples (filter_map.rs:563-577,700-724). */
+int32_t dbsp_map_index(dbsp_ctx* ctx, const dbsp_batch* b,
+                       const dbsp_proj* proj, dbsp_batch** out);
+/* shard_batch (operator/communication/shard.rs:165-199): split by
+ * hash(key) % n_shards into n_shards ordered batches.  The exchange itself
+ * (exchange.rs:128-200) is done by the host with its collective library on
+ * dbsp_batch_device_columns(); the receiver merges (shard.rs:136-144). */
+int32_t dbsp_shard_partition(dbsp_ctx* ctx, const dbsp_batch* b,
+                             uint32_t n_shards, dbsp_batch** outs);
+/* Builder path (trace/mod.rs:338-368): adopt rows that are already sorted
+ * and consolidated (e.g. a segment received from a peer). */
+int32_t dbsp_batch_from_sorted(dbsp_ctx* ctx, const dbsp_schema* schema,
+                               const uint64_t* const* cols,
+                               const int64_t* weights, uint64_t n,
+                               int32_t on_device, dbsp_batch** out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBSP_B200_H */

@@ -1,0 +1,862 @@
+// dbsp_oracle.cpp — CPU restatement of the reference's Z-set delta hot path.
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing in the product package may link, load or
+// call this file; only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs use it, as the checker or as the timed
+// CPU baseline.  The reference is Rust and cannot be built here (no rustc), so
+// this is a "port": every routine follows the reference file:line it cites
+// (paths relative to /root/reference/crates/dbsp/src/).  Parity is pinned by
+// the reference's own golden vectors (tests/test_oracle_golden.py), see
+// SURVEY.md §8c.
+//
+// The C entry points mirror include/dbsp_b200.h one to one with the prefix
+// `orc_` so that the same host-side operator layer can be driven against the
+// oracle from the test-suite.
+//
+// Storage follows the reference structs: OrdZSet = ColumnLayer{keys,diffs}
+// (trace/ord/zset_batch.rs:28-31, trace/layers/column_layer/mod.rs:31-36);
+// OrdIndexedZSet = OrderedLayer{keys,offs,ColumnLayer{vals,diffs}}
+// (trace/ord/indexed_zset_batch.rs:27-41, trace/layers/ordered/mod.rs:32-44).
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../include/dbsp_b200.h"
+
+typedef uint64_t u64;
+typedef int64_t i64;
+#define MAXL DBSP_MAX_LANES
+
+namespace {
+
+// A column-major layer of `nl` lanes, `n` rows (nl may be 0: key = ()).
+struct Layer {
+  int nl = 0;
+  uint8_t ty[MAXL] = {0};
+  std::vector<u64> c[MAXL];
+  size_t n = 0;
+  void init(int nl_, const uint8_t* ty_) {
+    nl = nl_;
+    for (int l = 0; l < nl; l++) ty[l] = ty_[l];
+  }
+  void push(const u64* row) {
+    for (int l = 0; l < nl; l++) c[l].push_back(row[l]);
+    n++;
+  }
+  void push_from(const Layer& o, size_t i) {
+    for (int l = 0; l < nl; l++) c[l].push_back(o.c[l][i]);
+    n++;
+  }
+  void get(size_t i, u64* row) const {
+    for (int l = 0; l < nl; l++) row[l] = c[l][i];
+  }
+};
+
+inline int cmp1(uint8_t ty, u64 a, u64 b) {
+  if (ty == DBSP_I64) return ((i64)a < (i64)b) ? -1 : ((i64)a > (i64)b);
+  return (a < b) ? -1 : (a > b);
+}
+inline int cmp_rows(const Layer& A, size_t i, const Layer& B, size_t j) {
+  for (int l = 0; l < A.nl; l++) {
+    int c = cmp1(A.ty[l], A.c[l][i], B.c[l][j]);
+    if (c) return c;
+  }
+  return 0;
+}
+inline int cmp_row_tuple(const Layer& A, size_t i, const u64* t) {
+  for (int l = 0; l < A.nl; l++) {
+    int c = cmp1(A.ty[l], A.c[l][i], t[l]);
+    if (c) return c;
+  }
+  return 0;
+}
+inline int cmp_tuples(const uint8_t* ty, int nl, const u64* a, const u64* b) {
+  for (int l = 0; l < nl; l++) {
+    int c = cmp1(ty[l], a[l], b[l]);
+    if (c) return c;
+  }
+  return 0;
+}
+
+struct Batch {
+  dbsp_schema s;
+  Layer K;                 // keys (n = key count; = tuple count when nv == 0)
+  std::vector<u64> offs;   // nkeys+1 when nv > 0
+  Layer V;                 // values (nv lanes)
+  std::vector<i64> w;      // diffs
+  explicit Batch(const dbsp_schema& sc) : s(sc) {
+    K.init(s.n_key_lanes, s.lane_types);
+    V.init(s.n_val_lanes, s.lane_types + s.n_key_lanes);
+    if (s.n_val_lanes) offs.push_back(0);
+  }
+  bool indexed() const { return s.n_val_lanes > 0; }
+  size_t len() const { return w.size(); }
+  size_t nkeys() const { return K.n; }
+  void vrange(size_t ki, size_t& lo, size_t& hi) const {
+    if (indexed()) { lo = offs[ki]; hi = offs[ki + 1]; } else { lo = ki; hi = ki + 1; }
+  }
+};
+typedef std::shared_ptr<Batch> BatchP;
+
+// advance: count of the prefix of [lo,hi) satisfying the monotone predicate.
+// Linear scan of <= 8, then exponential + binary search
+// (trace/layers/advance.rs:3,25-72).
+template <class F>
+size_t advance(size_t lo, size_t hi, F pred) {
+  const size_t SMALL = 8;
+  size_t len = hi - lo;
+  if (len > SMALL && pred(lo + SMALL)) {
+    size_t index = SMALL + 1;
+    if (index < len && pred(lo + index)) {
+      size_t step = 1;
+      while (index + step < len && pred(lo + index + step)) { index += step; step <<= 1; }
+      step >>= 1;
+      while (step > 0) {
+        if (index + step < len && pred(lo + index + step)) index += step;
+        step >>= 1;
+      }
+      index += 1;
+    }
+    return index;
+  }
+  size_t limit = std::min(len, SMALL);
+  for (size_t i = 0; i < limit; i++) if (!pred(lo + i)) return i;
+  return limit;
+}
+
+// Builder (trace/layers/ordered/mod.rs:468-479,874-888;
+// column_layer/builders.rs:203-216): rows arrive sorted and consolidated.
+struct Builder {
+  BatchP b;
+  explicit Builder(const dbsp_schema& s) : b(std::make_shared<Batch>(s)) {}
+  void push(const u64* key, const u64* val, i64 w) {
+    Batch& B = *b;
+    if (!B.indexed()) { B.K.push(key); B.w.push_back(w); return; }
+    if (B.K.n == 0 || cmp_row_tuple(B.K, B.K.n - 1, key) != 0) {
+      if (B.K.n > 0) B.offs.push_back(B.w.size());  // close previous key
+      B.K.push(key);
+    }
+    B.V.push(val);
+    B.w.push_back(w);
+  }
+  BatchP done() {
+    Batch& B = *b;
+    if (B.indexed()) { if (B.K.n > 0) B.offs.push_back(B.w.size()); }
+    return b;
+  }
+};
+
+// consolidate (trace/consolidation/mod.rs:32-52): sort by key, sum the
+// weights of equal keys, drop zeros; then Builder (merge_batcher/mod.rs:65-80).
+// The reference sorts with its own pdqsort (consolidation/quicksort.rs:12-33);
+// only the sorted order is observable, std::sort (introsort) stands in.
+BatchP from_tuples(const dbsp_schema& s, const u64* const* cols, const i64* w, size_t n) {
+  int nl = s.n_key_lanes + s.n_val_lanes;
+  std::vector<size_t> idx(n);
+  for (size_t i = 0; i < n; i++) idx[i] = i;
+  auto less = [&](size_t a, size_t b) {
+    for (int l = 0; l < nl; l++) {
+      int c = cmp1(s.lane_types[l], cols[l][a], cols[l][b]);
+      if (c) return c < 0;
+    }
+    return false;
+  };
+  std::sort(idx.begin(), idx.end(), less);
+  Builder bld(s);
+  u64 row[MAXL];
+  size_t i = 0;
+  while (i < n) {
+    size_t j = i;
+    i64 sum = 0;
+    while (j < n && !less(idx[i], idx[j]) && !less(idx[j], idx[i])) {
+      sum = (i64)((u64)sum + (u64)(w ? w[idx[j]] : 1));  // isize add wraps in release
+      j++;
+    }
+    if (sum != 0) {
+      for (int l = 0; l < nl; l++) row[l] = cols[l][idx[i]];
+      bld.push(row, row + s.n_key_lanes, sum);
+    }
+    i = j;
+  }
+  return bld.done();
+}
+
+// Tuple accumulator feeding from_tuples.
+struct Tuples {
+  dbsp_schema s;
+  std::vector<u64> c[MAXL];
+  std::vector<i64> w;
+  explicit Tuples(const dbsp_schema& sc) : s(sc) {}
+  void push(const u64* row, i64 wt) {
+    int nl = s.n_key_lanes + s.n_val_lanes;
+    for (int l = 0; l < nl; l++) c[l].push_back(row[l]);
+    w.push_back(wt);
+  }
+  BatchP build() {
+    const u64* cols[MAXL];
+    for (int l = 0; l < MAXL; l++) cols[l] = c[l].data();
+    return from_tuples(s, cols, w.data(), w.size());
+  }
+};
+
+// ColumnLayerBuilder::copy_range + push_merge
+// (trace/layers/column_layer/builders.rs:85-96, 98-169): galloping 2-way
+// merge, copies capped at 1000 rows, equal keys summed, zero sums dropped.
+void leaf_push_merge(Layer& outK, std::vector<i64>& outW, const Layer& A, const std::vector<i64>& wa,
+                     size_t lo1, size_t hi1, const Layer& B, const std::vector<i64>& wb, size_t lo2,
+                     size_t hi2) {
+  auto copy_range = [&](const Layer& S, const std::vector<i64>& ws, size_t lo, size_t hi) {
+    for (int l = 0; l < S.nl; l++) outK.c[l].insert(outK.c[l].end(), S.c[l].begin() + lo, S.c[l].begin() + hi);
+    outK.n += hi - lo;
+    outW.insert(outW.end(), ws.begin() + lo, ws.begin() + hi);
+  };
+  while (lo1 < hi1 && lo2 < hi2) {
+    int c = cmp_rows(A, lo1, B, lo2);
+    if (c < 0) {
+      size_t step = 1 + advance(lo1 + 1, hi1, [&](size_t i) { return cmp_rows(A, i, B, lo2) < 0; });
+      step = std::min<size_t>(step, 1000);
+      copy_range(A, wa, lo1, lo1 + step);
+      lo1 += step;
+    } else if (c == 0) {
+      i64 sum = (i64)((u64)wa[lo1] + (u64)wb[lo2]);
+      if (sum != 0) { outK.push_from(A, lo1); outW.push_back(sum); }
+      lo1++; lo2++;
+    } else {
+      size_t step = 1 + advance(lo2 + 1, hi2, [&](size_t i) { return cmp_rows(B, i, A, lo1) < 0; });
+      step = std::min<size_t>(step, 1000);
+      copy_range(B, wb, lo2, lo2 + step);
+      lo2 += step;
+    }
+  }
+  if (lo1 < hi1) copy_range(A, wa, lo1, hi1);
+  if (lo2 < hi2) copy_range(B, wb, lo2, hi2);
+}
+
+// Batch::merge.  OrdZSet: one leaf push_merge (zset_batch.rs:307-318).
+// OrdIndexedZSet: OrderedBuilder::merge_step / push_merge / copy_range
+// (trace/layers/ordered/mod.rs:344-396, 787-834): on equal keys merge the two
+// value ranges and keep the key iff something survived; offsets rebased.
+BatchP merge(const Batch& a, const Batch& b) {
+  auto out = std::make_shared<Batch>(a.s);
+  Batch& O = *out;
+  if (!a.indexed()) {
+    leaf_push_merge(O.K, O.w, a.K, a.w, 0, a.K.n, b.K, b.w, 0, b.K.n);
+    return out;
+  }
+  auto copy_range = [&](const Batch& S, size_t lo, size_t hi) {
+    for (size_t k = lo; k < hi; k++) {
+      O.K.push_from(S.K, k);
+      size_t vlo = S.offs[k], vhi = S.offs[k + 1];
+      for (int l = 0; l < S.V.nl; l++) O.V.c[l].insert(O.V.c[l].end(), S.V.c[l].begin() + vlo, S.V.c[l].begin() + vhi);
+      O.V.n += vhi - vlo;
+      O.w.insert(O.w.end(), S.w.begin() + vlo, S.w.begin() + vhi);
+      O.offs.push_back(O.w.size());
+    }
+  };
+  size_t lo1 = 0, hi1 = a.K.n, lo2 = 0, hi2 = b.K.n;
+  while (lo1 < hi1 && lo2 < hi2) {
+    int c = cmp_rows(a.K, lo1, b.K, lo2);
+    if (c < 0) {
+      size_t step = 1 + advance(lo1 + 1, hi1, [&](size_t i) { return cmp_rows(a.K, i, b.K, lo2) < 0; });
+      step = std::min<size_t>(step, 1000);
+      copy_range(a, lo1, lo1 + step);
+      lo1 += step;
+    } else if (c == 0) {
+      size_t before = O.w.size();
+      leaf_push_merge(O.V, O.w, a.V, a.w, a.offs[lo1], a.offs[lo1 + 1], b.V, b.w, b.offs[lo2], b.offs[lo2 + 1]);
+      if (O.w.size() > before) { O.K.push_from(a.K, lo1); O.offs.push_back(O.w.size()); }
+      lo1++; lo2++;
+    } else {
+      size_t step = 1 + advance(lo2 + 1, hi2, [&](size_t i) { return cmp_rows(b.K, i, a.K, lo1) < 0; });
+      step = std::min<size_t>(step, 1000);
+      copy_range(b, lo2, lo2 + step);
+      lo2 += step;
+    }
+  }
+  if (lo1 < hi1) copy_range(a, lo1, hi1);
+  if (lo2 < hi2) copy_range(b, lo2, hi2);
+  return out;
+}
+
+// Cursor::seek_key: first key index >= `key` (exponential search from `from`,
+// trace/layers/column_layer/cursor.rs:121-128 via advance).
+size_t seek_key(const Batch& b, size_t from, const u64* key) {
+  return from + advance(from, b.K.n, [&](size_t i) { return cmp_row_tuple(b.K, i, key) < 0; });
+}
+
+// truncate_keys_below (column_layer/mod.rs:316-319, trace/mod.rs:227-233):
+// the reference only raises `lower_bound`; cursors start there.  The oracle
+// materialises the suffix, which is observably the same.
+BatchP truncate_keys_below(const Batch& b, const u64* key) {
+  size_t k0 = seek_key(b, 0, key);
+  if (k0 == 0) return nullptr;
+  auto out = std::make_shared<Batch>(b.s);
+  Batch& O = *out;
+  for (size_t k = k0; k < b.K.n; k++) {
+    O.K.push_from(b.K, k);
+    size_t lo, hi;
+    b.vrange(k, lo, hi);
+    if (b.indexed()) {
+      for (size_t v = lo; v < hi; v++) { O.V.push_from(b.V, v); O.w.push_back(b.w[v]); }
+      O.offs.push_back(O.w.size());
+    } else {
+      O.w.push_back(b.w[k]);
+    }
+  }
+  return out;
+}
+
+// Spine (trace/spine_fueled.rs:107-119).  The reference places a batch at
+// level log2(len.next_power_of_two()) and spends fuel on in-progress merges
+// (:605-634, :730-812).  The merge *schedule* is unobservable in operator
+// outputs (cursors see the union of all batches, cursor/cursor_list.rs), so
+// this oracle — like the CUDA spine — keeps the same geometric invariant with
+// eager merges: after an insert, while the two newest batches are within 2x
+// of each other they are merged.  Documented in DESIGN.md.
+struct Spine {
+  dbsp_schema s;
+  std::vector<BatchP> batches;   // oldest (largest) first
+  bool has_bound = false;
+  u64 bound[MAXL];
+  explicit Spine(const dbsp_schema& sc) : s(sc) {}
+  void insert(BatchP b) {
+    if (b->len() == 0) return;   // spine_fueled.rs:606-608
+    if (has_bound) { BatchP t = truncate_keys_below(*b, bound); if (t) b = t; if (b->len() == 0) return; }
+    batches.push_back(b);
+    while (batches.size() >= 2) {
+      size_t m = batches.size();
+      if (batches[m - 2]->len() >= 2 * batches[m - 1]->len()) break;
+      BatchP merged = merge(*batches[m - 2], *batches[m - 1]);
+      batches.pop_back(); batches.pop_back();
+      if (merged->len()) batches.push_back(merged);
+    }
+  }
+  BatchP consolidate() {   // spine_fueled.rs:583-600
+    BatchP acc = std::make_shared<Batch>(s);
+    for (auto& b : batches) acc = merge(*acc, *b);
+    return acc;
+  }
+  void truncate(const u64* key) {   // spine_fueled.rs:223-233
+    has_bound = true;
+    for (int l = 0; l < s.n_key_lanes; l++) bound[l] = key[l];
+    std::vector<BatchP> keep;
+    for (auto& b : batches) {
+      BatchP t = truncate_keys_below(*b, key);
+      if (!t) t = b;
+      if (t->len()) keep.push_back(t);
+    }
+    batches.swap(keep);
+  }
+  size_t len() const { size_t n = 0; for (auto& b : batches) n += b->len(); return n; }
+};
+
+// CursorList view of one key (trace/cursor/cursor_list.rs:57-127,200-210):
+// the union of the key's values over all spine batches in value order, the
+// weight of a value being the SUM over batches (may be zero).
+struct KV { const Batch* b; size_t pos; };
+void key_group(const Spine& sp, const u64* key, std::vector<std::pair<KV, i64>>& out) {
+  out.clear();
+  std::vector<KV> all;
+  for (auto& bp : sp.batches) {
+    const Batch& b = *bp;
+    size_t k = seek_key(b, 0, key);
+    if (k < b.K.n && cmp_row_tuple(b.K, k, key) == 0) {
+      size_t lo, hi;
+      b.vrange(k, lo, hi);
+      for (size_t v = lo; v < hi; v++) all.push_back({&b, v});
+    }
+  }
+  std::stable_sort(all.begin(), all.end(), [](const KV& x, const KV& y) {
+    return x.b->V.nl && cmp_rows(x.b->V, x.pos, y.b->V, y.pos) < 0;
+  });
+  size_t i = 0;
+  while (i < all.size()) {
+    size_t j = i;
+    i64 sum = 0;
+    while (j < all.size() && (all[i].b->V.nl == 0 || cmp_rows(all[i].b->V, all[i].pos, all[j].b->V, all[j].pos) == 0)) {
+      sum = (i64)((u64)sum + (u64)all[j].b->w[all[j].pos]);
+      j++;
+    }
+    out.push_back({all[i], sum});
+    i = j;
+  }
+}
+
+// ---- declarative row expressions -------------------------------------
+struct Env { const u64* key; const u64* lv; const u64* rv; };
+inline u64 src_val(const dbsp_src& s, const Env& e) {
+  switch (s.kind) {
+    case DBSP_SRC_KEY: return e.key[s.idx];
+    case DBSP_SRC_LVAL: return e.lv[s.idx];
+    case DBSP_SRC_RVAL: return e.rv[s.idx];
+    default: return (u64)s.cst;
+  }
+}
+inline u64 expr_val(const dbsp_expr& x, const Env& e) {
+  u64 a = src_val(x.a, e);
+  switch (x.op) {
+    case DBSP_OP_COPY: return a;
+    case DBSP_OP_NEG: return (u64)0 - a;
+    case DBSP_OP_ADD: return a + src_val(x.b, e);
+    case DBSP_OP_SUB: return a - src_val(x.b, e);
+    case DBSP_OP_MUL: return a * src_val(x.b, e);
+    case DBSP_OP_DIV: { i64 d = (i64)src_val(x.b, e); return d == 0 ? 0 : (u64)((i64)a / d); }
+  }
+  return a;
+}
+inline bool pred_ok(const dbsp_pred& p, const Env& e) {
+  u64 a = src_val(p.a, e), b = src_val(p.b, e);
+  int c = p.is_signed ? (((i64)a < (i64)b) ? -1 : ((i64)a > (i64)b)) : ((a < b) ? -1 : (a > b));
+  switch (p.cmp) {
+    case DBSP_CMP_EQ: return c == 0;
+    case DBSP_CMP_NE: return c != 0;
+    case DBSP_CMP_LT: return c < 0;
+    case DBSP_CMP_LE: return c <= 0;
+    case DBSP_CMP_GT: return c > 0;
+    case DBSP_CMP_GE: return c >= 0;
+    case DBSP_CMP_IN: return a < 64 && ((b >> a) & 1);
+  }
+  return false;
+}
+inline bool project(const dbsp_proj& p, const Env& e, u64* row) {
+  for (int i = 0; i < p.n_pred; i++) if (!pred_ok(p.pred[i], e)) return false;
+  int nl = p.out_schema.n_key_lanes + p.out_schema.n_val_lanes;
+  for (int l = 0; l < nl; l++) row[l] = expr_val(p.out[l], e);
+  return true;
+}
+
+// Join::eval (operator/join.rs:436-473) — also the inner loop of
+// JoinTrace::eval (:751-787): merge-walk both key sets, on equal keys the
+// cartesian product of the value ranges, weight = w1*w2 (MulByRef,
+// algebra/mod.rs:195-213), join_func = proj.
+void join_into(const Batch& L, const Batch& R, const dbsp_proj& proj, bool swap, Tuples& out) {
+  size_t i = 0, j = 0;
+  u64 key[MAXL], v1[MAXL], v2[MAXL], row[MAXL];
+  while (i < L.K.n && j < R.K.n) {
+    int c = cmp_rows(L.K, i, R.K, j);
+    if (c < 0) { i = i + advance(i, L.K.n, [&](size_t x) { return cmp_rows(L.K, x, R.K, j) < 0; }); }
+    else if (c > 0) { j = j + advance(j, R.K.n, [&](size_t x) { return cmp_rows(R.K, x, L.K, i) < 0; }); }
+    else {
+      L.K.get(i, key);
+      size_t l0, l1, r0, r1;
+      L.vrange(i, l0, l1);
+      R.vrange(j, r0, r1);
+      for (size_t a = l0; a < l1; a++) {
+        if (L.indexed()) L.V.get(a, v1);
+        for (size_t b = r0; b < r1; b++) {
+          if (R.indexed()) R.V.get(b, v2);
+          Env e = swap ? Env{key, v2, v1} : Env{key, v1, v2};
+          if (project(proj, e, row)) out.push(row, (i64)((u64)L.w[a] * (u64)R.w[b]));
+        }
+      }
+      i++; j++;
+    }
+  }
+}
+
+}  // namespace
+
+// ===================== C entry points (prefix orc_) ======================
+struct orc_batch { BatchP p; };
+struct orc_spine { Spine s; explicit orc_spine(const dbsp_schema& sc) : s(sc) {} };
+struct orc_ctx { int dummy; };
+static thread_local std::string g_err;
+
+static orc_batch* wrap(BatchP p) { return new orc_batch{p}; }
+
+extern "C" {
+
+int32_t orc_ctx_create(int32_t, orc_ctx** out) { *out = new orc_ctx{0}; return DBSP_OK; }
+int32_t orc_ctx_destroy(orc_ctx* c) { delete c; return DBSP_OK; }
+int32_t orc_ctx_sync(orc_ctx*) { return DBSP_OK; }
+const char* orc_last_error(void) { return g_err.c_str(); }
+int32_t orc_ctx_stats(orc_ctx*, u64* a, u64* b, u64* c, int32_t) { if (a) *a = 0; if (b) *b = 0; if (c) *c = 0; return DBSP_OK; }
+void* orc_ctx_stream(orc_ctx*) { return nullptr; }
+
+int32_t orc_batch_from_tuples(orc_ctx*, const dbsp_schema* s, const u64* const* cols, const i64* w, u64 n,
+                              int32_t, orc_batch** out) {
+  *out = wrap(from_tuples(*s, cols, w, n));
+  return DBSP_OK;
+}
+
+// FlatMap::eval + from_tuples (operator/filter_map.rs:700-724).
+int32_t orc_batch_from_table(orc_ctx*, const u64* const* cols, uint32_t ncols, const i64* w, u64 n, int32_t,
+                             const dbsp_proj* proj, orc_batch** out) {
+  Tuples t(proj->out_schema);
+  u64 lv[MAXL] = {0}, row[MAXL];
+  for (u64 i = 0; i < n; i++) {
+    for (uint32_t c = 0; c < ncols && c < MAXL; c++) lv[c] = cols[c][i];
+    Env e{lv, lv, lv};
+    if (project(*proj, e, row)) t.push(row, w ? w[i] : 1);
+  }
+  *out = wrap(t.build());
+  return DBSP_OK;
+}
+
+int32_t orc_batch_empty(orc_ctx*, const dbsp_schema* s, orc_batch** out) {
+  *out = wrap(std::make_shared<Batch>(*s));
+  return DBSP_OK;
+}
+
+int32_t orc_batch_merge(orc_ctx*, const orc_batch* a, const orc_batch* b, orc_batch** out) {
+  *out = wrap(merge(*a->p, *b->p));
+  return DBSP_OK;
+}
+
+// neg (column_layer/mod.rs:452-480).
+int32_t orc_batch_neg(orc_ctx*, const orc_batch* a, orc_batch** out) {
+  auto o = std::make_shared<Batch>(*a->p);
+  for (auto& x : o->w) x = (i64)((u64)0 - (u64)x);
+  *out = wrap(o);
+  return DBSP_OK;
+}
+
+// Flat rows of a batch: (key lanes, val lanes, weight) per tuple.
+static void flat_rows(const Batch& b, Tuples& t) {
+  u64 row[MAXL];
+  for (size_t k = 0; k < b.K.n; k++) {
+    b.K.get(k, row);
+    size_t lo, hi;
+    b.vrange(k, lo, hi);
+    for (size_t v = lo; v < hi; v++) {
+      if (b.indexed()) b.V.get(v, row + b.s.n_key_lanes);
+      t.push(row, b.w[v]);
+    }
+  }
+}
+
+// index() (operator/index.rs:128-157) and its inverse: re-split the lanes.
+int32_t orc_batch_reindex(orc_ctx*, const orc_batch* a, uint32_t nk, orc_batch** out) {
+  dbsp_schema s = a->p->s;
+  int nl = s.n_key_lanes + s.n_val_lanes;
+  if ((int)nk > nl) return DBSP_ERR_INVALID;
+  s.n_key_lanes = nk; s.n_val_lanes = nl - nk;
+  Tuples t(s);
+  flat_rows(*a->p, t);
+  *out = wrap(t.build());
+  return DBSP_OK;
+}
+
+int32_t orc_batch_len(const orc_batch* b, u64* n) { *n = b->p->len(); return DBSP_OK; }
+int32_t orc_batch_key_count(orc_ctx*, const orc_batch* b, u64* n) { *n = b->p->nkeys(); return DBSP_OK; }
+int32_t orc_batch_schema(const orc_batch* b, dbsp_schema* out) { *out = b->p->s; return DBSP_OK; }
+
+int32_t orc_batch_download_csr(orc_ctx*, const orc_batch* bb, u64* const* keys, u64* offs, u64* const* vals,
+                               i64* diffs) {
+  const Batch& b = *bb->p;
+  if (keys) for (int l = 0; l < b.K.nl; l++) if (keys[l]) std::copy(b.K.c[l].begin(), b.K.c[l].end(), keys[l]);
+  if (offs && b.indexed()) {
+    if (b.K.n == 0) offs[0] = 0; else std::copy(b.offs.begin(), b.offs.end(), offs);
+  }
+  if (vals) for (int l = 0; l < b.V.nl; l++) if (vals[l]) std::copy(b.V.c[l].begin(), b.V.c[l].end(), vals[l]);
+  if (diffs) std::copy(b.w.begin(), b.w.end(), diffs);
+  return DBSP_OK;
+}
+
+int32_t orc_batch_device_columns(const orc_batch*, const u64**, const i64**) { return DBSP_ERR_UNSUPPORTED; }
+
+// fast_forward_keys + get_key (operator/time_series/watermark.rs:38-45).
+int32_t orc_batch_last_key(orc_ctx*, const orc_batch* b, u64* key, int32_t* valid) {
+  const Batch& B = *b->p;
+  *valid = B.K.n > 0;
+  if (B.K.n) B.K.get(B.K.n - 1, key);
+  return DBSP_OK;
+}
+int32_t orc_batch_clone(const orc_batch* b, orc_batch** out) { *out = wrap(b->p); return DBSP_OK; }
+int32_t orc_batch_free(orc_batch* b) { delete b; return DBSP_OK; }
+
+int32_t orc_batch_from_sorted(orc_ctx* c, const dbsp_schema* s, const u64* const* cols, const i64* w, u64 n,
+                              int32_t d, orc_batch** out) {
+  return orc_batch_from_tuples(c, s, cols, w, n, d, out);
+}
+
+int32_t orc_spine_new(orc_ctx*, const dbsp_schema* s, orc_spine** out) { *out = new orc_spine(*s); return DBSP_OK; }
+int32_t orc_spine_insert(orc_ctx*, orc_spine* s, const orc_batch* b) { s->s.insert(b->p); return DBSP_OK; }
+int32_t orc_spine_consolidate(orc_ctx*, orc_spine* s, orc_batch** out) { *out = wrap(s->s.consolidate()); return DBSP_OK; }
+int32_t orc_spine_truncate_keys_below(orc_ctx*, orc_spine* s, const u64* key) { s->s.truncate(key); return DBSP_OK; }
+int32_t orc_spine_len(const orc_spine* s, u64* n, uint32_t* nb) {
+  if (n) *n = s->s.len();
+  if (nb) *nb = (uint32_t)s->s.batches.size();
+  return DBSP_OK;
+}
+int32_t orc_spine_free(orc_spine* s) { delete s; return DBSP_OK; }
+
+// JoinTrace::eval with Time = () (operator/join.rs:732-863): the trace
+// cursor is a CursorList over the spine's batches and map_times yields each
+// batch's weight separately (:769-776), i.e. delta is joined with every batch
+// and the outputs are consolidated by the Batcher (:845-858).
+int32_t orc_join_delta_trace(orc_ctx*, const orc_batch* delta, const orc_spine* tr, const dbsp_proj* proj,
+                             int32_t delta_is_left, orc_batch** out) {
+  Tuples t(proj->out_schema);
+  for (auto& b : tr->s.batches) join_into(*delta->p, *b, *proj, !delta_is_left, t);
+  *out = wrap(t.build());
+  return DBSP_OK;
+}
+
+int32_t orc_join_batches(orc_ctx*, const orc_batch* l, const orc_batch* r, const dbsp_proj* proj, orc_batch** out) {
+  Tuples t(proj->out_schema);
+  join_into(*l->p, *r->p, *proj, false, t);
+  *out = wrap(t.build());
+  return DBSP_OK;
+}
+
+// SemiJoinStream::eval (operator/semijoin.rs:100-142).
+int32_t orc_semijoin(orc_ctx*, const orc_batch* pairs, const orc_batch* keys, orc_batch** out) {
+  const Batch& P = *pairs->p;
+  const Batch& Kb = *keys->p;
+  Builder bld(P.s);
+  size_t i = 0, j = 0;
+  u64 key[MAXL], val[MAXL];
+  while (i < P.K.n && j < Kb.K.n) {
+    int c = cmp_rows(P.K, i, Kb.K, j);
+    if (c < 0) i++;
+    else if (c > 0) j++;
+    else {
+      P.K.get(i, key);
+      size_t lo, hi;
+      P.vrange(i, lo, hi);
+      for (size_t v = lo; v < hi; v++) {
+        if (P.indexed()) P.V.get(v, val);
+        i64 w = (i64)((u64)P.w[v] * (u64)Kb.w[j]);
+        if (w != 0) bld.push(key, val, w);
+      }
+      i++; j++;
+    }
+  }
+  *out = wrap(bld.done());
+  return DBSP_OK;
+}
+
+// AggregateIncremental::eval / eval_key (operator/aggregate/mod.rs:479-547,
+// 600-684) producing (key, Option<out>) per delta key, then Upsert::eval
+// (operator/upsert.rs:161-208): retract the key's current values in the
+// output trace, insert the new one, consolidate per key.
+int32_t orc_aggregate_delta(orc_ctx*, const orc_batch* delta, const orc_spine* in_tr, const orc_spine* out_tr,
+                            int32_t kind, orc_batch** out) {
+  const Batch& D = *delta->p;
+  const dbsp_schema& os = out_tr->s.s;
+  int nk = os.n_key_lanes, nov = os.n_val_lanes;
+  Builder bld(os);
+  std::vector<std::pair<KV, i64>> grp;
+  u64 key[MAXL], key2[MAXL], newv[MAXL];
+  size_t nkeys = D.K.n;
+  for (size_t ki = 0; ki < nkeys; ki++) {
+    D.K.get(ki, key);
+    if (kind == DBSP_AGG_WCOUNT2) {
+      // key = leading nk lanes of the (K.., which) row; visit each K once.
+      if (ki > 0) { D.K.get(ki - 1, key2); if (cmp_tuples(D.s.lane_types, nk, key, key2) == 0) continue; }
+    }
+    bool has_new = false;
+    if (kind == DBSP_AGG_MAX) {          // max.rs:36-55: walk back to the last value with weight != 0
+      key_group(in_tr->s, key, grp);
+      for (size_t g = grp.size(); g-- > 0;) if (grp[g].second != 0) { grp[g].first.b->V.get(grp[g].first.pos, newv); has_new = true; break; }
+    } else if (kind == DBSP_AGG_MIN) {   // min.rs:38-57
+      key_group(in_tr->s, key, grp);
+      for (size_t g = 0; g < grp.size(); g++) if (grp[g].second != 0) { grp[g].first.b->V.get(grp[g].first.pos, newv); has_new = true; break; }
+    } else if (kind == DBSP_AGG_FOLD_COUNT || kind == DBSP_AGG_FOLD_SUM) {   // fold.rs:76-96
+      key_group(in_tr->s, key, grp);
+      u64 acc = 0;
+      for (auto& g : grp) if (g.second != 0) { has_new = true; acc += (kind == DBSP_AGG_FOLD_COUNT) ? 1 : g.first.b->V.c[0][g.first.pos]; }
+      newv[0] = acc;
+    } else if (kind == DBSP_AGG_WCOUNT) {   // aggregate/mod.rs:129-156
+      key_group(in_tr->s, key, grp);
+      i64 sum = 0;
+      for (auto& g : grp) sum = (i64)((u64)sum + (u64)g.second);
+      has_new = sum != 0; newv[0] = (u64)sum;
+    } else if (kind == DBSP_AGG_WCOUNT2) {  // Avg is zero iff sum and count are both zero (average.rs:88-95)
+      i64 sc[2] = {0, 0};
+      for (int which = 0; which < 2; which++) {
+        for (int l = 0; l < nk; l++) key2[l] = key[l];
+        key2[nk] = (u64)which;
+        key_group(in_tr->s, key2, grp);
+        for (auto& g : grp) sc[which] = (i64)((u64)sc[which] + (u64)g.second);
+      }
+      has_new = sc[0] != 0 || sc[1] != 0; newv[0] = (u64)sc[0]; newv[1] = (u64)sc[1];
+    } else return DBSP_ERR_INVALID;
+    // Upsert::eval for this key.
+    key_group(out_tr->s, key, grp);
+    std::vector<std::pair<std::vector<u64>, i64>> upd;
+    if (has_new) upd.push_back({std::vector<u64>(newv, newv + nov), 1});
+    for (auto& g : grp) if (g.second != 0) {
+      std::vector<u64> v(nov);
+      g.first.b->V.get(g.first.pos, v.data());
+      upd.push_back({v, (i64)((u64)0 - (u64)g.second)});
+    }
+    const uint8_t* vty = os.lane_types + nk;
+    std::sort(upd.begin(), upd.end(), [&](auto& a, auto& b) { return cmp_tuples(vty, nov, a.first.data(), b.first.data()) < 0; });
+    size_t i = 0;
+    while (i < upd.size()) {
+      size_t j = i; i64 sum = 0;
+      while (j < upd.size() && cmp_tuples(vty, nov, upd[i].first.data(), upd[j].first.data()) == 0) { sum = (i64)((u64)sum + (u64)upd[j].second); j++; }
+      if (sum != 0) bld.push(key, upd[i].first.data(), sum);
+      i = j;
+    }
+  }
+  *out = wrap(bld.done());
+  return DBSP_OK;
+}
+
+// weigh (operator/aggregate/mod.rs:297-323).
+int32_t orc_weigh(orc_ctx*, const orc_batch* b, const dbsp_expr* f, int32_t mode, orc_batch** out) {
+  const Batch& B = *b->p;
+  dbsp_schema s = B.s;
+  s.n_val_lanes = 0;
+  if (mode == DBSP_WEIGH_AVG) { s.lane_types[s.n_key_lanes] = DBSP_U64; s.n_key_lanes++; }
+  Builder bld(s);
+  u64 key[MAXL], val[MAXL] = {0};
+  for (size_t k = 0; k < B.K.n; k++) {
+    B.K.get(k, key);
+    size_t lo, hi;
+    B.vrange(k, lo, hi);
+    i64 agg = 0, cnt = 0;
+    for (size_t v = lo; v < hi; v++) {
+      if (B.indexed()) B.V.get(v, val);
+      Env e{key, val, val};
+      agg = (i64)((u64)agg + expr_val(*f, e) * (u64)B.w[v]);
+      cnt = (i64)((u64)cnt + (u64)B.w[v]);
+    }
+    if (mode == DBSP_WEIGH_AVG) {
+      key[B.s.n_key_lanes] = 0; if (agg != 0) bld.push(key, nullptr, agg);
+      key[B.s.n_key_lanes] = 1; if (cnt != 0) bld.push(key, nullptr, cnt);
+    } else if (agg != 0) {
+      bld.push(key, nullptr, agg);
+    }
+  }
+  *out = wrap(bld.done());
+  return DBSP_OK;
+}
+
+// DistinctIncrementalTotal::eval (operator/distinct.rs:196-254).
+int32_t orc_distinct_delta(orc_ctx*, const orc_batch* delta, const orc_spine* integral, orc_batch** out) {
+  const Batch& D = *delta->p;
+  Builder bld(D.s);
+  std::vector<std::pair<KV, i64>> grp;
+  u64 key[MAXL], val[MAXL];
+  for (size_t k = 0; k < D.K.n; k++) {
+    D.K.get(k, key);
+    key_group(integral->s, key, grp);
+    size_t lo, hi;
+    D.vrange(k, lo, hi);
+    for (size_t v = lo; v < hi; v++) {
+      if (D.indexed()) D.V.get(v, val);
+      i64 w = D.w[v], oldw = 0;
+      for (auto& g : grp)
+        if (!D.indexed() || cmp_row_tuple(g.first.b->V, g.first.pos, val) == 0) { oldw = g.second; break; }
+      i64 neww = (i64)((u64)oldw + (u64)w);
+      if (oldw <= 0) { if (neww > 0) bld.push(key, val, 1); }
+      else if (neww <= 0) bld.push(key, val, -1);
+    }
+  }
+  *out = wrap(bld.done());
+  return DBSP_OK;
+}
+
+// IndexedZSet::distinct (algebra/zset/mod.rs:14-38).
+int32_t orc_stream_distinct(orc_ctx*, const orc_batch* b, orc_batch** out) {
+  const Batch& B = *b->p;
+  Builder bld(B.s);
+  u64 key[MAXL], val[MAXL];
+  for (size_t k = 0; k < B.K.n; k++) {
+    B.K.get(k, key);
+    size_t lo, hi;
+    B.vrange(k, lo, hi);
+    for (size_t v = lo; v < hi; v++) {
+      if (B.indexed()) B.V.get(v, val);
+      if (B.w[v] > 0) bld.push(key, val, 1);
+    }
+  }
+  *out = wrap(bld.done());
+  return DBSP_OK;
+}
+
+// Window::eval (operator/time_series/window.rs:144-222).
+int32_t orc_window_delta(orc_ctx*, const orc_spine* tr, const orc_batch* delta, int32_t has_prev, const u64* s0,
+                         const u64* e0, const u64* s1, const u64* e1, orc_batch** out) {
+  const dbsp_schema& s = delta->p->s;
+  int nk = s.n_key_lanes;
+  Tuples t(s);
+  u64 row[MAXL];
+  auto lt = [&](const u64* a, const u64* b) { return cmp_tuples(s.lane_types, nk, a, b) < 0; };
+  // emit keys of `b` in [from, min(until1, until2)) with weight * sign
+  auto emit = [&](const Batch& b, const u64* from, const u64* until1, const u64* until2, int sign) {
+    size_t k = seek_key(b, 0, from);
+    for (; k < b.K.n; k++) {
+      b.K.get(k, row);
+      if (!lt(row, until1)) break;
+      if (until2 && !lt(row, until2)) break;
+      size_t lo, hi;
+      b.vrange(k, lo, hi);
+      for (size_t v = lo; v < hi; v++) {
+        if (b.indexed()) b.V.get(v, row + nk);
+        t.push(row, sign > 0 ? b.w[v] : (i64)((u64)0 - (u64)b.w[v]));
+      }
+    }
+  };
+  if (has_prev) {
+    for (auto& b : tr->s.batches) {
+      emit(*b, s0, s1, e0, -1);                       // region 1: slid out on the left
+      if (lt(e1, e0)) emit(*b, e1, e0, nullptr, -1);  // window shrank on the right
+      const u64* from = lt(e0, s1) ? s1 : e0;         // max(end0, start1)
+      emit(*b, from, e1, nullptr, +1);                // region 3: slid in
+    }
+  }
+  emit(*delta->p, s1, e1, nullptr, +1);
+  *out = wrap(t.build());
+  return DBSP_OK;
+}
+
+// Map/FlatMap::eval + from_tuples (operator/filter_map.rs:563-577,700-724).
+int32_t orc_map_index(orc_ctx*, const orc_batch* b, const dbsp_proj* proj, orc_batch** out) {
+  const Batch& B = *b->p;
+  Tuples t(proj->out_schema);
+  u64 key[MAXL], val[MAXL] = {0}, row[MAXL];
+  for (size_t k = 0; k < B.K.n; k++) {
+    B.K.get(k, key);
+    size_t lo, hi;
+    B.vrange(k, lo, hi);
+    for (size_t v = lo; v < hi; v++) {
+      if (B.indexed()) B.V.get(v, val);
+      Env e{key, val, val};
+      if (project(*proj, e, row)) t.push(row, B.w[v]);
+    }
+  }
+  *out = wrap(t.build());
+  return DBSP_OK;
+}
+
+// The shard hash.  The reference uses XXH3-64 (hash.rs:6-13); placement is
+// unobservable after the union over workers (communication/shard.rs:38-51),
+// so both the oracle and the CUDA path use this splitmix64 fold instead.
+static inline u64 mix64(u64 x) {
+  x += 0x9e3779b97f4a7c15ull;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+  return x ^ (x >> 31);
+}
+// shard_batch (operator/communication/shard.rs:165-199).
+int32_t orc_shard_partition(orc_ctx*, const orc_batch* b, uint32_t P, orc_batch** outs) {
+  const Batch& B = *b->p;
+  std::vector<Builder> blds;
+  for (uint32_t p = 0; p < P; p++) blds.emplace_back(B.s);
+  u64 key[MAXL], val[MAXL];
+  for (size_t k = 0; k < B.K.n; k++) {
+    B.K.get(k, key);
+    u64 h = 0;
+    for (int l = 0; l < B.K.nl; l++) h = mix64(h ^ key[l]);
+    uint32_t p = (uint32_t)(h % P);
+    size_t lo, hi;
+    B.vrange(k, lo, hi);
+    for (size_t v = lo; v < hi; v++) {
+      if (B.indexed()) B.V.get(v, val);
+      blds[p].push(key, val, B.w[v]);
+    }
+  }
+  for (uint32_t p = 0; p < P; p++) outs[p] = wrap(blds[p].done());
+  return DBSP_OK;
+}
+
+}  // extern "C"
