@@ -1,0 +1,376 @@
+// capi.cu — the extern "C" boundary declared in include/dbsp_b200.h, plus the
+// host-side Spine (trace) logic.  No CPU compute path lives here: every
+// data-touching call launches kernels from consolidate.cu / merge.cu / ops.cu.
+#include "ops.cuh"
+
+const char* get_error();
+
+struct dbsp_ctx : Ctx {};
+struct dbsp_batch : Batch {};
+struct dbsp_spine : Spine {};
+
+static inline Batch* B(const dbsp_batch* b) { return (Batch*)b; }
+static inline dbsp_batch* H(Batch* b) { return (dbsp_batch*)b; }
+
+#define CHECK_ARG(c, msg)                 \
+  do {                                    \
+    if (!(c)) { set_error(msg); return DBSP_ERR_INVALID; } \
+  } while (0)
+
+// Stage host columns on the device (stream-ordered).  Host memory may be
+// pageable; pinned memory makes the copy asynchronous.
+static int32_t stage_columns(Ctx* ctx, const u64* const* cols, int ncols, const i64* w, u64 n, int on_device, BufP* hold,
+                             Cols* dc, const i64** dw) {
+  for (int l = 0; l < MAXL; l++) dc->c[l] = nullptr;
+  *dw = nullptr;
+  if (on_device || n == 0) {
+    for (int l = 0; l < ncols; l++) dc->c[l] = cols[l];
+    *dw = w;
+    return DBSP_OK;
+  }
+  u64 cap = (n + 31) & ~31ull;
+  TRY(dev_alloc(ctx, (size_t)cap * 8 * (ncols + 1), hold));
+  u64* base = (u64*)(*hold)->p;
+  for (int l = 0; l < ncols; l++) {
+    CUDA_TRY(cudaMemcpyAsync(base + (size_t)l * cap, cols[l], n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    dc->c[l] = base + (size_t)l * cap;
+    ctx->h2d_bytes += n * 8;
+  }
+  if (w) {
+    i64* p = (i64*)(base + (size_t)ncols * cap);
+    CUDA_TRY(cudaMemcpyAsync(p, w, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += n * 8;
+    *dw = p;
+  }
+  return DBSP_OK;
+}
+
+// Spine::insert (trace/spine_fueled.rs:605-634).  The reference assigns the
+// batch to level log2(len.next_power_of_two()) and advances in-progress merges
+// with fuel (:730-812).  The schedule of merges is not observable through
+// cursors (cursor/cursor_list.rs), so the device spine keeps the same
+// geometric invariant with whole merges on the stream: while the two newest
+// batches are within 2x of each other they are merged (K3/K4).
+static int32_t spine_truncate_batch(Ctx* ctx, Spine* s, Batch* b, Batch** out);
+static int32_t spine_insert(Ctx* ctx, Spine* s, Batch* b) {
+  if (b->n == 0) return DBSP_OK;
+  Batch* nb = nullptr;
+  if (s->has_bound) {
+    TRY(spine_truncate_batch(ctx, s, b, &nb));
+    if (nb->n == 0) { batch_unref(nb); return DBSP_OK; }
+  } else {
+    batch_ref(b);
+    nb = b;
+  }
+  s->batches.push_back(nb);
+  while (s->batches.size() >= 2) {
+    size_t m = s->batches.size();
+    Batch* x = s->batches[m - 2];
+    Batch* y = s->batches[m - 1];
+    if (x->n >= 2 * y->n) break;
+    Batch* merged = nullptr;
+    TRY(merge_batches(ctx, x, y, &merged));
+    s->batches.pop_back();
+    s->batches.pop_back();
+    batch_unref(x);
+    batch_unref(y);
+    if (merged->n) s->batches.push_back(merged); else batch_unref(merged);
+  }
+  return DBSP_OK;
+}
+
+// truncate_keys_below (spine_fueled.rs:223-233; column_layer/mod.rs:316-319):
+// a zero-copy suffix view of the batch.
+static int32_t spine_truncate_batch(Ctx* ctx, Spine* s, Batch* b, Batch** out) {
+  u64 pos;
+  TRY(batch_lower_bound(ctx, b, s->bound, &pos));
+  if (pos == 0) { batch_ref(b); *out = b; return DBSP_OK; }
+  Batch* v = new Batch();
+  v->s = b->s;
+  v->ctx = ctx;
+  v->n = b->n - pos;
+  for (int l = 0; l < b->nl(); l++) v->col[l] = b->col[l] + pos;
+  v->w = b->w + pos;
+  v->bufs = b->bufs;
+  if (v->n == 0) v->nkeys = 0;
+  *out = v;
+  return DBSP_OK;
+}
+
+extern "C" {
+
+const char* dbsp_last_error(void) { return get_error(); }
+
+int32_t dbsp_ctx_create(int32_t device, dbsp_ctx** out) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0 || device >= count) {
+    set_error(std::string("no usable CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+    return DBSP_ERR_NO_DEVICE;
+  }
+  CUDA_TRY(cudaSetDevice(device));
+  dbsp_ctx* c = new dbsp_ctx();
+  c->device = device;
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaMallocHost(&c->h_scratch, 256 * 8));
+  CUDA_TRY(cudaMalloc(&c->d_scratch, 256 * 8));
+  CUDA_TRY(cudaMemset(c->d_scratch, 0, 256 * 8));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  // keep freed blocks cached in the stream-ordered pool
+  cudaMemPool_t pool;
+  CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t thr = ~0ull;
+  CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  *out = c;
+  return DBSP_OK;
+}
+int32_t dbsp_ctx_destroy(dbsp_ctx* c) {
+  if (!c) return DBSP_OK;
+  cudaStreamSynchronize(c->stream);
+  cudaFreeHost(c->h_scratch);
+  cudaFree(c->d_scratch);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return DBSP_OK;
+}
+int32_t dbsp_ctx_sync(dbsp_ctx* c) {
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return DBSP_OK;
+}
+int32_t dbsp_ctx_stats(dbsp_ctx* c, uint64_t* k, uint64_t* h2d, uint64_t* d2h, int32_t reset) {
+  if (k) *k = c->kernel_launches;
+  if (h2d) *h2d = c->h2d_bytes;
+  if (d2h) *d2h = c->d2h_bytes;
+  if (reset) c->kernel_launches = c->h2d_bytes = c->d2h_bytes = 0;
+  return DBSP_OK;
+}
+void* dbsp_ctx_stream(dbsp_ctx* c) { return (void*)c->stream; }
+
+int32_t dbsp_batch_from_tuples(dbsp_ctx* ctx, const dbsp_schema* s, const uint64_t* const* cols, const int64_t* w,
+                               uint64_t n, int32_t on_device, dbsp_batch** out) {
+  int L = s->n_key_lanes + s->n_val_lanes;
+  CHECK_ARG(L >= 1 && L <= MAXL, "schema must have 1..8 lanes");
+  BufP hold;
+  Cols dc;
+  const i64* dw;
+  TRY(stage_columns(ctx, cols, L, w, n, on_device, &hold, &dc, &dw));
+  Batch* b = nullptr;
+  TRY(consolidate_rows(ctx, *s, dc, dw, n, nullptr, &b));
+  *out = H(b);
+  return DBSP_OK;
+}
+
+int32_t dbsp_batch_from_table(dbsp_ctx* ctx, const uint64_t* const* cols, uint32_t n_cols, const int64_t* w, uint64_t n,
+                              int32_t on_device, const dbsp_proj* proj, dbsp_batch** out) {
+  CHECK_ARG(n_cols >= 1 && n_cols <= MAXL, "table must have 1..8 columns");
+  BufP hold;
+  Cols dc;
+  const i64* dw;
+  TRY(stage_columns(ctx, cols, (int)n_cols, w, n, on_device, &hold, &dc, &dw));
+  Batch* b = nullptr;
+  TRY(project_and_consolidate(ctx, dc, 0, (int)n_cols, dw, n, *proj, &b));
+  *out = H(b);
+  return DBSP_OK;
+}
+
+int32_t dbsp_batch_from_sorted(dbsp_ctx* ctx, const dbsp_schema* s, const uint64_t* const* cols, const int64_t* w,
+                               uint64_t n, int32_t on_device, dbsp_batch** out) {
+  int L = s->n_key_lanes + s->n_val_lanes;
+  if (n == 0) { *out = H(batch_new_empty(ctx, *s)); return DBSP_OK; }
+  Batch* b;
+  MCols oc;
+  i64* ow;
+  TRY(batch_alloc(ctx, *s, n, &b, &oc, &ow));
+  cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  for (int l = 0; l < L; l++) CUDA_TRY(cudaMemcpyAsync(oc.c[l], cols[l], n * 8, kind, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ow, w, n * 8, kind, ctx->stream));
+  if (!on_device) { ctx->h2d_bytes += n * 8 * (L + 1); CUDA_TRY(cudaStreamSynchronize(ctx->stream)); }
+  *out = H(b);
+  return DBSP_OK;
+}
+
+int32_t dbsp_batch_empty(dbsp_ctx* ctx, const dbsp_schema* s, dbsp_batch** out) {
+  *out = H(batch_new_empty(ctx, *s));
+  return DBSP_OK;
+}
+
+int32_t dbsp_batch_merge(dbsp_ctx* ctx, const dbsp_batch* a, const dbsp_batch* b, dbsp_batch** out) {
+  Batch* o = nullptr;
+  TRY(merge_batches(ctx, B(a), B(b), &o));
+  *out = H(o);
+  return DBSP_OK;
+}
+
+int32_t dbsp_batch_neg(dbsp_ctx* ctx, const dbsp_batch* a, dbsp_batch** out) {
+  Batch* o = nullptr;
+  TRY(op_neg(ctx, B(a), &o));
+  *out = H(o);
+  return DBSP_OK;
+}
+
+int32_t dbsp_batch_reindex(dbsp_ctx* ctx, const dbsp_batch* a, uint32_t nk, dbsp_batch** out) {
+  const Batch* x = B(a);
+  CHECK_ARG((int)nk <= x->nl(), "reindex: too many key lanes");
+  Batch* v = new Batch();
+  v->s = x->s;
+  v->s.n_key_lanes = (uint8_t)nk;
+  v->s.n_val_lanes = (uint8_t)(x->nl() - nk);
+  v->ctx = ctx;
+  v->n = x->n;
+  for (int l = 0; l < MAXL; l++) v->col[l] = x->col[l];
+  v->w = x->w;
+  v->bufs = x->bufs;
+  if (v->n == 0) v->nkeys = 0;
+  *out = H(v);
+  return DBSP_OK;
+}
+
+int32_t dbsp_batch_len(const dbsp_batch* b, uint64_t* n) { *n = B(b)->n; return DBSP_OK; }
+int32_t dbsp_batch_key_count(dbsp_ctx* ctx, const dbsp_batch* b, uint64_t* n) {
+  Batch* x = B(b);
+  if (x->s.n_val_lanes == 0) { *n = x->n; return DBSP_OK; }
+  TRY(batch_build_csr(ctx, x));
+  *n = x->nkeys;
+  return DBSP_OK;
+}
+int32_t dbsp_batch_schema(const dbsp_batch* b, dbsp_schema* out) { *out = B(b)->s; return DBSP_OK; }
+
+int32_t dbsp_batch_download_csr(dbsp_ctx* ctx, const dbsp_batch* bb, uint64_t* const* keys, uint64_t* offs,
+                                uint64_t* const* vals, int64_t* diffs) {
+  Batch* b = B(bb);
+  cudaStream_t st = ctx->stream;
+  int nk = b->s.n_key_lanes, nv = b->s.n_val_lanes;
+  if (b->n == 0) { if (offs && nv) offs[0] = 0; return DBSP_OK; }
+  if (nv == 0) {
+    if (keys) for (int l = 0; l < nk; l++) if (keys[l]) { CUDA_TRY(cudaMemcpyAsync(keys[l], b->col[l], b->n * 8, cudaMemcpyDeviceToHost, st)); ctx->d2h_bytes += b->n * 8; }
+  } else {
+    TRY(batch_build_csr(ctx, b));
+    u64 nkeys = b->nkeys;
+    if (offs) { CUDA_TRY(cudaMemcpyAsync(offs, b->keystart->p, (nkeys + 1) * 8, cudaMemcpyDeviceToHost, st)); ctx->d2h_bytes += (nkeys + 1) * 8; }
+    if (keys && nk) {
+      // gather the key lanes at the key starts: download flat, compact on the host side of the ABI
+      std::vector<u64> ks(nkeys + 1);
+      CUDA_TRY(cudaMemcpyAsync(ks.data(), b->keystart->p, (nkeys + 1) * 8, cudaMemcpyDeviceToHost, st));
+      std::vector<u64> flat(b->n);
+      for (int l = 0; l < nk; l++) {
+        if (!keys[l]) continue;
+        CUDA_TRY(cudaMemcpyAsync(flat.data(), b->col[l], b->n * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        ctx->d2h_bytes += b->n * 8;
+        for (u64 k = 0; k < nkeys; k++) keys[l][k] = flat[ks[k]];
+      }
+    }
+    if (vals) for (int l = 0; l < nv; l++) if (vals[l]) { CUDA_TRY(cudaMemcpyAsync(vals[l], b->col[nk + l], b->n * 8, cudaMemcpyDeviceToHost, st)); ctx->d2h_bytes += b->n * 8; }
+  }
+  if (diffs) { CUDA_TRY(cudaMemcpyAsync(diffs, b->w, b->n * 8, cudaMemcpyDeviceToHost, st)); ctx->d2h_bytes += b->n * 8; }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return DBSP_OK;
+}
+
+int32_t dbsp_batch_device_columns(const dbsp_batch* b, const uint64_t** cols, const int64_t** w) {
+  const Batch* x = B(b);
+  for (int l = 0; l < x->nl(); l++) cols[l] = x->col[l];
+  if (w) *w = x->w;
+  return DBSP_OK;
+}
+
+int32_t dbsp_batch_last_key(dbsp_ctx* ctx, const dbsp_batch* b, uint64_t* key, int32_t* valid) {
+  const Batch* x = B(b);
+  *valid = x->n > 0;
+  if (!x->n) return DBSP_OK;
+  for (int l = 0; l < x->s.n_key_lanes; l++) {
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_scratch + l, x->col[l] + (x->n - 1), 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  for (int l = 0; l < x->s.n_key_lanes; l++) key[l] = ctx->h_scratch[l];
+  ctx->d2h_bytes += 8 * x->s.n_key_lanes;
+  return DBSP_OK;
+}
+
+int32_t dbsp_batch_clone(const dbsp_batch* b, dbsp_batch** out) { batch_ref(B(b)); *out = (dbsp_batch*)b; return DBSP_OK; }
+int32_t dbsp_batch_free(dbsp_batch* b) { batch_unref(B(b)); return DBSP_OK; }
+
+int32_t dbsp_spine_new(dbsp_ctx* ctx, const dbsp_schema* s, dbsp_spine** out) {
+  dbsp_spine* sp = new dbsp_spine();
+  sp->s = *s;
+  sp->ctx = ctx;
+  *out = sp;
+  return DBSP_OK;
+}
+int32_t dbsp_spine_insert(dbsp_ctx* ctx, dbsp_spine* s, const dbsp_batch* b) {
+  CHECK_ARG(memcmp(&s->s, &B(b)->s, sizeof(dbsp_schema)) == 0, "spine_insert: schema mismatch");
+  return spine_insert(ctx, s, B(b));
+}
+int32_t dbsp_spine_consolidate(dbsp_ctx* ctx, dbsp_spine* s, dbsp_batch** out) {
+  Batch* acc = batch_new_empty(ctx, s->s);
+  for (Batch* b : s->batches) {
+    Batch* m = nullptr;
+    int32_t rc = merge_batches(ctx, acc, b, &m);
+    batch_unref(acc);
+    if (rc) return rc;
+    acc = m;
+  }
+  *out = H(acc);
+  return DBSP_OK;
+}
+int32_t dbsp_spine_truncate_keys_below(dbsp_ctx* ctx, dbsp_spine* s, const uint64_t* key) {
+  s->has_bound = true;
+  for (int l = 0; l < s->s.n_key_lanes; l++) s->bound[l] = key[l];
+  std::vector<Batch*> keep;
+  for (Batch* b : s->batches) {
+    Batch* v = nullptr;
+    TRY(spine_truncate_batch(ctx, s, b, &v));
+    batch_unref(b);
+    if (v->n) keep.push_back(v); else batch_unref(v);
+  }
+  s->batches.swap(keep);
+  return DBSP_OK;
+}
+int32_t dbsp_spine_len(const dbsp_spine* s, uint64_t* n, uint32_t* nb) {
+  u64 t = 0;
+  for (Batch* b : s->batches) t += b->n;
+  if (n) *n = t;
+  if (nb) *nb = (uint32_t)s->batches.size();
+  return DBSP_OK;
+}
+int32_t dbsp_spine_free(dbsp_spine* s) {
+  if (!s) return DBSP_OK;
+  for (Batch* b : s->batches) batch_unref(b);
+  delete s;
+  return DBSP_OK;
+}
+
+#define OUT1(call)            \
+  Batch* o__ = nullptr;       \
+  TRY(call);                  \
+  *out = H(o__);              \
+  return DBSP_OK;
+
+int32_t dbsp_join_delta_trace(dbsp_ctx* ctx, const dbsp_batch* d, const dbsp_spine* t, const dbsp_proj* p, int32_t dl,
+                              dbsp_batch** out) { OUT1(op_join_delta_trace(ctx, B(d), t, p, dl, &o__)) }
+int32_t dbsp_join_batches(dbsp_ctx* ctx, const dbsp_batch* l, const dbsp_batch* r, const dbsp_proj* p, dbsp_batch** out) {
+  OUT1(op_join_batches(ctx, B(l), B(r), p, &o__)) }
+int32_t dbsp_semijoin(dbsp_ctx* ctx, const dbsp_batch* pairs, const dbsp_batch* keys, dbsp_batch** out) {
+  OUT1(op_semijoin(ctx, B(pairs), B(keys), &o__)) }
+int32_t dbsp_aggregate_delta(dbsp_ctx* ctx, const dbsp_batch* d, const dbsp_spine* in_tr, const dbsp_spine* out_tr,
+                             int32_t kind, dbsp_batch** out) { OUT1(op_aggregate_delta(ctx, B(d), in_tr, out_tr, kind, &o__)) }
+int32_t dbsp_weigh(dbsp_ctx* ctx, const dbsp_batch* b, const dbsp_expr* f, int32_t mode, dbsp_batch** out) {
+  OUT1(op_weigh(ctx, B(b), f, mode, &o__)) }
+int32_t dbsp_distinct_delta(dbsp_ctx* ctx, const dbsp_batch* d, const dbsp_spine* i, dbsp_batch** out) {
+  OUT1(op_distinct_delta(ctx, B(d), i, &o__)) }
+int32_t dbsp_stream_distinct(dbsp_ctx* ctx, const dbsp_batch* b, dbsp_batch** out) { OUT1(op_stream_distinct(ctx, B(b), &o__)) }
+int32_t dbsp_window_delta(dbsp_ctx* ctx, const dbsp_spine* t, const dbsp_batch* d, int32_t has_prev, const uint64_t* s0,
+                          const uint64_t* e0, const uint64_t* s1, const uint64_t* e1, dbsp_batch** out) {
+  OUT1(op_window_delta(ctx, t, B(d), has_prev, s0, e0, s1, e1, &o__)) }
+int32_t dbsp_map_index(dbsp_ctx* ctx, const dbsp_batch* b, const dbsp_proj* p, dbsp_batch** out) {
+  OUT1(op_map_index(ctx, B(b), p, &o__)) }
+int32_t dbsp_shard_partition(dbsp_ctx* ctx, const dbsp_batch* b, uint32_t P, dbsp_batch** outs) {
+  std::vector<Batch*> o(P, nullptr);
+  TRY(op_shard_partition(ctx, B(b), P, o.data()));
+  for (uint32_t p = 0; p < P; p++) outs[p] = H(o[p]);
+  return DBSP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+// common.cuh — shared types of the CUDA Z-set library (sm_100a).
+//
+// Device layout of a batch: column-major, one contiguous u64
+// array per lane + one i64 weight array; rows sorted lexicographically over
+// (key lanes, val lanes), consolidated.  i64 lanes are compared through the
+// order-preserving map x -> x ^ 0x8000000000000000 ("flip").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/dbsp_b200.h"
+
+typedef uint64_t u64;
+typedef int64_t i64;
+typedef uint32_t u32;
+#define MAXL DBSP_MAX_LANES
+
+struct Ctx;
+
+void set_error(const std::string& s);
+#define CUDA_TRY(expr)                                                                    \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      set_error(std::string(#expr) + ": " + cudaGetErrorString(e__) + " @" + __FILE__ + ":" + std::to_string(__LINE__)); \
+      return DBSP_ERR_CUDA;                                                               \
+    }                                                                                     \
+  } while (0)
+#define TRY(expr)                 \
+  do {                            \
+    int32_t rc__ = (expr);        \
+    if (rc__ != DBSP_OK) return rc__; \
+  } while (0)
+
+// Column pointers + per-lane sign flips, passed to kernels by value.
+struct Cols {
+  const u64* c[MAXL];
+};
+struct MCols {
+  u64* c[MAXL];
+};
+struct Flips {
+  u64 f[MAXL];
+};
+
+// Stream-ordered device buffer (cudaMallocAsync on the context's stream).
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  Ctx* ctx = nullptr;
+  ~DevBuf();
+};
+typedef std::shared_ptr<DevBuf> BufP;
+
+struct Batch {
+  dbsp_schema s;
+  u64 n = 0;
+  const u64* col[MAXL] = {nullptr};   // device pointers of the lanes
+  const i64* w = nullptr;
+  std::vector<BufP> bufs;             // storage kept alive (shared between views)
+  // lazily built CSR view: row index of each key's first tuple
+  u64 nkeys = ~0ull;
+  BufP keystart;                      // u64[nkeys+1]
+  std::atomic<int> refs{1};
+  Ctx* ctx = nullptr;
+  int nl() const { return s.n_key_lanes + s.n_val_lanes; }
+  Cols cols() const {
+    Cols c;
+    for (int l = 0; l < MAXL; l++) c.c[l] = col[l];
+    return c;
+  }
+  Flips flips() const {
+    Flips f;
+    for (int l = 0; l < MAXL; l++) f.f[l] = (l < nl() && s.lane_types[l] == DBSP_I64) ? 0x8000000000000000ull : 0ull;
+    return f;
+  }
+};
+
+struct Spine {
+  dbsp_schema s;
+  std::vector<Batch*> batches;   // oldest (largest) first; each holds one ref
+  bool has_bound = false;
+  u64 bound[MAXL];
+  Ctx* ctx = nullptr;
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  // pinned scratch for small D2H readbacks (counts, min/max)
+  u64* h_scratch = nullptr;   // 256 u64
+  u64* d_scratch = nullptr;   // 256 u64
+  u64 kernel_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+  int sm_count = 148;
+};
+
+#define LAUNCH_COUNT(ctx) ((ctx)->kernel_launches++)
+
+// ---- host helpers (ctx.cu) ---------------------------------------------
+int32_t dev_alloc(Ctx* ctx, size_t bytes, BufP* out);
+// Allocate storage for an (L lanes + weights) batch of capacity n rows.
+int32_t batch_alloc(Ctx* ctx, const dbsp_schema& s, u64 n, Batch** out, MCols* cols, i64** w);
+Batch* batch_new_empty(Ctx* ctx, const dbsp_schema& s);
+void batch_unref(Batch* b);
+inline void batch_ref(Batch* b) { b->refs.fetch_add(1); }
+// Copy `count` u64 from device to pinned host scratch and wait.
+int32_t read_back(Ctx* ctx, const void* dsrc, size_t count_u64, u64* hdst);
+int32_t read_back32(Ctx* ctx, const void* dsrc, u32* hdst);
+int32_t exclusive_scan_u32(Ctx* ctx, const u32* in, u32* out, u64 n);   // out[n] = total (n+1 entries)
+int32_t inclusive_scan_i64(Ctx* ctx, const i64* in, i64* out, u64 n);
+
+// ---- consolidate.cu ------------------------------------------------------
+// Sort (lanes, weights) rows, sum equal rows, drop zero weights -> batch.
+// `cols`/`w` are device arrays of n rows; w == nullptr means all +1.
+// minmax (optional, device, 2*L u64: min then max of flipped lanes) lets a
+// producer that already reduced the lane ranges skip that pass.
+int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const i64* w, u64 n, const u64* d_minmax,
+                         Batch** out);
+
+// ---- merge.cu --------------------------------------------------------------
+int32_t merge_batches(Ctx* ctx, const Batch* a, const Batch* b, Batch** out);
+
+// ---- device helpers ----------------------------------------------------------
+#ifdef __CUDACC__
+// lexicographic compare of row i of A against row j of B over lanes [0,nl)
+__device__ __forceinline__ int cmp_rows_g(const Cols& A, u64 i, const Cols& B, u64 j, int nl, const Flips& f) {
+  for (int l = 0; l < nl; l++) {
+    u64 a = A.c[l][i] ^ f.f[l], b = B.c[l][j] ^ f.f[l];
+    if (a != b) return a < b ? -1 : 1;
+  }
+  return 0;
+}
+// compare row i of A against a query tuple q (already flipped)
+__device__ __forceinline__ int cmp_row_q(const Cols& A, u64 i, const u64* q, int nl, const Flips& f) {
+  for (int l = 0; l < nl; l++) {
+    u64 a = A.c[l][i] ^ f.f[l];
+    if (a != q[l]) return a < q[l] ? -1 : 1;
+  }
+  return 0;
+}
+// first row in [lo,hi) whose first nl lanes are >= q  (q flipped)
+__device__ __forceinline__ u64 lower_bound_q(const Cols& A, u64 lo, u64 hi, const u64* q, int nl, const Flips& f) {
+  while (lo < hi) {
+    u64 mid = lo + ((hi - lo) >> 1);
+    if (cmp_row_q(A, mid, q, nl, f) < 0) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+// first row in [lo,hi) whose first nl lanes are > q
+__device__ __forceinline__ u64 upper_bound_q(const Cols& A, u64 lo, u64 hi, const u64* q, int nl, const Flips& f) {
+  while (lo < hi) {
+    u64 mid = lo + ((hi - lo) >> 1);
+    if (cmp_row_q(A, mid, q, nl, f) <= 0) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+#endif

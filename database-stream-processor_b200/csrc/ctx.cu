@@ -1,0 +1,99 @@
+// ctx.cu — context, stream-ordered memory, small host<->device plumbing.
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+
+static thread_local std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+const char* get_error() { return g_err.c_str(); }
+
+DevBuf::~DevBuf() {
+  if (p && ctx) cudaFreeAsync(p, ctx->stream);
+}
+
+int32_t dev_alloc(Ctx* ctx, size_t bytes, BufP* out) {
+  auto b = std::make_shared<DevBuf>();
+  b->ctx = ctx;
+  b->bytes = bytes;
+  if (bytes == 0) bytes = 16;
+  CUDA_TRY(cudaMallocAsync(&b->p, bytes, ctx->stream));
+  *out = b;
+  return DBSP_OK;
+}
+
+int32_t batch_alloc(Ctx* ctx, const dbsp_schema& s, u64 n, Batch** out, MCols* cols, i64** w) {
+  int L = s.n_key_lanes + s.n_val_lanes;
+  u64 cap = (n + 31) & ~31ull;   // keep every lane 256-byte aligned
+  if (cap == 0) cap = 32;
+  BufP buf;
+  TRY(dev_alloc(ctx, (size_t)cap * 8 * (L + 1), &buf));
+  Batch* b = new Batch();
+  b->s = s;
+  b->n = n;
+  b->ctx = ctx;
+  b->bufs.push_back(buf);
+  u64* base = (u64*)buf->p;
+  for (int l = 0; l < L; l++) {
+    b->col[l] = base + (size_t)l * cap;
+    if (cols) cols->c[l] = base + (size_t)l * cap;
+  }
+  b->w = (const i64*)(base + (size_t)L * cap);
+  if (w) *w = (i64*)(base + (size_t)L * cap);
+  *out = b;
+  return DBSP_OK;
+}
+
+Batch* batch_new_empty(Ctx* ctx, const dbsp_schema& s) {
+  Batch* b = new Batch();
+  b->s = s;
+  b->n = 0;
+  b->ctx = ctx;
+  b->nkeys = 0;
+  return b;
+}
+
+void batch_unref(Batch* b) {
+  if (!b) return;
+  if (b->refs.fetch_sub(1) == 1) delete b;
+}
+
+int32_t read_back(Ctx* ctx, const void* dsrc, size_t count_u64, u64* hdst) {
+  if (count_u64 > 256) { set_error("read_back: too large"); return DBSP_ERR_INVALID; }
+  CUDA_TRY(cudaMemcpyAsync(ctx->h_scratch, dsrc, count_u64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < count_u64; i++) hdst[i] = ctx->h_scratch[i];
+  ctx->d2h_bytes += count_u64 * 8;
+  return DBSP_OK;
+}
+
+int32_t read_back32(Ctx* ctx, const void* dsrc, u32* hdst) {
+  CUDA_TRY(cudaMemcpyAsync(ctx->h_scratch, dsrc, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  *hdst = *(u32*)ctx->h_scratch;
+  ctx->d2h_bytes += 4;
+  return DBSP_OK;
+}
+
+// Device-wide prefix sums are plumbing between the hand-written kernels (the
+// hot merge kernel carries its own decoupled look-back instead).
+int32_t exclusive_scan_u32(Ctx* ctx, const u32* in, u32* out, u64 n) {
+  // out has n+1 entries: out[n] = total.  Scan n+1 inputs where in[n] is
+  // ignored by construction: callers allocate in with n+1 entries.
+  size_t tmp_bytes = 0;
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (size_t)(n + 1), ctx->stream));
+  BufP tmp;
+  TRY(dev_alloc(ctx, tmp_bytes, &tmp));
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp->p, tmp_bytes, in, out, (size_t)(n + 1), ctx->stream));
+  LAUNCH_COUNT(ctx);
+  return DBSP_OK;
+}
+
+int32_t inclusive_scan_i64(Ctx* ctx, const i64* in, i64* out, u64 n) {
+  size_t tmp_bytes = 0;
+  CUDA_TRY(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, in, out, (size_t)n, ctx->stream));
+  BufP tmp;
+  TRY(dev_alloc(ctx, tmp_bytes, &tmp));
+  CUDA_TRY(cub::DeviceScan::InclusiveSum(tmp->p, tmp_bytes, in, out, (size_t)n, ctx->stream));
+  LAUNCH_COUNT(ctx);
+  return DBSP_OK;
+}

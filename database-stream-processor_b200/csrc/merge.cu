@@ -1,0 +1,281 @@
+// merge.cu — K3/K4: sorted 2-way merge of consolidated batches.
+//
+// Replaces ColumnLayerBuilder::push_merge
+// (crates/dbsp/src/trace/layers/column_layer/builders.rs:98-169) and the
+// two-level OrderedBuilder::merge_step / push_merge
+// (trace/layers/ordered/mod.rs:344-396, 806-834): merging the flat
+// (key lanes, val lanes) rows lexicographically is the same function as the
+// reference's key-then-value-range merge; equal rows have their weights
+// summed and zero sums are dropped.
+//
+// One pass over HBM: a merge-path partition kernel cuts the merged sequence
+// into tiles; each CTA stages its A and B segments in shared memory
+// (coalesced loads), every thread merge-path-searches its own diagonal and
+// serially merges IPT items, the kept rows are compacted in shared memory and
+// written back coalesced.  Because both inputs are consolidated, an equal pair
+// is always (a, b) adjacent in merged order: the A item absorbs its partner's
+// weight, the B item is skipped — also across thread and tile boundaries (one
+// halo element on each side).  The tile's global output offset comes from a
+// decoupled look-back over per-tile status words (tiles take their index from
+// an atomic ticket, so predecessors are always resident or done).
+#include "common.cuh"
+
+namespace {
+
+constexpr int MERGE_THREADS = 256;
+constexpr u64 ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62, ST_MASK = (1ull << 62) - 1;
+
+template <int L>
+struct MergeCfg {
+  static constexpr int IPT = (L <= 2) ? 8 : (L <= 5 ? 4 : 2);
+  static constexpr int TILE = MERGE_THREADS * IPT;
+  static constexpr size_t SMEM = (size_t)(TILE + 2) * (L + 1) * 8 + (size_t)TILE * 4;
+};
+
+// a-count of the merge path at diagonal d: number of A rows among the first d
+// merged rows (ties: A first).
+template <int L>
+__device__ __forceinline__ u64 diag_search_g(const Cols& A, u64 nA, const Cols& B, u64 nB, const Flips& f, u64 d) {
+  u64 lo = d > nB ? d - nB : 0, hi = d < nA ? d : nA;
+  while (lo < hi) {
+    u64 mid = (lo + hi) >> 1;
+    u64 j = d - 1 - mid;
+    bool le = true;   // A[mid] <= B[j] ?
+#pragma unroll
+    for (int l = 0; l < L; l++) {
+      u64 a = A.c[l][mid] ^ f.f[l], b = B.c[l][j] ^ f.f[l];
+      if (a != b) { le = a < b; break; }
+    }
+    if (le) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <int L>
+__global__ void k_merge_partition(Cols A, u64 nA, Cols B, u64 nB, Flips f, u32 tile, u32 ntiles, u64* part) {
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > ntiles) return;
+  u64 total = nA + nB;
+  u64 d = (u64)t * tile;
+  if (d > total) d = total;
+  part[t] = diag_search_g<L>(A, nA, B, nB, f, d);
+}
+
+template <int L>
+__global__ void __launch_bounds__(MERGE_THREADS)
+k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __restrict__ wB, u64 nB, Flips f,
+              const u64* __restrict__ part, u32 ntiles, u32* ticket, u64* status, MCols O, i64* wO, u64* n_out) {
+  constexpr int IPT = MergeCfg<L>::IPT;
+  constexpr int TILE = MergeCfg<L>::TILE;
+  constexpr int S = TILE + 2;   // stride of one staged lane
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  u64* sl = (u64*)smem_raw;                 // L lanes of S (flipped values)
+  i64* sw = (i64*)(sl + (size_t)L * S);     // S weights; reused as output weights
+  u32* perm = (u32*)(sw + S);               // TILE staged-row indices of kept rows
+  __shared__ u32 s_tile;
+  __shared__ u64 s_base;
+  __shared__ u32 s_warp[MERGE_THREADS / 32];
+
+  const int tid = threadIdx.x;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const u32 t = s_tile;
+  const u64 total = nA + nB;
+  const u64 d0 = (u64)t * TILE;
+  const u64 d1 = (d0 + TILE < total) ? d0 + TILE : total;
+  const u64 a0 = part[t], a1 = part[t + 1];
+  const u64 b0 = d0 - a0, b1 = d1 - a1;
+  const int na = (int)(a1 - a0), nb = (int)(b1 - b0);
+  const bool has_prev = a0 > 0, has_next = b1 < nB;
+
+  // ---- stage: [0] = A[a0-1] halo, [1,1+na) = A, [1+na,1+na+nb) = B, then B[b1] halo
+  for (int x = tid; x < na + 1; x += MERGE_THREADS) {
+    if (x == 0 && !has_prev) continue;
+    u64 g = a0 + x - 1;
+#pragma unroll
+    for (int l = 0; l < L; l++) sl[l * S + x] = A.c[l][g] ^ f.f[l];
+    sw[x] = wA[g];
+  }
+  for (int x = tid; x < nb + 1; x += MERGE_THREADS) {
+    if (x == nb && !has_next) continue;
+    u64 g = b0 + x;
+#pragma unroll
+    for (int l = 0; l < L; l++) sl[l * S + 1 + na + x] = B.c[l][g] ^ f.f[l];
+    sw[1 + na + x] = wB[g];
+  }
+  __syncthreads();
+
+  auto le = [&](int ia, int ib) {   // staged row ia <= staged row ib
+#pragma unroll
+    for (int l = 0; l < L; l++) {
+      u64 a = sl[l * S + ia], b = sl[l * S + ib];
+      if (a != b) return a < b;
+    }
+    return true;
+  };
+  auto eq = [&](int ia, int ib) {
+#pragma unroll
+    for (int l = 0; l < L; l++)
+      if (sl[l * S + ia] != sl[l * S + ib]) return false;
+    return true;
+  };
+
+  // ---- per-thread merge path ------------------------------------------------
+  const int n = na + nb;
+  int dt = tid * IPT;
+  if (dt > n) dt = n;
+  int lo = dt > nb ? dt - nb : 0, hi = dt < na ? dt : na;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (le(1 + mid, 1 + na + (dt - 1 - mid))) lo = mid + 1; else hi = mid;
+  }
+  int ai = lo, bi = dt - lo;
+
+  u32 src[IPT];
+  i64 wv[IPT];
+  u32 keep = 0;
+#pragma unroll
+  for (int k = 0; k < IPT; k++) {
+    src[k] = 0;
+    wv[k] = 0;
+    if (ai + bi < n) {
+      bool take_a = (bi >= nb) || (ai < na && le(1 + ai, 1 + na + bi));
+      if (take_a) {
+        i64 w = sw[1 + ai];
+        bool partner = (bi < nb || has_next) && eq(1 + ai, 1 + na + bi);
+        if (partner) w = (i64)((u64)w + (u64)sw[1 + na + bi]);
+        src[k] = 1 + ai;
+        wv[k] = w;
+        if (w != 0) keep |= 1u << k;
+        ai++;
+      } else {
+        bool absorbed = (ai > 0 || has_prev) && eq(ai, 1 + na + bi);
+        i64 w = sw[1 + na + bi];
+        src[k] = 1 + na + bi;
+        wv[k] = w;
+        if (!absorbed && w != 0) keep |= 1u << k;
+        bi++;
+      }
+    }
+  }
+
+  // ---- block exclusive scan of kept counts ------------------------------------
+  const u32 cnt = __popc(keep);
+  u32 incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    u32 v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((tid & 31) >= o) incl += v;
+  }
+  if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+  __syncthreads();   // also: every thread is done reading sw (weights are in registers)
+  u32 warp_off = 0, tile_total = 0;
+#pragma unroll
+  for (int wi = 0; wi < MERGE_THREADS / 32; wi++) {
+    u32 v = s_warp[wi];
+    if (wi < (tid >> 5)) warp_off += v;
+    tile_total += v;
+  }
+  u32 off = warp_off + incl - cnt;
+
+  // ---- decoupled look-back for the tile's global output offset -------------------
+  if (tid == 0) {
+    volatile u64* vs = status;
+    u64 base = 0;
+    if (t == 0) {
+      vs[0] = ST_PREFIX | (u64)tile_total;
+    } else {
+      vs[t] = ST_AGG | (u64)tile_total;
+      u32 p = t - 1;
+      while (true) {
+        u64 v;
+        do { v = vs[p]; } while ((v >> 62) == 0);
+        base += v & ST_MASK;
+        if ((v >> 62) == 2) break;
+        p--;
+      }
+      vs[t] = ST_PREFIX | (base + tile_total);
+    }
+    s_base = base;
+    if (t == ntiles - 1) *n_out = base + tile_total;
+  }
+
+  // ---- compact kept rows in shared memory -------------------------------------------
+#pragma unroll
+  for (int k = 0; k < IPT; k++) {
+    if (keep & (1u << k)) {
+      perm[off] = src[k];
+      sw[off] = wv[k];
+      off++;
+    }
+  }
+  __syncthreads();
+  const u64 base = s_base;
+  for (u32 o = tid; o < tile_total; o += MERGE_THREADS) {
+    u32 s = perm[o];
+#pragma unroll
+    for (int l = 0; l < L; l++) O.c[l][base + o] = sl[l * S + s] ^ f.f[l];
+    wO[base + o] = sw[o];
+  }
+}
+
+template <int L>
+int32_t merge_launch(Ctx* ctx, const Batch* a, const Batch* b, Batch** out) {
+  typedef MergeCfg<L> Cfg;
+  cudaStream_t st = ctx->stream;
+  u64 total = a->n + b->n;
+  u32 ntiles = (u32)((total + Cfg::TILE - 1) / Cfg::TILE);
+  BufP aux;
+  // part[ntiles+1] u64 | status[ntiles] u64 | n_out u64 | ticket u32
+  size_t aux_u64 = (size_t)(ntiles + 1) + ntiles + 2;
+  TRY(dev_alloc(ctx, aux_u64 * 8, &aux));
+  u64* part = (u64*)aux->p;
+  u64* status = part + (ntiles + 1);
+  u64* n_out = status + ntiles;
+  u32* ticket = (u32*)(n_out + 1);
+  CUDA_TRY(cudaMemsetAsync(status, 0, (size_t)(ntiles + 2) * 8, st));
+  Batch* o;
+  MCols oc;
+  i64* ow;
+  TRY(batch_alloc(ctx, a->s, total, &o, &oc, &ow));
+  Flips f = a->flips();
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(k_merge_tiles<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    attr_set = true;
+  }
+  k_merge_partition<L><<<(ntiles + 1 + 127) / 128, 128, 0, st>>>(a->cols(), a->n, b->cols(), b->n, f, Cfg::TILE, ntiles, part);
+  k_merge_tiles<L><<<ntiles, MERGE_THREADS, Cfg::SMEM, st>>>(a->cols(), a->w, a->n, b->cols(), b->w, b->n, f, part, ntiles,
+                                                           ticket, status, oc, ow, n_out);
+  ctx->kernel_launches += 2;
+  u64 nout;
+  int32_t rc = read_back(ctx, n_out, 1, &nout);
+  if (rc != DBSP_OK) { batch_unref(o); return rc; }
+  o->n = nout;
+  if (nout == 0) { batch_unref(o); o = batch_new_empty(ctx, a->s); }
+  *out = o;
+  return DBSP_OK;
+}
+
+}  // namespace
+
+int32_t merge_batches(Ctx* ctx, const Batch* a, const Batch* b, Batch** out) {
+  if (a->nl() != b->nl() || memcmp(&a->s, &b->s, sizeof(dbsp_schema)) != 0) {
+    set_error("merge: schema mismatch");
+    return DBSP_ERR_INVALID;
+  }
+  if (a->n == 0) { batch_ref((Batch*)b); *out = (Batch*)b; return DBSP_OK; }
+  if (b->n == 0) { batch_ref((Batch*)a); *out = (Batch*)a; return DBSP_OK; }
+  switch (a->nl()) {
+    case 1: return merge_launch<1>(ctx, a, b, out);
+    case 2: return merge_launch<2>(ctx, a, b, out);
+    case 3: return merge_launch<3>(ctx, a, b, out);
+    case 4: return merge_launch<4>(ctx, a, b, out);
+    case 5: return merge_launch<5>(ctx, a, b, out);
+    case 6: return merge_launch<6>(ctx, a, b, out);
+    case 7: return merge_launch<7>(ctx, a, b, out);
+    case 8: return merge_launch<8>(ctx, a, b, out);
+  }
+  set_error("merge: unsupported lane count");
+  return DBSP_ERR_UNSUPPORTED;
+}

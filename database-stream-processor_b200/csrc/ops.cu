@@ -1,0 +1,766 @@
+// ops.cu — operator kernels: projection/filter, delta-vs-trace probes (join,
+// aggregate, distinct), window ranges, shard partition.  Each host entry
+// cites the reference `eval` it replaces (paths under crates/dbsp/src/).
+#include "ops.cuh"
+
+namespace {
+
+constexpr int TB = 256;
+
+// ---------------- declarative row expressions on the device ------------------
+struct Env {
+  const u64* key;
+  const u64* lv;
+  const u64* rv;
+};
+__device__ __forceinline__ u64 src_val(const dbsp_src& s, const Env& e) {
+  switch (s.kind) {
+    case DBSP_SRC_KEY: return e.key[s.idx];
+    case DBSP_SRC_LVAL: return e.lv[s.idx];
+    case DBSP_SRC_RVAL: return e.rv[s.idx];
+    default: return (u64)s.cst;
+  }
+}
+__device__ __forceinline__ u64 expr_val(const dbsp_expr& x, const Env& e) {
+  u64 a = src_val(x.a, e);
+  switch (x.op) {
+    case DBSP_OP_COPY: return a;
+    case DBSP_OP_NEG: return (u64)0 - a;
+    case DBSP_OP_ADD: return a + src_val(x.b, e);
+    case DBSP_OP_SUB: return a - src_val(x.b, e);
+    case DBSP_OP_MUL: return a * src_val(x.b, e);
+    case DBSP_OP_DIV: {
+      i64 d = (i64)src_val(x.b, e);
+      return d == 0 ? 0 : (u64)((i64)a / d);
+    }
+  }
+  return a;
+}
+__device__ __forceinline__ bool pred_ok(const dbsp_pred& p, const Env& e) {
+  u64 a = src_val(p.a, e), b = src_val(p.b, e);
+  if (p.cmp == DBSP_CMP_IN) return a < 64 && ((b >> a) & 1);
+  int c = p.is_signed ? (((i64)a < (i64)b) ? -1 : ((i64)a > (i64)b)) : ((a < b) ? -1 : (a > b));
+  switch (p.cmp) {
+    case DBSP_CMP_EQ: return c == 0;
+    case DBSP_CMP_NE: return c != 0;
+    case DBSP_CMP_LT: return c < 0;
+    case DBSP_CMP_LE: return c <= 0;
+    case DBSP_CMP_GT: return c > 0;
+    case DBSP_CMP_GE: return c >= 0;
+  }
+  return false;
+}
+__device__ __forceinline__ bool project(const dbsp_proj& p, const Env& e, u64* row) {
+  for (int i = 0; i < p.n_pred; i++)
+    if (!pred_ok(p.pred[i], e)) return false;
+  int nl = p.out_schema.n_key_lanes + p.out_schema.n_val_lanes;
+  for (int l = 0; l < nl; l++) row[l] = expr_val(p.out[l], e);
+  return true;
+}
+
+// Unordered compaction: the CTA reserves a contiguous output range with one
+// atomic; order inside the output is irrelevant because a sort follows.
+__device__ __forceinline__ u64 block_reserve(bool have, u64* counter, u32* s_warp, u64* s_base) {
+  unsigned m = __ballot_sync(0xffffffffu, have);
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) s_warp[wid] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 tot = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++) { u32 v = s_warp[i]; s_warp[i] = tot; tot += v; }
+    *s_base = tot ? atomicAdd((unsigned long long*)counter, (unsigned long long)tot) : 0;
+  }
+  __syncthreads();
+  u64 pos = *s_base + s_warp[wid] + __popc(m & ((1u << lane) - 1));
+  __syncthreads();
+  return pos;
+}
+
+// flat_map_index over a raw table (filter_map.rs:700-724) / map_index over a
+// batch: evaluate the closure, append surviving rows unordered.
+__global__ void k_project_rows(Cols in, int nk_in, int n_in_lanes, const i64* w, u64 n, dbsp_proj proj, MCols out,
+                               i64* out_w, u64* counter) {
+  __shared__ u32 s_warp[TB / 32];
+  __shared__ u64 s_base;
+  u64 base = (u64)blockIdx.x * blockDim.x * 4;
+  for (int it = 0; it < 4; it++) {
+    u64 i = base + (u64)it * blockDim.x + threadIdx.x;
+    u64 lanes[MAXL], row[MAXL];
+    bool ok = false;
+    if (i < n) {
+      for (int l = 0; l < n_in_lanes; l++) lanes[l] = in.c[l][i];
+      Env e{lanes, lanes + nk_in, lanes + nk_in};
+      ok = project(proj, e, row);
+    }
+    u64 pos = block_reserve(ok, counter, s_warp, &s_base);
+    if (ok) {
+      int nl = proj.out_schema.n_key_lanes + proj.out_schema.n_val_lanes;
+      for (int l = 0; l < nl; l++) out.c[l][pos] = row[l];
+      out_w[pos] = w ? w[i] : 1;
+    }
+  }
+}
+
+// ---------------- delta x trace probes -----------------------------------------
+// For every delta row: [lo, lo+cnt) = rows of batch T whose first nk lanes
+// equal the delta row's first nk lanes (binary search, the `seek_key` of
+// cursor/mod.rs + advance.rs, once per delta row per trace batch).
+__global__ void k_probe_ranges(Cols D, u64 nd, Cols T, u64 nt, int nk, Flips f, u32* lo_out, u32* cnt_out) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nd) return;
+  if (i == nd) { cnt_out[nd] = 0; return; }
+  u64 q[MAXL];
+  for (int l = 0; l < nk; l++) q[l] = D.c[l][i] ^ f.f[l];
+  u64 lo = lower_bound_q(T, 0, nt, q, nk, f);
+  u64 hi = upper_bound_q(T, lo, nt, q, nk, f);
+  lo_out[i] = (u32)lo;
+  cnt_out[i] = (u32)(hi - lo);
+}
+
+// Expand the matches: output slot o -> (delta row i, trace row lo[i] + j).
+// proj_mode 1: join_func(k, v1, v2) with filter (join.rs:751-787), weight w1*w2;
+// proj_mode 0: copy the trace row (gather of a key group, weight = trace weight).
+__global__ void k_probe_fill(Cols D, const i64* wD, u64 nd, Cols T, const i64* wT, int nk, int nvD, int nvT,
+                             const u32* lo, const u32* exscan, u64 total, int proj_mode, int delta_is_left,
+                             dbsp_proj proj, MCols out, i64* out_w, u64* counter) {
+  __shared__ u32 s_warp[TB / 32];
+  __shared__ u64 s_base;
+  u64 o = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  bool ok = false;
+  u64 row[MAXL];
+  i64 wout = 0;
+  int nl_out = 0;
+  if (o < total) {
+    // largest i with exscan[i] <= o
+    u64 a = 0, b = nd;
+    while (b - a > 1) {
+      u64 mid = (a + b) >> 1;
+      if (exscan[mid] <= o) a = mid; else b = mid;
+    }
+    u64 i = a, t = (u64)lo[i] + (o - exscan[i]);
+    if (proj_mode == 0) {
+      nl_out = nk + nvT;
+      for (int l = 0; l < nl_out; l++) row[l] = T.c[l][t];
+      wout = wT[t];
+      ok = true;
+    } else {
+      u64 key[MAXL], dv[MAXL], tv[MAXL];
+      for (int l = 0; l < nk; l++) key[l] = D.c[l][i];
+      for (int l = 0; l < nvD; l++) dv[l] = D.c[nk + l][i];
+      for (int l = 0; l < nvT; l++) tv[l] = T.c[nk + l][t];
+      Env e = delta_is_left ? Env{key, dv, tv} : Env{key, tv, dv};
+      ok = project(proj, e, row);
+      nl_out = proj.out_schema.n_key_lanes + proj.out_schema.n_val_lanes;
+      wout = (i64)((u64)wD[i] * (u64)wT[t]);
+    }
+  }
+  u64 pos = block_reserve(ok, counter, s_warp, &s_base);
+  if (ok) {
+    for (int l = 0; l < nl_out; l++) out.c[l][pos] = row[l];
+    out_w[pos] = wout;
+  }
+}
+
+// Sum over one trace batch of the weight of the *exact* row (all L lanes).
+__global__ void k_lookup_add(Cols D, u64 nd, Cols T, const i64* wT, u64 nt, int L, Flips f, i64* acc) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nd) return;
+  u64 q[MAXL];
+  for (int l = 0; l < L; l++) q[l] = D.c[l][i] ^ f.f[l];
+  u64 lo = lower_bound_q(T, 0, nt, q, L, f);
+  if (lo < nt && cmp_row_q(T, lo, q, L, f) == 0) acc[i] = (i64)((u64)acc[i] + (u64)wT[lo]);
+}
+
+// DistinctIncrementalTotal::eval decision (distinct.rs:196-254).
+__global__ void k_distinct_decide(const i64* wD, const i64* oldw, u64 n, u32* keep, i64* neww) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  if (i == n) { keep[n] = 0; return; }
+  i64 o = oldw[i], nw = (i64)((u64)o + (u64)wD[i]);
+  u32 k = 0;
+  i64 w = 0;
+  if (o <= 0) { if (nw > 0) { k = 1; w = 1; } }
+  else if (nw <= 0) { k = 1; w = -1; }
+  keep[i] = k;
+  neww[i] = w;
+}
+
+// IndexedZSet::distinct (algebra/zset/mod.rs:14-38).
+__global__ void k_positive(const i64* w, u64 n, u32* keep, i64* neww) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  if (i == n) { keep[n] = 0; return; }
+  keep[i] = w[i] > 0 ? 1u : 0u;
+  neww[i] = 1;
+}
+
+// SemiJoinStream::eval (semijoin.rs:100-142): weight product with the key set.
+__global__ void k_semijoin(Cols P, const i64* wP, u64 np, Cols K, const i64* wK, u64 nkeys, int nk, Flips f, u32* keep,
+                           i64* neww) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > np) return;
+  if (i == np) { keep[np] = 0; return; }
+  u64 q[MAXL];
+  for (int l = 0; l < nk; l++) q[l] = P.c[l][i] ^ f.f[l];
+  u64 lo = lower_bound_q(K, 0, nkeys, q, nk, f);
+  i64 w = 0;
+  if (lo < nkeys && cmp_row_q(K, lo, q, nk, f) == 0) w = (i64)((u64)wP[i] * (u64)wK[lo]);
+  keep[i] = w != 0;
+  neww[i] = w;
+}
+
+// head flag over the first nk lanes (key boundaries of the flat rows).
+__global__ void k_key_heads(Cols C, u64 n, int nk, u32* flags) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  if (i == n) { flags[n] = 0; return; }
+  bool head = i == 0;
+  if (!head)
+    for (int l = 0; l < nk; l++)
+      if (C.c[l][i] != C.c[l][i - 1]) { head = true; break; }
+  flags[i] = head ? 1u : 0u;
+}
+
+// ordered compaction: out[pos[i]] = row i for keep[i] != 0
+__global__ void k_scatter(Cols in, int L, const i64* w, const u32* keep, const u32* pos, u64 n, MCols out, i64* out_w) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !keep[i]) return;
+  u32 o = pos[i];
+  for (int l = 0; l < L; l++) out.c[l][o] = in.c[l][i];
+  if (out_w) out_w[o] = w[i];
+}
+__global__ void k_scatter_index(const u32* keep, const u32* pos, u64 n, u64* out, u64 nout) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && keep[i]) out[pos[i]] = i;
+  if (i == 0) out[nout] = n;
+}
+
+__global__ void k_fill_i64(i64* out, u64 n, i64 v) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = v;
+}
+
+__global__ void k_neg(const i64* w, u64 n, i64* out) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (i64)((u64)0 - (u64)w[i]);
+}
+
+// Aggregator pick over a gathered, consolidated key group batch G (rows of the
+// affected keys, weights summed over the spine's batches, zeros dropped):
+// Max = last row of each key (max.rs:36-55), Min = first (min.rs:38-57),
+// Fold count / sum (fold.rs:76-96), WeightedCount (aggregate/mod.rs:129-156).
+__global__ void k_agg_pick(Cols G, const i64* wG, u64 n, int nk, int nv, int kind, const i64* psum, Flips f, u32* keep,
+                           MCols out, int out_nv) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  if (i == n) { keep[n] = 0; return; }
+  bool first = i == 0, last = i == n - 1;
+  if (!first)
+    for (int l = 0; l < nk; l++)
+      if (G.c[l][i] != G.c[l][i - 1]) { first = true; break; }
+  if (!last)
+    for (int l = 0; l < nk; l++)
+      if (G.c[l][i] != G.c[l][i + 1]) { last = true; break; }
+  u32 k = 0;
+  u64 v[MAXL];
+  if (kind == DBSP_AGG_MAX) {
+    k = last;
+    for (int l = 0; l < nv; l++) v[l] = G.c[nk + l][i];
+  } else if (kind == DBSP_AGG_MIN) {
+    k = first;
+    for (int l = 0; l < nv; l++) v[l] = G.c[nk + l][i];
+  } else if (kind == DBSP_AGG_FOLD_COUNT || kind == DBSP_AGG_FOLD_SUM) {
+    k = last;
+    if (last) {
+      u64 q[MAXL];
+      for (int l = 0; l < nk; l++) q[l] = G.c[l][i] ^ f.f[l];
+      u64 start = lower_bound_q(G, 0, i + 1, q, nk, f);
+      if (kind == DBSP_AGG_FOLD_COUNT) v[0] = i - start + 1;
+      else v[0] = (u64)psum[i] - (start ? (u64)psum[start - 1] : 0ull);
+    }
+  } else if (kind == DBSP_AGG_WCOUNT) {
+    k = 1;
+    v[0] = (u64)wG[i];
+  } else {   // WCOUNT2: rows (K.., which): sum at which == 0, count at which == 1
+    k = first;
+    if (first) {
+      u64 which = G.c[nk][i];
+      bool two = !last;   // a second row of the same key follows
+      v[0] = which == 0 ? (u64)wG[i] : 0;
+      v[1] = which == 1 ? (u64)wG[i] : (two ? (u64)wG[i + 1] : 0);
+    }
+  }
+  keep[i] = k;
+  if (k)
+    for (int l = 0; l < out_nv; l++) out.c[l][i] = v[l];
+}
+
+// weigh (aggregate/mod.rs:297-323): per row f(k,v)*w; AVG mode emits the
+// (sum, count) pair weight as two rows (K,0) / (K,1).
+__global__ void k_weigh(Cols B, const i64* w, u64 n, int nk, int nv, dbsp_expr fx, int mode, MCols out, i64* out_w) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 lanes[MAXL];
+  for (int l = 0; l < nk + nv; l++) lanes[l] = B.c[l][i];
+  Env e{lanes, lanes + nk, lanes + nk};
+  u64 fv = expr_val(fx, e);
+  if (mode == DBSP_WEIGH_AVG) {
+    for (int l = 0; l < nk; l++) { out.c[l][2 * i] = lanes[l]; out.c[l][2 * i + 1] = lanes[l]; }
+    out.c[nk][2 * i] = 0;
+    out.c[nk][2 * i + 1] = 1;
+    out_w[2 * i] = (i64)(fv * (u64)w[i]);
+    out_w[2 * i + 1] = w[i];
+  } else {
+    for (int l = 0; l < nk; l++) out.c[l][i] = lanes[l];
+    out_w[i] = (i64)(fv * (u64)w[i]);
+  }
+}
+
+// lower bounds of several key tuples in one batch (window ranges, truncation)
+__global__ void k_lower_bounds(Cols T, u64 nt, int nk, Flips f, const u64* queries, int nq, u64* out) {
+  int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  u64 q[MAXL];
+  for (int l = 0; l < nk; l++) q[l] = queries[qi * MAXL + l] ^ f.f[l];
+  out[qi] = lower_bound_q(T, 0, nt, q, nk, f);
+}
+
+__global__ void k_copy_range(Cols T, const i64* wT, int L, u64 lo, u64 cnt, int negate, MCols out, i64* out_w, u64 dst) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cnt) return;
+  for (int l = 0; l < L; l++) out.c[l][dst + i] = T.c[l][lo + i];
+  i64 w = wT[lo + i];
+  out_w[dst + i] = negate ? (i64)((u64)0 - (u64)w) : w;
+}
+
+__device__ __forceinline__ u64 mix64(u64 x) {
+  x += 0x9e3779b97f4a7c15ull;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+  return x ^ (x >> 31);
+}
+// shard_batch (communication/shard.rs:165-199): keep[i] = hash(key) % P == p
+__global__ void k_shard_flags(Cols B, u64 n, int nk, u32 P, u32 p, u32* keep) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  if (i == n) { keep[n] = 0; return; }
+  u64 h = 0;
+  for (int l = 0; l < nk; l++) h = mix64(h ^ B.c[l][i]);
+  keep[i] = (u32)(h % P) == p ? 1u : 0u;
+}
+
+inline unsigned blocks(u64 n) { return (unsigned)((n + TB - 1) / TB); }
+
+}  // namespace
+
+// ============================ host side =======================================
+
+// Temporary unsorted row store (L lanes + weights) of capacity cap.
+struct TmpRows {
+  BufP buf;
+  MCols c;
+  i64* w = nullptr;
+  Cols cc() const {
+    Cols r;
+    for (int l = 0; l < MAXL; l++) r.c[l] = c.c[l];
+    return r;
+  }
+};
+static int32_t tmp_alloc(Ctx* ctx, int L, u64 cap, TmpRows* t) {
+  u64 c = (cap + 31) & ~31ull;
+  if (c == 0) c = 32;
+  TRY(dev_alloc(ctx, (size_t)c * 8 * (L + 1), &t->buf));
+  u64* base = (u64*)t->buf->p;
+  for (int l = 0; l < MAXL; l++) t->c.c[l] = l < L ? base + (size_t)l * c : nullptr;
+  t->w = (i64*)(base + (size_t)L * c);
+  return DBSP_OK;
+}
+
+int32_t compact_ordered(Ctx* ctx, const dbsp_schema& s, const Cols& in, const i64* w, const u32* keep, u64 n, Batch** out) {
+  // keep has n+1 entries (keep[n] == 0)
+  int L = s.n_key_lanes + s.n_val_lanes;
+  BufP pbuf;
+  TRY(dev_alloc(ctx, (size_t)(n + 1) * 4, &pbuf));
+  u32* pos = (u32*)pbuf->p;
+  TRY(exclusive_scan_u32(ctx, keep, pos, n));
+  u32 nout;
+  TRY(read_back32(ctx, pos + n, &nout));
+  if (nout == 0) { *out = batch_new_empty(ctx, s); return DBSP_OK; }
+  Batch* b;
+  MCols oc;
+  i64* ow;
+  TRY(batch_alloc(ctx, s, nout, &b, &oc, &ow));
+  k_scatter<<<blocks(n), TB, 0, ctx->stream>>>(in, L, w, keep, pos, n, oc, ow);
+  LAUNCH_COUNT(ctx);
+  *out = b;
+  return DBSP_OK;
+}
+
+// project rows of (in cols) through proj, then consolidate.
+int32_t project_and_consolidate(Ctx* ctx, const Cols& in, int nk_in, int n_in_lanes, const i64* w, u64 n,
+                                const dbsp_proj& proj, Batch** out) {
+  const dbsp_schema& os = proj.out_schema;
+  int Lo = os.n_key_lanes + os.n_val_lanes;
+  if (n == 0) { *out = batch_new_empty(ctx, os); return DBSP_OK; }
+  TmpRows t;
+  TRY(tmp_alloc(ctx, Lo, n, &t));
+  u64* counter = ctx->d_scratch + 8;
+  CUDA_TRY(cudaMemsetAsync(counter, 0, 8, ctx->stream));
+  unsigned g = (unsigned)((n + TB * 4 - 1) / (TB * 4));
+  k_project_rows<<<g, TB, 0, ctx->stream>>>(in, nk_in, n_in_lanes, w, n, proj, t.c, t.w, counter);
+  LAUNCH_COUNT(ctx);
+  u64 m;
+  TRY(read_back(ctx, counter, 1, &m));
+  return consolidate_rows(ctx, os, t.cc(), t.w, m, nullptr, out);
+}
+
+// Probe `delta` against every batch of `trace` and expand the matches.
+// proj == nullptr: gather the matching trace rows unchanged.
+static int32_t probe_spine(Ctx* ctx, const Batch* delta, int nk, const Spine* trace, const dbsp_proj* proj,
+                           int delta_is_left, const dbsp_schema& out_schema, Batch** out) {
+  cudaStream_t st = ctx->stream;
+  u64 nd = delta->n;
+  size_t nb = trace->batches.size();
+  if (nd == 0 || nb == 0) { *out = batch_new_empty(ctx, out_schema); return DBSP_OK; }
+  Flips f = delta->flips();
+  // per batch: lo[nd], cnt[nd+1], exscan[nd+1]
+  BufP pb;
+  size_t per = (size_t)(nd + 1) * 3;
+  TRY(dev_alloc(ctx, per * 4 * nb, &pb));
+  std::vector<u64> totals(nb);
+  u64 grand = 0;
+  for (size_t b = 0; b < nb; b++) {
+    const Batch* T = trace->batches[b];
+    u32* lo = (u32*)pb->p + per * b;
+    u32* cnt = lo + (nd + 1);
+    u32* ex = cnt + (nd + 1);
+    k_probe_ranges<<<blocks(nd + 1), TB, 0, st>>>(delta->cols(), nd, T->cols(), T->n, nk, f, lo, cnt);
+    LAUNCH_COUNT(ctx);
+    TRY(exclusive_scan_u32(ctx, cnt, ex, nd));
+  }
+  for (size_t b = 0; b < nb; b++) {   // one sync for all totals would need a gather; nb is small
+    u32 tot;
+    u32* ex = (u32*)pb->p + per * b + 2 * (nd + 1);
+    TRY(read_back32(ctx, ex + nd, &tot));
+    totals[b] = tot;
+    grand += tot;
+  }
+  if (grand == 0) { *out = batch_new_empty(ctx, out_schema); return DBSP_OK; }
+  int Lo = out_schema.n_key_lanes + out_schema.n_val_lanes;
+  TmpRows t;
+  TRY(tmp_alloc(ctx, Lo, grand, &t));
+  u64* counter = ctx->d_scratch + 8;
+  CUDA_TRY(cudaMemsetAsync(counter, 0, 8, st));
+  dbsp_proj pj;
+  if (proj) pj = *proj; else memset(&pj, 0, sizeof(pj));
+  for (size_t b = 0; b < nb; b++) {
+    if (!totals[b]) continue;
+    const Batch* T = trace->batches[b];
+    u32* lo = (u32*)pb->p + per * b;
+    u32* ex = lo + 2 * (nd + 1);
+    k_probe_fill<<<blocks(totals[b]), TB, 0, st>>>(delta->cols(), delta->w, nd, T->cols(), T->w, nk,
+                                                   delta->nl() - nk, T->nl() - nk, lo, ex, totals[b], proj ? 1 : 0,
+                                                   delta_is_left, pj, t.c, t.w, counter);
+    LAUNCH_COUNT(ctx);
+  }
+  u64 m;
+  TRY(read_back(ctx, counter, 1, &m));
+  return consolidate_rows(ctx, out_schema, t.cc(), t.w, m, nullptr, out);
+}
+
+// JoinTrace::eval (operator/join.rs:732-863)
+int32_t op_join_delta_trace(Ctx* ctx, const Batch* delta, const Spine* trace, const dbsp_proj* proj, int delta_is_left,
+                            Batch** out) {
+  if (delta->s.n_key_lanes != trace->s.n_key_lanes) { set_error("join: key lanes differ"); return DBSP_ERR_INVALID; }
+  return probe_spine(ctx, delta, delta->s.n_key_lanes, trace, proj, delta_is_left, proj->out_schema, out);
+}
+
+// Join::eval (operator/join.rs:436-473)
+int32_t op_join_batches(Ctx* ctx, const Batch* l, const Batch* r, const dbsp_proj* proj, Batch** out) {
+  Spine sp;
+  sp.s = r->s;
+  sp.ctx = ctx;
+  if (r->n) sp.batches.push_back((Batch*)r);
+  return op_join_delta_trace(ctx, l, &sp, proj, 1, out);
+}
+
+// distinct keys (first nk lanes) of a batch as an OrdZSet<K> batch with weight 1
+static int32_t distinct_keys(Ctx* ctx, const Batch* b, int nk, Batch** out) {
+  dbsp_schema ks;
+  memset(&ks, 0, sizeof(ks));
+  ks.n_key_lanes = nk;
+  for (int l = 0; l < nk; l++) ks.lane_types[l] = b->s.lane_types[l];
+  if (b->n == 0) { *out = batch_new_empty(ctx, ks); return DBSP_OK; }
+  BufP fb;
+  TRY(dev_alloc(ctx, (size_t)(b->n + 1) * 4, &fb));
+  u32* flags = (u32*)fb->p;
+  k_key_heads<<<blocks(b->n + 1), TB, 0, ctx->stream>>>(b->cols(), b->n, nk, flags);
+  LAUNCH_COUNT(ctx);
+  return compact_ordered(ctx, ks, b->cols(), b->w, flags, b->n, out);
+}
+
+// AggregateIncremental::eval + Upsert::eval
+// (operator/aggregate/mod.rs:479-547,600-684; operator/upsert.rs:161-208).
+int32_t op_aggregate_delta(Ctx* ctx, const Batch* delta, const Spine* in_tr, const Spine* out_tr, int kind, Batch** out) {
+  cudaStream_t st = ctx->stream;
+  const dbsp_schema& os = out_tr->s;
+  int nk = os.n_key_lanes, nov = os.n_val_lanes;
+  if (delta->n == 0) { *out = batch_new_empty(ctx, os); return DBSP_OK; }
+  // 1. affected keys
+  Batch* keys = nullptr;
+  TRY(distinct_keys(ctx, delta, nk, &keys));
+  // 2. their value groups in the input trace, weights summed over batches
+  Batch* G = nullptr;
+  int32_t rc = probe_spine(ctx, keys, nk, in_tr, nullptr, 1, in_tr->s, &G);
+  if (rc) { batch_unref(keys); return rc; }
+  // 3. aggregate per key -> rows (key, new value) with weight +1
+  Batch* N = nullptr;
+  if (G->n) {
+    int gnk = nk, gnv = G->nl() - nk;
+    if (kind == DBSP_AGG_WCOUNT2) gnv = 0;   // (K.., which) rows: `which` read as lane nk
+    BufP kb, ps;
+    TRY(dev_alloc(ctx, (size_t)(G->n + 1) * 4, &kb));
+    u32* keep = (u32*)kb->p;
+    const i64* psum = nullptr;
+    if (kind == DBSP_AGG_FOLD_SUM) {
+      TRY(dev_alloc(ctx, (size_t)G->n * 8, &ps));
+      TRY(inclusive_scan_i64(ctx, (const i64*)G->col[nk], (i64*)ps->p, G->n));
+      psum = (const i64*)ps->p;
+    }
+    TmpRows nv;
+    TRY(tmp_alloc(ctx, nov, G->n, &nv));
+    k_agg_pick<<<blocks(G->n + 1), TB, 0, st>>>(G->cols(), G->w, G->n, gnk, gnv, kind, psum, G->flips(), keep, nv.c, nov);
+    LAUNCH_COUNT(ctx);
+    // rows (key lanes of G, new value lanes), weight +1 (reuse delta-free ones array: build below)
+    Cols src;
+    for (int l = 0; l < MAXL; l++) src.c[l] = nullptr;
+    for (int l = 0; l < nk; l++) src.c[l] = G->col[l];
+    for (int l = 0; l < nov; l++) src.c[nk + l] = nv.c.c[l];
+    // weights: all +1
+    BufP ones;
+    TRY(dev_alloc(ctx, (size_t)G->n * 8, &ones));
+    k_fill_i64<<<blocks(G->n), TB, 0, st>>>((i64*)ones->p, G->n, 1);
+    LAUNCH_COUNT(ctx);
+    rc = compact_ordered(ctx, os, src, (const i64*)ones->p, keep, G->n, &N);
+    if (rc) { batch_unref(keys); batch_unref(G); return rc; }
+  } else {
+    N = batch_new_empty(ctx, os);
+  }
+  batch_unref(G);
+  // 4. current values of those keys in the output trace, negated
+  Batch* O = nullptr;
+  rc = probe_spine(ctx, keys, nk, out_tr, nullptr, 1, os, &O);
+  batch_unref(keys);
+  if (rc) { batch_unref(N); return rc; }
+  // 5. consolidate(+new, -old) per key == merge of two consolidated batches
+  Batch* On = nullptr;
+  rc = op_neg(ctx, O, &On);
+  batch_unref(O);
+  if (rc) { batch_unref(N); return rc; }
+  rc = merge_batches(ctx, N, On, out);
+  batch_unref(N);
+  batch_unref(On);
+  return rc;
+}
+
+int32_t op_neg(Ctx* ctx, const Batch* a, Batch** out) {
+  if (a->n == 0) { *out = batch_new_empty(ctx, a->s); return DBSP_OK; }
+  BufP wb;
+  TRY(dev_alloc(ctx, (size_t)a->n * 8, &wb));
+  k_neg<<<blocks(a->n), TB, 0, ctx->stream>>>(a->w, a->n, (i64*)wb->p);
+  LAUNCH_COUNT(ctx);
+  Batch* b = new Batch();
+  b->s = a->s;
+  b->n = a->n;
+  b->ctx = ctx;
+  for (int l = 0; l < MAXL; l++) b->col[l] = a->col[l];
+  b->w = (const i64*)wb->p;
+  b->bufs = a->bufs;   // share the lane storage
+  b->bufs.push_back(wb);
+  *out = b;
+  return DBSP_OK;
+}
+
+// weigh (operator/aggregate/mod.rs:297-323)
+int32_t op_weigh(Ctx* ctx, const Batch* b, const dbsp_expr* f, int mode, Batch** out) {
+  int nk = b->s.n_key_lanes, nv = b->s.n_val_lanes;
+  dbsp_schema os;
+  memset(&os, 0, sizeof(os));
+  os.n_key_lanes = nk + (mode == DBSP_WEIGH_AVG ? 1 : 0);
+  for (int l = 0; l < nk; l++) os.lane_types[l] = b->s.lane_types[l];
+  if (b->n == 0) { *out = batch_new_empty(ctx, os); return DBSP_OK; }
+  u64 m = b->n * (mode == DBSP_WEIGH_AVG ? 2 : 1);
+  TmpRows t;
+  TRY(tmp_alloc(ctx, os.n_key_lanes, m, &t));
+  k_weigh<<<blocks(b->n), TB, 0, ctx->stream>>>(b->cols(), b->w, b->n, nk, nv, *f, mode, t.c, t.w);
+  LAUNCH_COUNT(ctx);
+  return consolidate_rows(ctx, os, t.cc(), t.w, m, nullptr, out);
+}
+
+// DistinctIncrementalTotal::eval (operator/distinct.rs:196-254)
+int32_t op_distinct_delta(Ctx* ctx, const Batch* delta, const Spine* integral, Batch** out) {
+  u64 n = delta->n;
+  if (n == 0) { *out = batch_new_empty(ctx, delta->s); return DBSP_OK; }
+  cudaStream_t st = ctx->stream;
+  BufP ab, kb;
+  TRY(dev_alloc(ctx, (size_t)n * 8 * 2, &ab));
+  TRY(dev_alloc(ctx, (size_t)(n + 1) * 4, &kb));
+  i64* acc = (i64*)ab->p;
+  i64* neww = acc + n;
+  CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)n * 8, st));
+  for (Batch* T : integral->batches) {
+    k_lookup_add<<<blocks(n), TB, 0, st>>>(delta->cols(), n, T->cols(), T->w, T->n, delta->nl(), delta->flips(), acc);
+    LAUNCH_COUNT(ctx);
+  }
+  k_distinct_decide<<<blocks(n + 1), TB, 0, st>>>(delta->w, acc, n, (u32*)kb->p, neww);
+  LAUNCH_COUNT(ctx);
+  return compact_ordered(ctx, delta->s, delta->cols(), neww, (u32*)kb->p, n, out);
+}
+
+// IndexedZSet::distinct (algebra/zset/mod.rs:14-38)
+int32_t op_stream_distinct(Ctx* ctx, const Batch* b, Batch** out) {
+  u64 n = b->n;
+  if (n == 0) { *out = batch_new_empty(ctx, b->s); return DBSP_OK; }
+  BufP ab, kb;
+  TRY(dev_alloc(ctx, (size_t)n * 8, &ab));
+  TRY(dev_alloc(ctx, (size_t)(n + 1) * 4, &kb));
+  k_positive<<<blocks(n + 1), TB, 0, ctx->stream>>>(b->w, n, (u32*)kb->p, (i64*)ab->p);
+  LAUNCH_COUNT(ctx);
+  return compact_ordered(ctx, b->s, b->cols(), (i64*)ab->p, (u32*)kb->p, n, out);
+}
+
+// SemiJoinStream::eval (operator/semijoin.rs:100-142)
+int32_t op_semijoin(Ctx* ctx, const Batch* pairs, const Batch* keys, Batch** out) {
+  u64 n = pairs->n;
+  if (n == 0 || keys->n == 0) { *out = batch_new_empty(ctx, pairs->s); return DBSP_OK; }
+  BufP ab, kb;
+  TRY(dev_alloc(ctx, (size_t)n * 8, &ab));
+  TRY(dev_alloc(ctx, (size_t)(n + 1) * 4, &kb));
+  k_semijoin<<<blocks(n + 1), TB, 0, ctx->stream>>>(pairs->cols(), pairs->w, n, keys->cols(), keys->w, keys->n,
+                                                   pairs->s.n_key_lanes, pairs->flips(), (u32*)kb->p, (i64*)ab->p);
+  LAUNCH_COUNT(ctx);
+  return compact_ordered(ctx, pairs->s, pairs->cols(), (i64*)ab->p, (u32*)kb->p, n, out);
+}
+
+// Window::eval (operator/time_series/window.rs:144-222)
+int32_t op_window_delta(Ctx* ctx, const Spine* trace, const Batch* delta, int has_prev, const u64* s0, const u64* e0,
+                        const u64* s1, const u64* e1, Batch** out) {
+  cudaStream_t st = ctx->stream;
+  const dbsp_schema& s = delta->s;
+  int nk = s.n_key_lanes, L = delta->nl();
+  auto lt = [&](const u64* a, const u64* b) {
+    for (int l = 0; l < nk; l++) {
+      u64 x = a[l], y = b[l];
+      if (s.lane_types[l] == DBSP_I64) { x ^= 1ull << 63; y ^= 1ull << 63; }
+      if (x != y) return x < y;
+    }
+    return false;
+  };
+  struct Range { const Batch* b; u64 lo, hi; int neg; };
+  std::vector<Range> ranges;
+  // queries: s0, s1, e0, e1 lower bounds in every batch (+ delta)
+  u64 hq[4 * MAXL];
+  memset(hq, 0, sizeof(hq));
+  for (int l = 0; l < nk; l++) { hq[0 * MAXL + l] = s0[l]; hq[1 * MAXL + l] = s1[l]; hq[2 * MAXL + l] = e0[l]; hq[3 * MAXL + l] = e1[l]; }
+  BufP qb;
+  TRY(dev_alloc(ctx, sizeof(hq) + 4 * 8, &qb));
+  u64* dq = (u64*)qb->p;
+  u64* dres = dq + 4 * MAXL;
+  CUDA_TRY(cudaMemcpyAsync(dq, hq, sizeof(hq), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));   // hq is a stack buffer
+  ctx->h2d_bytes += sizeof(hq);
+  auto bounds = [&](const Batch* b, u64* r) -> int32_t {
+    if (b->n == 0) { r[0] = r[1] = r[2] = r[3] = 0; return DBSP_OK; }
+    k_lower_bounds<<<1, 32, 0, st>>>(b->cols(), b->n, nk, b->flips(), dq, 4, dres);
+    LAUNCH_COUNT(ctx);
+    return read_back(ctx, dres, 4, r);
+  };
+  u64 r[4];
+  if (has_prev) {
+    for (Batch* b : trace->batches) {
+      TRY(bounds(b, r));
+      u64 ps0 = r[0], ps1 = r[1], pe0 = r[2], pe1 = r[3];
+      // region 1: [s0, min(s1, e0))
+      u64 hi1 = std::min(ps1, pe0);
+      if (hi1 > ps0) ranges.push_back({b, ps0, hi1, 1});
+      // shrunk on the right: [e1, e0) when e1 < e0
+      if (lt(e1, e0) && pe0 > pe1) ranges.push_back({b, pe1, pe0, 1});
+      // region 3: [max(e0, s1), e1)
+      u64 from = std::max(pe0, ps1);
+      if (pe1 > from) ranges.push_back({b, from, pe1, 0});
+    }
+  }
+  TRY(bounds(delta, r));
+  if (r[3] > r[1]) ranges.push_back({delta, r[1], r[3], 0});
+  u64 total = 0;
+  for (auto& g : ranges) total += g.hi - g.lo;
+  if (total == 0) { *out = batch_new_empty(ctx, s); return DBSP_OK; }
+  TmpRows t;
+  TRY(tmp_alloc(ctx, L, total, &t));
+  u64 dst = 0;
+  for (auto& g : ranges) {
+    u64 cnt = g.hi - g.lo;
+    k_copy_range<<<blocks(cnt), TB, 0, st>>>(g.b->cols(), g.b->w, L, g.lo, cnt, g.neg, t.c, t.w, dst);
+    LAUNCH_COUNT(ctx);
+    dst += cnt;
+  }
+  return consolidate_rows(ctx, s, t.cc(), t.w, total, nullptr, out);
+}
+
+// Map/FlatMap/Index::eval + from_tuples (operator/filter_map.rs:563-577,700-724)
+int32_t op_map_index(Ctx* ctx, const Batch* b, const dbsp_proj* proj, Batch** out) {
+  return project_and_consolidate(ctx, b->cols(), b->s.n_key_lanes, b->nl(), b->w, b->n, *proj, out);
+}
+
+// shard_batch (operator/communication/shard.rs:165-199)
+int32_t op_shard_partition(Ctx* ctx, const Batch* b, u32 P, Batch** outs) {
+  for (u32 p = 0; p < P; p++) outs[p] = nullptr;
+  if (b->n == 0) {
+    for (u32 p = 0; p < P; p++) outs[p] = batch_new_empty(ctx, b->s);
+    return DBSP_OK;
+  }
+  BufP kb;
+  TRY(dev_alloc(ctx, (size_t)(b->n + 1) * 4, &kb));
+  for (u32 p = 0; p < P; p++) {
+    k_shard_flags<<<blocks(b->n + 1), TB, 0, ctx->stream>>>(b->cols(), b->n, b->s.n_key_lanes, P, p, (u32*)kb->p);
+    LAUNCH_COUNT(ctx);
+    TRY(compact_ordered(ctx, b->s, b->cols(), b->w, (u32*)kb->p, b->n, &outs[p]));
+  }
+  return DBSP_OK;
+}
+
+// CSR view: row index of every key's first tuple (OrderedLayer offs,
+// trace/layers/ordered/mod.rs:32-44), built on demand.
+int32_t batch_build_csr(Ctx* ctx, Batch* b) {
+  if (b->nkeys != ~0ull) return DBSP_OK;
+  if (b->n == 0) { b->nkeys = 0; return DBSP_OK; }
+  int nk = b->s.n_key_lanes;
+  BufP fb, pb;
+  TRY(dev_alloc(ctx, (size_t)(b->n + 1) * 4 * 2, &fb));
+  u32* flags = (u32*)fb->p;
+  u32* pos = flags + (b->n + 1);
+  k_key_heads<<<blocks(b->n + 1), TB, 0, ctx->stream>>>(b->cols(), b->n, nk, flags);
+  LAUNCH_COUNT(ctx);
+  TRY(exclusive_scan_u32(ctx, flags, pos, b->n));
+  u32 nkeys;
+  TRY(read_back32(ctx, pos + b->n, &nkeys));
+  TRY(dev_alloc(ctx, (size_t)(nkeys + 1) * 8, &pb));
+  k_scatter_index<<<blocks(b->n), TB, 0, ctx->stream>>>(flags, pos, b->n, (u64*)pb->p, nkeys);
+  LAUNCH_COUNT(ctx);
+  b->keystart = pb;
+  b->nkeys = nkeys;
+  return DBSP_OK;
+}
+
+// lower bound of one key tuple in a batch (host value)
+int32_t batch_lower_bound(Ctx* ctx, const Batch* b, const u64* key, u64* pos) {
+  if (b->n == 0) { *pos = 0; return DBSP_OK; }
+  u64 hq[MAXL] = {0};
+  for (int l = 0; l < b->s.n_key_lanes; l++) hq[l] = key[l];
+  u64* dq = ctx->d_scratch + 96;
+  CUDA_TRY(cudaMemcpyAsync(dq, hq, sizeof(hq), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  k_lower_bounds<<<1, 32, 0, ctx->stream>>>(b->cols(), b->n, b->s.n_key_lanes, b->flips(), dq, 1, ctx->d_scratch + 120);
+  LAUNCH_COUNT(ctx);
+  return read_back(ctx, ctx->d_scratch + 120, 1, pos);
+}
