@@ -89,7 +89,22 @@ struct Spine {
   Ctx* ctx = nullptr;
 };
 
+// Kernel ids for the optional per-kernel timing (CUDA events on the context's
+// stream; bench.py's roofline figures come from here).
+enum KernelId {
+  KID_MERGE = 0, KID_MERGE_PARTITION, KID_PROBE_RANGES, KID_PROBE_FILL, KID_PROJECT, KID_RADIX_SORT, KID_PACK,
+  KID_HEADS, KID_EMIT, KID_MINMAX, KID_SEG_REDUCE, KID_LOOKUP, KID_COMPACT, KID_SCAN, KID_AGG_PICK, KID_MISC, KID_COUNT
+};
+struct ProfRec {
+  cudaEvent_t a, b;
+  int id;
+  u64 bytes;
+};
+
 struct Ctx {
+  bool prof_on = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
   int device = 0;
   cudaStream_t stream = nullptr;
   // pinned scratch for small D2H readbacks (counts, min/max)
@@ -100,6 +115,16 @@ struct Ctx {
 };
 
 #define LAUNCH_COUNT(ctx) ((ctx)->kernel_launches++)
+
+// RAII timing scope: records events around the kernels launched inside it.
+struct ProfScope {
+  Ctx* c;
+  long idx = -1;
+  ProfScope(Ctx* ctx, int id, u64 bytes);
+  ~ProfScope();
+  void set_bytes(u64 b) { if (idx >= 0) c->prof[idx].bytes = b; }
+};
+const char* kernel_name(int id);
 
 // ---- host helpers (ctx.cu) ---------------------------------------------
 int32_t dev_alloc(Ctx* ctx, size_t bytes, BufP* out);

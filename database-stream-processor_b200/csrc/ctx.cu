@@ -7,6 +7,28 @@ static thread_local std::string g_err;
 void set_error(const std::string& s) { g_err = s; }
 const char* get_error() { return g_err.c_str(); }
 
+static const char* KNAMES[KID_COUNT] = {
+    "merge_tiles", "merge_partition", "probe_ranges", "probe_fill", "project_rows", "radix_sort", "pack_keys",
+    "heads", "emit", "minmax", "seg_reduce", "lookup", "compact", "scan", "agg_pick", "misc"};
+const char* kernel_name(int id) { return (id >= 0 && id < KID_COUNT) ? KNAMES[id] : "?"; }
+
+ProfScope::ProfScope(Ctx* ctx, int id, u64 bytes) : c(ctx) {
+  if (!ctx->prof_on) return;
+  ProfRec r;
+  r.id = id;
+  r.bytes = bytes;
+  for (cudaEvent_t* e : {&r.a, &r.b}) {
+    if (!ctx->ev_pool.empty()) { *e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
+    else cudaEventCreate(e);
+  }
+  cudaEventRecord(r.a, ctx->stream);
+  idx = (long)ctx->prof.size();
+  ctx->prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (idx >= 0) cudaEventRecord(c->prof[idx].b, c->stream);
+}
+
 DevBuf::~DevBuf() {
   if (p && ctx) cudaFreeAsync(p, ctx->stream);
 }

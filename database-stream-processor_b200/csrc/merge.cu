@@ -18,6 +18,9 @@
 // halo element on each side).  The tile's global output offset comes from a
 // decoupled look-back over per-tile status words (tiles take their index from
 // an atomic ticket, so predecessors are always resident or done).
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -180,25 +183,28 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
 
   // ---- decoupled look-back for the tile's global output offset -------------------
   if (tid == 0) {
-    volatile u64* vs = status;
+    unsigned long long* vs = (unsigned long long*)status;
     u64 base = 0;
     if (t == 0) {
-      vs[0] = ST_PREFIX | (u64)tile_total;
+      atomicExch(&vs[0], ST_PREFIX | (u64)tile_total);
     } else {
-      vs[t] = ST_AGG | (u64)tile_total;
+      atomicExch(&vs[t], ST_AGG | (u64)tile_total);
       u32 p = t - 1;
       while (true) {
         u64 v;
-        do { v = vs[p]; } while ((v >> 62) == 0);
+        do { v = atomicAdd(&vs[p], 0ull); } while ((v >> 62) == 0);
         base += v & ST_MASK;
         if ((v >> 62) == 2) break;
         p--;
       }
-      vs[t] = ST_PREFIX | (base + tile_total);
+      atomicExch(&vs[t], ST_PREFIX | (base + tile_total));
     }
     s_base = base;
     if (t == ntiles - 1) *n_out = base + tile_total;
   }
+  // Lane 0 may still be spinning above while lanes 1..31 run ahead: reconverge
+  // the warp before anything that ends in the (aligned) block barrier below.
+  __syncwarp();
 
   // ---- compact kept rows in shared memory -------------------------------------------
 #pragma unroll

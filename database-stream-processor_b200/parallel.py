@@ -1,0 +1,99 @@
+"""Multi-GPU plumbing: one process per GPU, `torch.distributed` (NCCL over
+NVLink on the B200 box, gloo in the CPU tests).
+
+Mirrors the reference's only distribution scheme: N
+identical circuit replicas, inputs re-partitioned by key hash in front of
+every keyed operator (operator/communication/shard.rs:36-162), one exchange
+round per sharded stream per step (exchange.rs:36-44), gather for
+verification (gather.rs:41-103), watermark all-reduce (watermark.rs:53-70).
+The traces never move: only delta batches cross NVLink.
+
+Wire format of one exchange: every rank sends to peer p one contiguous int64
+segment [lane 0 rows | lane 1 rows | ... | weights] holding the rows of its
+batch whose hash(key) % P == p — already sorted, so the receiver only merges
+(shard.rs:136-144).  Segment sizes are data dependent: a P-element count
+all-to-all precedes the payload all-to-all.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .zset import Backend, Batch
+
+
+class Comm:
+    def __init__(self, device: torch.device | None = None, group=None):
+        assert dist.is_initialized(), "torch.distributed must be initialised (torchrun)"
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world_size = dist.get_world_size(group)
+        self.device = device or torch.device("cpu")
+        self.bytes_sent = 0   # payload bytes that left this rank (for the NVLink roofline)
+
+    # -- scalars -----------------------------------------------------------
+    def allreduce_max(self, x: int) -> int:
+        t = torch.tensor([int(x)], dtype=torch.int64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return int(t.item())
+
+    def allreduce_sum(self, x: float) -> float:
+        t = torch.tensor([float(x)], dtype=torch.float64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return float(t.item())
+
+    def barrier(self):
+        dist.barrier(group=self.group)
+
+    # -- batches -----------------------------------------------------------
+    def _exchange(self, be: Backend, parts: list[Batch]) -> list[Batch]:
+        """All-to-all of one batch per peer; returns the batches received."""
+        P = self.world_size
+        schema = parts[0].schema
+        L1 = schema.nl + 1
+        counts = [len(p) for p in parts]
+        send_counts = torch.tensor(counts, dtype=torch.int64, device=self.device)
+        recv_counts = torch.empty(P, dtype=torch.int64, device=self.device)
+        dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+        rc = recv_counts.tolist()
+        segs = []
+        for p in parts:
+            cols, w = be.batch_flat_tensors(p)
+            segs.extend(cols)
+            segs.append(w)
+        send = torch.cat(segs) if sum(counts) else torch.empty(0, dtype=torch.int64, device=self.device)
+        recv = torch.empty(sum(rc) * L1, dtype=torch.int64, device=self.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=[c * L1 for c in rc],
+                               input_split_sizes=[c * L1 for c in counts], group=self.group)
+        self.bytes_sent += (sum(counts) - counts[self.rank]) * L1 * 8
+        out, off = [], 0
+        for q in range(P):
+            n = rc[q]
+            seg = recv[off: off + n * L1]
+            off += n * L1
+            cols = [seg[l * n: (l + 1) * n] for l in range(schema.nl)]
+            out.append(be.batch_from_flat_tensors(schema, cols, seg[schema.nl * n: L1 * n]))
+        return out
+
+    @staticmethod
+    def _merge_all(be: Backend, batches: list[Batch]) -> Batch:
+        """Receiver side of shard(): insert the P batches into a spine and
+        consolidate (shard.rs:136-144) — here a balanced merge tree."""
+        while len(batches) > 1:
+            nxt = [be.merge(batches[i], batches[i + 1]) for i in range(0, len(batches) - 1, 2)]
+            if len(batches) % 2:
+                nxt.append(batches[-1])
+            batches = nxt
+        return batches[0]
+
+    def shard(self, be: Backend, b: Batch) -> Batch:
+        """shard (communication/shard.rs:106-162)."""
+        parts = be.shard_partition(b, self.world_size)
+        return self._merge_all(be, self._exchange(be, parts))
+
+    def gather(self, be: Backend, b: Batch, root: int = 0) -> Batch:
+        """gather (communication/gather.rs:41-103): everything to `root`,
+        empty batches elsewhere."""
+        empty = be.batch_empty(b.schema)
+        parts = [b if p == root else empty for p in range(self.world_size)]
+        return self._merge_all(be, self._exchange(be, parts))

@@ -16,7 +16,7 @@ from ._capi import CApi, DbspError
 from .zset import Backend, Batch, Schema
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdbsp_b200.so")
+LIB_PATH = os.environ.get("DBSP_B200_LIB") or os.path.join(_HERE, "libdbsp_b200.so")
 
 _lib = None
 
