@@ -65,6 +65,8 @@ _SIGS = {
     "ctx_destroy": [_P],
     "ctx_sync": [_P],
     "ctx_stats": [_P, _U64P, _U64P, _U64P, C.c_int32],
+    "ctx_profile": [_P, C.c_int32],
+    "ctx_profile_read": [_P, C.c_int32, C.c_char_p, _U64P, C.POINTER(C.c_double), _U64P],
     "batch_from_tuples": [_P, C.POINTER(CSchema), _PP, _P, C.c_uint64, C.c_int32, _PP],
     "batch_from_table": [_P, _PP, C.c_uint32, _P, C.c_uint64, C.c_int32, C.POINTER(CProj), _PP],
     "batch_from_sorted": [_P, C.POINTER(CSchema), _PP, _P, C.c_uint64, C.c_int32, _PP],

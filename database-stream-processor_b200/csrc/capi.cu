@@ -148,6 +148,32 @@ int32_t dbsp_ctx_stats(dbsp_ctx* c, uint64_t* k, uint64_t* h2d, uint64_t* d2h, i
 }
 void* dbsp_ctx_stream(dbsp_ctx* c) { return (void*)c->stream; }
 
+int32_t dbsp_ctx_profile(dbsp_ctx* c, int32_t enable) {
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  for (auto& r : c->prof) { c->ev_pool.push_back(r.a); c->ev_pool.push_back(r.b); }
+  c->prof.clear();
+  c->prof_on = enable != 0;
+  return DBSP_OK;
+}
+int32_t dbsp_ctx_profile_read(dbsp_ctx* c, int32_t id, char* name32, uint64_t* launches, double* ms, uint64_t* bytes) {
+  if (id < 0 || id >= KID_COUNT) return DBSP_ERR_INVALID;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  u64 n = 0, b = 0;
+  double t = 0;
+  for (auto& r : c->prof) {
+    if (r.id != id) continue;
+    float e = 0;
+    if (cudaEventElapsedTime(&e, r.a, r.b) == cudaSuccess) t += e;
+    n++;
+    b += r.bytes;
+  }
+  if (name32) { strncpy(name32, kernel_name(id), 31); name32[31] = 0; }
+  if (launches) *launches = n;
+  if (ms) *ms = t;
+  if (bytes) *bytes = b;
+  return DBSP_OK;
+}
+
 int32_t dbsp_batch_from_tuples(dbsp_ctx* ctx, const dbsp_schema* s, const uint64_t* const* cols, const int64_t* w,
                                uint64_t n, int32_t on_device, dbsp_batch** out) {
   int L = s->n_key_lanes + s->n_val_lanes;

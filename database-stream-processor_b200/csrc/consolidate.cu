@@ -180,6 +180,7 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
       u64* dmm = ctx->d_scratch + 64;
       k_init_minmax<<<1, 32, 0, st>>>(dmm, L);
       int g = (int)std::min<u64>((n + TB - 1) / TB, (u64)ctx->sm_count * 8);
+      ProfScope ps(ctx, KID_MINMAX, n * (u64)L * 8);
       k_minmax<<<g, TB, 0, st>>>(cols, f, L, n, dmm);
       ctx->kernel_launches += 2;
       d_minmax = dmm;
@@ -226,18 +227,26 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
   for (int wd = 0; wd < p.W; wd++) {
     // Keys of the previous word are dead: always pack into ka.  The row ids
     // ping-pong between ia and ib.
-    if (wd == 0) {
-      k_pack<<<nblk, TB, 0, st>>>(cols, p, wd, nullptr, n, ka, ia);
-      idx_cur = ia;
-    } else {
-      k_pack<<<nblk, TB, 0, st>>>(cols, p, wd, idx_cur, n, ka, nullptr);
+    {
+      ProfScope ps(ctx, KID_PACK, n * (u64)L * 8 + n * 12);
+      if (wd == 0) {
+        k_pack<<<nblk, TB, 0, st>>>(cols, p, wd, nullptr, n, ka, ia);
+        idx_cur = ia;
+      } else {
+        k_pack<<<nblk, TB, 0, st>>>(cols, p, wd, idx_cur, n, ka, nullptr);
+      }
     }
     LAUNCH_COUNT(ctx);
     key_sorted = ka;
     if (p.wbits[wd] > 0 && n > 1) {
       cub::DoubleBuffer<u64> dk(ka, kb);
       cub::DoubleBuffer<u32> di(idx_cur, idx_cur == ia ? ib : ia);
-      CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp->p, tmp_bytes, dk, di, (int)n, 0, (int)p.wbits[wd], st));
+      {
+        // lower bound: the (key,id) pairs read once and written once; the LSD sort makes
+        // ceil(bits/8) such round trips
+        ProfScope ps(ctx, KID_RADIX_SORT, n * 12 * 2);
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp->p, tmp_bytes, dk, di, (int)n, 0, (int)p.wbits[wd], st));
+      }
       ctx->kernel_launches += (p.wbits[wd] + 7) / 8 + 1;
       idx_cur = di.Current();
       key_sorted = dk.Current();
@@ -247,7 +256,10 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
   // ---- epilogue ------------------------------------------------------------------
   u64* cnt = ctx->d_scratch + 32;
   CUDA_TRY(cudaMemsetAsync(cnt, 0, 16, st));
-  k_heads<<<nblk + 1, TB, 0, st>>>(cols, L, p.W, key_sorted, idx_cur, w, n, nullptr, nullptr, cnt);
+  {
+    ProfScope ps(ctx, KID_HEADS, n * (u64)(12 + (w ? 8 : 0)));
+    k_heads<<<nblk + 1, TB, 0, st>>>(cols, L, p.W, key_sorted, idx_cur, w, n, nullptr, nullptr, cnt);
+  }
   LAUNCH_COUNT(ctx);
   u64 hc[2];
   TRY(read_back(ctx, cnt, 2, hc));
@@ -257,7 +269,10 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
   if (hc[0] == 0 && hc[1] == 0) {
     Batch* b;
     TRY(batch_alloc(ctx, s, n, &b, &oc, &ow));
-    k_emit_unique<<<nblk, TB, 0, st>>>(cols, p, key_sorted, idx_cur, w, n, oc, ow);
+    {
+      ProfScope ps(ctx, KID_EMIT, n * (u64)(12 + (w ? 8 : 0)) + n * (u64)(L + 1) * 8);
+      k_emit_unique<<<nblk, TB, 0, st>>>(cols, p, key_sorted, idx_cur, w, n, oc, ow);
+    }
     LAUNCH_COUNT(ctx);
     *out = b;
     return DBSP_OK;

@@ -30,7 +30,9 @@ constexpr u64 ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62, ST_MASK = (1ull << 62
 
 template <int L>
 struct MergeCfg {
-  static constexpr int IPT = (L <= 2) ? 8 : (L <= 5 ? 4 : 2);
+  // odd items/thread: the per-thread serial merge walks shared memory with a
+  // stride of IPT 64-bit words between lanes of a warp -> bank-conflict free
+  static constexpr int IPT = (L <= 2) ? 7 : (L <= 4 ? 5 : 3);
   static constexpr int TILE = MERGE_THREADS * IPT;
   static constexpr size_t SMEM = (size_t)(TILE + 2) * (L + 1) * 8 + (size_t)TILE * 4;
 };
@@ -134,6 +136,31 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
   }
   int ai = lo, bi = dt - lo;
 
+  // Serial merge with both run heads held in registers: one 3-way compare per
+  // item, only the advanced side is re-read from shared memory.  `prev_eq`
+  // says the previous merged row was an A row equal to the current B head.
+  u64 ka[L], kb[L];
+  i64 wa = 0, wb = 0;
+  auto load_a = [&](int i) {
+#pragma unroll
+    for (int l = 0; l < L; l++) ka[l] = sl[l * S + 1 + i];
+    wa = sw[1 + i];
+  };
+  auto load_b = [&](int j) {
+#pragma unroll
+    for (int l = 0; l < L; l++) kb[l] = sl[l * S + 1 + na + j];
+    wb = sw[1 + na + j];
+  };
+  bool b_readable = (bi < nb) || (bi == nb && has_next);
+  if (ai < na) load_a(ai);
+  if (b_readable) load_b(bi);
+  bool prev_eq = false;
+  if ((ai > 0 || has_prev) && bi < nb) {   // A[ai-1] (index ai; halo at 0) vs B head
+    prev_eq = true;
+#pragma unroll
+    for (int l = 0; l < L; l++) prev_eq = prev_eq && (sl[l * S + ai] == kb[l]);
+  }
+
   u32 src[IPT];
   i64 wv[IPT];
   u32 keep = 0;
@@ -142,22 +169,32 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
     src[k] = 0;
     wv[k] = 0;
     if (ai + bi < n) {
-      bool take_a = (bi >= nb) || (ai < na && le(1 + ai, 1 + na + bi));
+      const bool a_ok = ai < na, b_in = bi < nb;
+      int c = 0;   // cmp3(A head, B head) when both are readable
+      if (a_ok && b_readable) {
+#pragma unroll
+        for (int l = 0; l < L; l++) {
+          if (c == 0 && ka[l] != kb[l]) c = ka[l] < kb[l] ? -1 : 1;
+        }
+      }
+      const bool take_a = !b_in || (a_ok && c <= 0);
       if (take_a) {
-        i64 w = sw[1 + ai];
-        bool partner = (bi < nb || has_next) && eq(1 + ai, 1 + na + bi);
-        if (partner) w = (i64)((u64)w + (u64)sw[1 + na + bi]);
+        const bool partner = b_readable && c == 0;
+        i64 w = partner ? (i64)((u64)wa + (u64)wb) : wa;
         src[k] = 1 + ai;
         wv[k] = w;
         if (w != 0) keep |= 1u << k;
+        prev_eq = partner;
         ai++;
+        if (ai < na) load_a(ai);
       } else {
-        bool absorbed = (ai > 0 || has_prev) && eq(ai, 1 + na + bi);
-        i64 w = sw[1 + na + bi];
         src[k] = 1 + na + bi;
-        wv[k] = w;
-        if (!absorbed && w != 0) keep |= 1u << k;
+        wv[k] = wb;
+        if (!prev_eq && wb != 0) keep |= 1u << k;
+        prev_eq = false;
         bi++;
+        b_readable = (bi < nb) || (bi == nb && has_next);
+        if (b_readable) load_b(bi);
       }
     }
   }
@@ -250,13 +287,21 @@ int32_t merge_launch(Ctx* ctx, const Batch* a, const Batch* b, Batch** out) {
     CUDA_TRY(cudaFuncSetAttribute(k_merge_tiles<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     attr_set = true;
   }
-  k_merge_partition<L><<<(ntiles + 1 + 127) / 128, 128, 0, st>>>(a->cols(), a->n, b->cols(), b->n, f, Cfg::TILE, ntiles, part);
+  {
+    ProfScope ps(ctx, KID_MERGE_PARTITION, (u64)(ntiles + 1) * 8);
+    k_merge_partition<L><<<(ntiles + 1 + 127) / 128, 128, 0, st>>>(a->cols(), a->n, b->cols(), b->n, f, Cfg::TILE, ntiles, part);
+  }
+  ProfScope* ps = new ProfScope(ctx, KID_MERGE, 0);
   k_merge_tiles<L><<<ntiles, MERGE_THREADS, Cfg::SMEM, st>>>(a->cols(), a->w, a->n, b->cols(), b->w, b->n, f, part, ntiles,
                                                            ticket, status, oc, ow, n_out);
+  long ps_idx = ps->idx;
+  delete ps;   // records the end event
   ctx->kernel_launches += 2;
   u64 nout;
   int32_t rc = read_back(ctx, n_out, 1, &nout);
   if (rc != DBSP_OK) { batch_unref(o); return rc; }
+  // algorithmic bytes: every input row read once, every output row written once
+  if (ps_idx >= 0) ctx->prof[ps_idx].bytes = (total + nout) * (u64)(L + 1) * 8;
   o->n = nout;
   if (nout == 0) { batch_unref(o); o = batch_new_empty(ctx, a->s); }
   *out = o;

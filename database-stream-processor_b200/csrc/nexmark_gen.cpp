@@ -151,6 +151,10 @@ void gen_range(u64 seed, u64 first, u64 lo, u64 hi, const Cols& c) {
       u64 len = 1 + r.range(std::max<u64>(horizon * 2, 1));
       if (c.a_expires) c.a_expires[i] = ts + len;
     } else {   // bids.rs:60-115
+      if (!c.b_auction && !c.b_bidder && !c.b_price && !c.b_dt && !c.b_extra) {   // table not requested
+        e += (TOTAL_PROP - 1 - rem);   // skip to the end of this 50-event epoch
+        continue;
+      }
       u64 i = bids_before(e) - b0;
       u64 auction = (r.range(HOT_AUCTION_RATIO) == 0)
                         ? next_base0_auction_id(r, e)

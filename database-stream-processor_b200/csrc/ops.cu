@@ -396,6 +396,20 @@ int32_t compact_ordered(Ctx* ctx, const dbsp_schema& s, const Cols& in, const i6
   return DBSP_OK;
 }
 
+// number of distinct input lanes the closure reads (algorithmic bytes)
+static int used_lanes(const dbsp_proj& p, int n_in_lanes) {
+  unsigned mask = 0;
+  auto use = [&](const dbsp_src& s, int nk) {
+    if (s.kind == DBSP_SRC_KEY) mask |= 1u << s.idx;
+    else if (s.kind == DBSP_SRC_LVAL || s.kind == DBSP_SRC_RVAL) mask |= 1u << (nk + s.idx);
+  };
+  int nl = p.out_schema.n_key_lanes + p.out_schema.n_val_lanes;
+  for (int l = 0; l < nl; l++) { use(p.out[l].a, 0); if (p.out[l].op >= DBSP_OP_ADD) use(p.out[l].b, 0); }
+  for (int i = 0; i < p.n_pred; i++) { use(p.pred[i].a, 0); use(p.pred[i].b, 0); }
+  int c = __builtin_popcount(mask);
+  return c > n_in_lanes ? n_in_lanes : c;
+}
+
 // project rows of (in cols) through proj, then consolidate.
 int32_t project_and_consolidate(Ctx* ctx, const Cols& in, int nk_in, int n_in_lanes, const i64* w, u64 n,
                                 const dbsp_proj& proj, Batch** out) {
@@ -407,10 +421,16 @@ int32_t project_and_consolidate(Ctx* ctx, const Cols& in, int nk_in, int n_in_la
   u64* counter = ctx->d_scratch + 8;
   CUDA_TRY(cudaMemsetAsync(counter, 0, 8, ctx->stream));
   unsigned g = (unsigned)((n + TB * 4 - 1) / (TB * 4));
-  k_project_rows<<<g, TB, 0, ctx->stream>>>(in, nk_in, n_in_lanes, w, n, proj, t.c, t.w, counter);
+  long pidx;
+  {
+    ProfScope ps(ctx, KID_PROJECT, 0);
+    pidx = ps.idx;
+    k_project_rows<<<g, TB, 0, ctx->stream>>>(in, nk_in, n_in_lanes, w, n, proj, t.c, t.w, counter);
+  }
   LAUNCH_COUNT(ctx);
   u64 m;
   TRY(read_back(ctx, counter, 1, &m));
+  if (pidx >= 0) ctx->prof[pidx].bytes = n * (u64)(used_lanes(proj, n_in_lanes) + (w ? 1 : 0)) * 8 + m * (u64)(Lo + 1) * 8;
   return consolidate_rows(ctx, os, t.cc(), t.w, m, nullptr, out);
 }
 
@@ -434,7 +454,11 @@ static int32_t probe_spine(Ctx* ctx, const Batch* delta, int nk, const Spine* tr
     u32* lo = (u32*)pb->p + per * b;
     u32* cnt = lo + (nd + 1);
     u32* ex = cnt + (nd + 1);
-    k_probe_ranges<<<blocks(nd + 1), TB, 0, st>>>(delta->cols(), nd, T->cols(), T->n, nk, f, lo, cnt);
+    {
+      u64 lg = 1; while ((1ull << lg) < T->n + 1) lg++;
+      ProfScope ps(ctx, KID_PROBE_RANGES, nd * ((u64)nk * 8 + 8 + 2 * lg * (u64)std::max(nk, 1) * 8));
+      k_probe_ranges<<<blocks(nd + 1), TB, 0, st>>>(delta->cols(), nd, T->cols(), T->n, nk, f, lo, cnt);
+    }
     LAUNCH_COUNT(ctx);
     TRY(exclusive_scan_u32(ctx, cnt, ex, nd));
   }
@@ -458,9 +482,14 @@ static int32_t probe_spine(Ctx* ctx, const Batch* delta, int nk, const Spine* tr
     const Batch* T = trace->batches[b];
     u32* lo = (u32*)pb->p + per * b;
     u32* ex = lo + 2 * (nd + 1);
-    k_probe_fill<<<blocks(totals[b]), TB, 0, st>>>(delta->cols(), delta->w, nd, T->cols(), T->w, nk,
-                                                   delta->nl() - nk, T->nl() - nk, lo, ex, totals[b], proj ? 1 : 0,
-                                                   delta_is_left, pj, t.c, t.w, counter);
+    {
+      // matched trace rows read once, delta rows read once, output rows written once
+      ProfScope ps(ctx, KID_PROBE_FILL, totals[b] * (u64)(T->nl() - nk + 1) * 8 + nd * (u64)(delta->nl() + 1) * 8 +
+                                            totals[b] * (u64)(Lo + 1) * 8);
+      k_probe_fill<<<blocks(totals[b]), TB, 0, st>>>(delta->cols(), delta->w, nd, T->cols(), T->w, nk,
+                                                     delta->nl() - nk, T->nl() - nk, lo, ex, totals[b], proj ? 1 : 0,
+                                                     delta_is_left, pj, t.c, t.w, counter);
+    }
     LAUNCH_COUNT(ctx);
   }
   u64 m;

@@ -347,6 +347,23 @@ class Backend:
         self.api.call("ctx_stats", self.ctx, C.byref(a), C.byref(b), C.byref(c), int(reset))
         return {"kernel_launches": a.value, "h2d_bytes": b.value, "d2h_bytes": c.value}
 
+    def profile(self, enable=True):
+        self.api.call("ctx_profile", self.ctx, int(enable))
+
+    def profile_read(self):
+        """{kernel name: dict(launches, ms, alg_bytes)} since profile(True)."""
+        out, i = {}, 0
+        while True:
+            name = C.create_string_buffer(32)
+            n, ms, b = C.c_uint64(), C.c_double(), C.c_uint64()
+            rc = self.api._ctx_profile_read(self.ctx, i, name, C.byref(n), C.byref(ms), C.byref(b))
+            if rc != 0:
+                break
+            if n.value:
+                out[name.value.decode()] = {"launches": n.value, "ms": ms.value, "alg_bytes": b.value}
+            i += 1
+        return out
+
     # -- construction ------------------------------------------------------
     def _out(self):
         return C.c_void_p()

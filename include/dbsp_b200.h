@@ -137,6 +137,15 @@ const char* dbsp_last_error(void);
  * since the last reset (bench.py's gpu_launches / e2e byte counts). */
 int32_t dbsp_ctx_stats(dbsp_ctx* ctx, uint64_t* kernel_launches,
                        uint64_t* h2d_bytes, uint64_t* d2h_bytes, int32_t reset);
+/* Optional per-kernel timing (CUDA events on the context's stream around the
+ * library's own kernels).  enable != 0 starts a fresh collection.  _read
+ * returns, for kernel class `kernel_id` (0,1,2,... until DBSP_ERR_INVALID),
+ * its name, launch count, summed device time and algorithmic bytes (the
+ * per-kernel byte formulas of DESIGN.md). */
+int32_t dbsp_ctx_profile(dbsp_ctx* ctx, int32_t enable);
+int32_t dbsp_ctx_profile_read(dbsp_ctx* ctx, int32_t kernel_id, char* name32,
+                              uint64_t* launches, double* ms,
+                              uint64_t* alg_bytes);
 /* CUDA stream the context launches on (cudaStream_t as void*), so a host
  * can order its own work / CUDA events on it. */
 void* dbsp_ctx_stream(dbsp_ctx* ctx);

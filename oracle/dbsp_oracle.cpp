@@ -476,6 +476,8 @@ int32_t orc_ctx_sync(orc_ctx*) { return DBSP_OK; }
 const char* orc_last_error(void) { return g_err.c_str(); }
 int32_t orc_ctx_stats(orc_ctx*, u64* a, u64* b, u64* c, int32_t) { if (a) *a = 0; if (b) *b = 0; if (c) *c = 0; return DBSP_OK; }
 void* orc_ctx_stream(orc_ctx*) { return nullptr; }
+int32_t orc_ctx_profile(orc_ctx*, int32_t) { return DBSP_OK; }
+int32_t orc_ctx_profile_read(orc_ctx*, int32_t, char*, u64*, double*, u64*) { return DBSP_ERR_INVALID; }
 
 int32_t orc_batch_from_tuples(orc_ctx*, const dbsp_schema* s, const u64* const* cols, const i64* w, u64 n,
                               int32_t, orc_batch** out) {
