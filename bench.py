@@ -233,6 +233,9 @@ def run_b200(args, query, rank, world, comm, device, do_e2e=True):
                       "d2h_bytes_per_step": st2["d2h_bytes"] // K, "ms_per_step": ms2 / K}
         del c, handles, out
     be.sync()
+    import gc
+
+    gc.collect()
     be.close()
     return res
 

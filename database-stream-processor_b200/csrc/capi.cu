@@ -131,8 +131,14 @@ int32_t dbsp_ctx_destroy(dbsp_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaFreeHost(c->h_scratch);
   cudaFree(c->d_scratch);
+  for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto& e : c->ev_pool) cudaEventDestroy(e);
+  c->prof.clear();
+  c->ev_pool.clear();
   cudaStreamDestroy(c->stream);
-  delete c;
+  c->stream = nullptr;
+  c->destroyed = true;
+  if (c->live_bufs.load() == 0) delete c;   // else the last DevBuf deletes it
   return DBSP_OK;
 }
 int32_t dbsp_ctx_sync(dbsp_ctx* c) {

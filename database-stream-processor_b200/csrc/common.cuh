@@ -102,6 +102,10 @@ struct ProfRec {
 };
 
 struct Ctx {
+  // lifetime: device buffers may outlive dbsp_ctx_destroy (host handles are
+  // freed by a garbage collector); the struct is deleted with the last buffer.
+  std::atomic<long> live_bufs{0};
+  bool destroyed = false;
   bool prof_on = false;
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_pool;

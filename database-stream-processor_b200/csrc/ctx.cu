@@ -30,12 +30,17 @@ ProfScope::~ProfScope() {
 }
 
 DevBuf::~DevBuf() {
-  if (p && ctx) cudaFreeAsync(p, ctx->stream);
+  if (!ctx) return;
+  if (p) {
+    if (ctx->destroyed) cudaFree(p); else cudaFreeAsync(p, ctx->stream);
+  }
+  if (ctx->live_bufs.fetch_sub(1) == 1 && ctx->destroyed) delete ctx;
 }
 
 int32_t dev_alloc(Ctx* ctx, size_t bytes, BufP* out) {
   auto b = std::make_shared<DevBuf>();
   b->ctx = ctx;
+  ctx->live_bufs.fetch_add(1);
   b->bytes = bytes;
   if (bytes == 0) bytes = 16;
   CUDA_TRY(cudaMallocAsync(&b->p, bytes, ctx->stream));
