@@ -406,6 +406,7 @@ def main():
             r = run_b200(args, q, rank, world, comm, device)
             extras[q] = {"value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "e2e": r.get("e2e"),
                          "gpu_launches": r["gpu_launches"], "roofline": roofline_from_profile(r["profile"]),
+                         "kernel_profile": {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "alg_GB": round(v["alg_bytes"] / 1e9, 4)} for k, v in r["profile"].items()},
                          "events": world * E * (W + K)}
         line["queries"] = extras
         if world == 1:

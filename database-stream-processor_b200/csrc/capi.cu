@@ -4,6 +4,8 @@
 #include "ops.cuh"
 
 const char* get_error();
+void print_host_stats(Ctx* c);
+void pool_release_all(Ctx* ctx);
 
 struct dbsp_ctx : Ctx {};
 struct dbsp_batch : Batch {};
@@ -118,19 +120,16 @@ int32_t dbsp_ctx_create(int32_t device, dbsp_ctx** out) {
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
-  // keep freed blocks cached in the stream-ordered pool
-  cudaMemPool_t pool;
-  CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
-  uint64_t thr = ~0ull;
-  CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
   *out = c;
   return DBSP_OK;
 }
 int32_t dbsp_ctx_destroy(dbsp_ctx* c) {
   if (!c) return DBSP_OK;
+  print_host_stats(c);
   cudaStreamSynchronize(c->stream);
   cudaFreeHost(c->h_scratch);
   cudaFree(c->d_scratch);
+  pool_release_all(c);
   for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto& e : c->ev_pool) cudaEventDestroy(e);
   c->prof.clear();
@@ -189,7 +188,7 @@ int32_t dbsp_batch_from_tuples(dbsp_ctx* ctx, const dbsp_schema* s, const uint64
   const i64* dw;
   TRY(stage_columns(ctx, cols, L, w, n, on_device, &hold, &dc, &dw));
   Batch* b = nullptr;
-  TRY(consolidate_rows(ctx, *s, dc, dw, n, nullptr, &b));
+  TRY(consolidate_rows(ctx, *s, dc, dw, n, (hold && dw) ? &hold : nullptr, &b));
   *out = H(b);
   return DBSP_OK;
 }

@@ -9,6 +9,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -51,7 +52,8 @@ struct Flips {
 // Stream-ordered device buffer (cudaMallocAsync on the context's stream).
 struct DevBuf {
   void* p = nullptr;
-  size_t bytes = 0;
+  size_t bytes = 0;   // requested
+  size_t cls = 0;     // size class actually reserved
   Ctx* ctx = nullptr;
   ~DevBuf();
 };
@@ -115,6 +117,15 @@ struct Ctx {
   u64* h_scratch = nullptr;   // 256 u64
   u64* d_scratch = nullptr;   // 256 u64
   u64 kernel_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+  // Device memory: size-classed cache of cudaMalloc blocks.  Everything runs on
+  // one stream, so a block freed by the host can be handed out again at once:
+  // later work is ordered after the work that last touched it.  (The
+  // stream-ordered cudaMallocAsync pool cost ~25 ms/step in pool growth.)
+  std::map<size_t, std::vector<void*>> free_blocks;
+  size_t pool_reserved = 0, pool_cached = 0;
+  // host-side overhead counters (printed at destroy when DBSP_HOST_STATS is set)
+  double t_alloc_us = 0, t_sync_us = 0;
+  u64 n_alloc = 0, n_sync = 0;
   int sm_count = 148;
 };
 
@@ -146,9 +157,9 @@ int32_t inclusive_scan_i64(Ctx* ctx, const i64* in, i64* out, u64 n);
 // ---- consolidate.cu ------------------------------------------------------
 // Sort (lanes, weights) rows, sum equal rows, drop zero weights -> batch.
 // `cols`/`w` are device arrays of n rows; w == nullptr means all +1.
-// minmax (optional, device, 2*L u64: min then max of flipped lanes) lets a
-// producer that already reduced the lane ranges skip that pass.
-int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const i64* w, u64 n, const u64* d_minmax,
+// `adopt` (optional): the buffer that owns cols/w; when the rows turn out to be
+// canonical already (ordered, duplicate- and zero-free) it becomes the batch.
+int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const i64* w, u64 n, const BufP* adopt,
                          Batch** out);
 
 // ---- merge.cu --------------------------------------------------------------

@@ -1,10 +1,24 @@
 // ctx.cu — context, stream-ordered memory, small host<->device plumbing.
 #include <cub/device/device_scan.cuh>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
+
+static inline double now_us() {
+  return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 static thread_local std::string g_err;
 void set_error(const std::string& s) { g_err = s; }
+void print_host_stats(Ctx* c) {
+  if (getenv("DBSP_HOST_STATS"))
+    fprintf(stderr, "[dbsp host] allocs %llu in %.1f ms; read-back syncs %llu waited %.1f ms; launches %llu\n",
+            (unsigned long long)c->n_alloc, c->t_alloc_us / 1e3, (unsigned long long)c->n_sync, c->t_sync_us / 1e3,
+            (unsigned long long)c->kernel_launches);
+}
 const char* get_error() { return g_err.c_str(); }
 
 static const char* KNAMES[KID_COUNT] = {
@@ -29,10 +43,31 @@ ProfScope::~ProfScope() {
   if (idx >= 0) cudaEventRecord(c->prof[idx].b, c->stream);
 }
 
+// size classes: 8 per doubling above 4 KiB (<= 12.5% slack), 512-byte steps below
+static size_t size_class(size_t b) {
+  if (b <= 4096) return (b + 511) & ~(size_t)511;
+  size_t p = (size_t)1 << (63 - __builtin_clzll((unsigned long long)b));
+  size_t step = p >> 3;
+  return (b + step - 1) / step * step;
+}
+
+void pool_release_all(Ctx* ctx) {
+  for (auto& kv : ctx->free_blocks)
+    for (void* p : kv.second) cudaFree(p);
+  ctx->free_blocks.clear();
+  ctx->pool_reserved -= ctx->pool_cached;
+  ctx->pool_cached = 0;
+}
+
 DevBuf::~DevBuf() {
   if (!ctx) return;
   if (p) {
-    if (ctx->destroyed) cudaFree(p); else cudaFreeAsync(p, ctx->stream);
+    if (ctx->destroyed) {
+      cudaFree(p);
+    } else {
+      ctx->free_blocks[cls].push_back(p);
+      ctx->pool_cached += cls;
+    }
   }
   if (ctx->live_bufs.fetch_sub(1) == 1 && ctx->destroyed) delete ctx;
 }
@@ -43,7 +78,30 @@ int32_t dev_alloc(Ctx* ctx, size_t bytes, BufP* out) {
   ctx->live_bufs.fetch_add(1);
   b->bytes = bytes;
   if (bytes == 0) bytes = 16;
-  CUDA_TRY(cudaMallocAsync(&b->p, bytes, ctx->stream));
+  b->cls = size_class(bytes);
+  double t0 = now_us();
+  auto it = ctx->free_blocks.find(b->cls);
+  if (it != ctx->free_blocks.end() && !it->second.empty()) {
+    b->p = it->second.back();
+    it->second.pop_back();
+    ctx->pool_cached -= b->cls;
+  } else {
+    cudaError_t e = cudaMalloc(&b->p, b->cls);
+    if (e != cudaSuccess) {   // out of memory: drop the cache and retry once
+      cudaGetLastError();
+      cudaStreamSynchronize(ctx->stream);
+      pool_release_all(ctx);
+      e = cudaMalloc(&b->p, b->cls);
+    }
+    if (e != cudaSuccess) {
+      b->p = nullptr;
+      set_error(std::string("cudaMalloc(") + std::to_string(b->cls) + "): " + cudaGetErrorString(e));
+      return DBSP_ERR_CUDA;
+    }
+    ctx->pool_reserved += b->cls;
+  }
+  ctx->t_alloc_us += now_us() - t0;
+  ctx->n_alloc++;
   *out = b;
   return DBSP_OK;
 }
@@ -86,16 +144,22 @@ void batch_unref(Batch* b) {
 
 int32_t read_back(Ctx* ctx, const void* dsrc, size_t count_u64, u64* hdst) {
   if (count_u64 > 256) { set_error("read_back: too large"); return DBSP_ERR_INVALID; }
+  double t0 = now_us();
   CUDA_TRY(cudaMemcpyAsync(ctx->h_scratch, dsrc, count_u64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->t_sync_us += now_us() - t0;
+  ctx->n_sync++;
   for (size_t i = 0; i < count_u64; i++) hdst[i] = ctx->h_scratch[i];
   ctx->d2h_bytes += count_u64 * 8;
   return DBSP_OK;
 }
 
 int32_t read_back32(Ctx* ctx, const void* dsrc, u32* hdst) {
+  double t0 = now_us();
   CUDA_TRY(cudaMemcpyAsync(ctx->h_scratch, dsrc, 4, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->t_sync_us += now_us() - t0;
+  ctx->n_sync++;
   *hdst = *(u32*)ctx->h_scratch;
   ctx->d2h_bytes += 4;
   return DBSP_OK;

@@ -50,41 +50,30 @@ __device__ __forceinline__ bool pred_ok(const dbsp_pred& p, const Env& e) {
   }
   return false;
 }
+// evaluates the output row unconditionally (a filtered row keeps its place in
+// an ordered output with weight 0) and returns whether the predicates hold
 __device__ __forceinline__ bool project(const dbsp_proj& p, const Env& e, u64* row) {
-  for (int i = 0; i < p.n_pred; i++)
-    if (!pred_ok(p.pred[i], e)) return false;
+  bool ok = true;
+  for (int i = 0; i < p.n_pred; i++) ok = ok && pred_ok(p.pred[i], e);
   int nl = p.out_schema.n_key_lanes + p.out_schema.n_val_lanes;
   for (int l = 0; l < nl; l++) row[l] = expr_val(p.out[l], e);
-  return true;
-}
-
-// Unordered compaction: the CTA reserves a contiguous output range with one
-// atomic; order inside the output is irrelevant because a sort follows.
-__device__ __forceinline__ u64 block_reserve(bool have, u64* counter, u32* s_warp, u64* s_base) {
-  unsigned m = __ballot_sync(0xffffffffu, have);
-  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) s_warp[wid] = __popc(m);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    u32 tot = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); i++) { u32 v = s_warp[i]; s_warp[i] = tot; tot += v; }
-    *s_base = tot ? atomicAdd((unsigned long long*)counter, (unsigned long long)tot) : 0;
-  }
-  __syncthreads();
-  u64 pos = *s_base + s_warp[wid] + __popc(m & ((1u << lane) - 1));
-  __syncthreads();
-  return pos;
+  return ok;
 }
 
 // flat_map_index over a raw table (filter_map.rs:700-724) / map_index over a
-// batch: evaluate the closure, append surviving rows unordered.
-__global__ void k_project_rows(Cols in, int nk_in, int n_in_lanes, const i64* w, u64 n, dbsp_proj proj, MCols out,
-                               i64* out_w, u64* counter) {
+// batch.  Order preserving: phase 0 counts the surviving rows per CTA, a scan
+// of the CTA counts gives each CTA its output base, phase 1 re-evaluates the
+// closure and writes the survivors in input order — so inputs that are already
+// ordered on the output key (id-ordered event tables, monotone projections)
+// reach the sort-free path of consolidate_rows.
+constexpr int PROJ_ROWS = TB * 4;
+__global__ void k_project_rows(Cols in, int nk_in, int n_in_lanes, const i64* w, u64 n, dbsp_proj proj, int phase,
+                               u32* blk_cnt, const u32* blk_base, MCols out, i64* out_w) {
   __shared__ u32 s_warp[TB / 32];
-  __shared__ u64 s_base;
-  u64 base = (u64)blockIdx.x * blockDim.x * 4;
+  u64 base = (u64)blockIdx.x * PROJ_ROWS;
+  u32 run = phase ? blk_base[blockIdx.x] : 0;
   for (int it = 0; it < 4; it++) {
-    u64 i = base + (u64)it * blockDim.x + threadIdx.x;
+    u64 i = base + (u64)it * TB + threadIdx.x;
     u64 lanes[MAXL], row[MAXL];
     bool ok = false;
     if (i < n) {
@@ -92,13 +81,22 @@ __global__ void k_project_rows(Cols in, int nk_in, int n_in_lanes, const i64* w,
       Env e{lanes, lanes + nk_in, lanes + nk_in};
       ok = project(proj, e, row);
     }
-    u64 pos = block_reserve(ok, counter, s_warp, &s_base);
-    if (ok) {
+    unsigned m = __ballot_sync(0xffffffffu, ok);
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) s_warp[wid] = __popc(m);
+    __syncthreads();
+    u32 before = 0, tot = 0;
+    for (int k = 0; k < TB / 32; k++) { u32 v = s_warp[k]; if (k < wid) before += v; tot += v; }
+    if (phase && ok) {
+      u64 pos = (u64)run + before + __popc(m & ((1u << lane) - 1));
       int nl = proj.out_schema.n_key_lanes + proj.out_schema.n_val_lanes;
       for (int l = 0; l < nl; l++) out.c[l][pos] = row[l];
       out_w[pos] = w ? w[i] : 1;
     }
+    run += tot;
+    __syncthreads();
   }
+  if (!phase && threadIdx.x == 0) blk_cnt[blockIdx.x] = run;
 }
 
 // ---------------- delta x trace probes -----------------------------------------
@@ -122,9 +120,7 @@ __global__ void k_probe_ranges(Cols D, u64 nd, Cols T, u64 nt, int nk, Flips f, 
 // proj_mode 0: copy the trace row (gather of a key group, weight = trace weight).
 __global__ void k_probe_fill(Cols D, const i64* wD, u64 nd, Cols T, const i64* wT, int nk, int nvD, int nvT,
                              const u32* lo, const u32* exscan, u64 total, int proj_mode, int delta_is_left,
-                             dbsp_proj proj, MCols out, i64* out_w, u64* counter) {
-  __shared__ u32 s_warp[TB / 32];
-  __shared__ u64 s_base;
+                             dbsp_proj proj, MCols out, i64* out_w) {
   u64 o = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   bool ok = false;
   u64 row[MAXL];
@@ -154,10 +150,13 @@ __global__ void k_probe_fill(Cols D, const i64* wD, u64 nd, Cols T, const i64* w
       wout = (i64)((u64)wD[i] * (u64)wT[t]);
     }
   }
-  u64 pos = block_reserve(ok, counter, s_warp, &s_base);
-  if (ok) {
-    for (int l = 0; l < nl_out; l++) out.c[l][pos] = row[l];
-    out_w[pos] = wout;
+  // Ordered output: slot o keeps its place; a row rejected by the join filter
+  // stays as a zero-weight row, which consolidation drops.  For a monotone
+  // join_func the slots are already in output order (delta rows ascending,
+  // trace rows ascending within a key), so no sort is needed afterwards.
+  if (o < total) {
+    for (int l = 0; l < nl_out; l++) out.c[l][o] = row[l];
+    out_w[o] = ok ? wout : 0;
   }
 }
 
@@ -233,6 +232,11 @@ __global__ void k_scatter_index(const u32* keep, const u32* pos, u64 n, u64* out
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && keep[i]) out[pos[i]] = i;
   if (i == 0) out[nout] = n;
+}
+
+__global__ void k_iota_u32(u32* out, u32 n, u32 mul) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i * mul;
 }
 
 __global__ void k_fill_i64(i64* out, u64 n, i64 v) {
@@ -416,22 +420,41 @@ int32_t project_and_consolidate(Ctx* ctx, const Cols& in, int nk_in, int n_in_la
   const dbsp_schema& os = proj.out_schema;
   int Lo = os.n_key_lanes + os.n_val_lanes;
   if (n == 0) { *out = batch_new_empty(ctx, os); return DBSP_OK; }
-  TmpRows t;
-  TRY(tmp_alloc(ctx, Lo, n, &t));
-  u64* counter = ctx->d_scratch + 8;
-  CUDA_TRY(cudaMemsetAsync(counter, 0, 8, ctx->stream));
-  unsigned g = (unsigned)((n + TB * 4 - 1) / (TB * 4));
+  unsigned g = (unsigned)((n + PROJ_ROWS - 1) / PROJ_ROWS);
+  BufP cb;
+  TRY(dev_alloc(ctx, (size_t)(g + 1) * 4 * 2, &cb));
+  u32* blk_cnt = (u32*)cb->p;
+  u32* blk_base = blk_cnt + (g + 1);
+  u64 m = n;
+  MCols none;
+  for (int l = 0; l < MAXL; l++) none.c[l] = nullptr;
   long pidx;
   {
     ProfScope ps(ctx, KID_PROJECT, 0);
     pidx = ps.idx;
-    k_project_rows<<<g, TB, 0, ctx->stream>>>(in, nk_in, n_in_lanes, w, n, proj, t.c, t.w, counter);
+    if (proj.n_pred > 0) {
+      k_project_rows<<<g, TB, 0, ctx->stream>>>(in, nk_in, n_in_lanes, w, n, proj, 0, blk_cnt, nullptr, none, nullptr);
+      LAUNCH_COUNT(ctx);
+      CUDA_TRY(cudaMemsetAsync(blk_cnt + g, 0, 4, ctx->stream));
+      TRY(exclusive_scan_u32(ctx, blk_cnt, blk_base, g));
+      u32 tot;
+      TRY(read_back32(ctx, blk_base + g, &tot));
+      m = tot;
+    } else {
+      k_iota_u32<<<(g + TB - 1) / TB, TB, 0, ctx->stream>>>(blk_base, g, PROJ_ROWS);
+      LAUNCH_COUNT(ctx);
+    }
+    if (m == 0) { *out = batch_new_empty(ctx, os); return DBSP_OK; }
+  }
+  TmpRows t;
+  TRY(tmp_alloc(ctx, Lo, m, &t));
+  {
+    ProfScope ps(ctx, KID_PROJECT, n * (u64)(used_lanes(proj, n_in_lanes) + (w ? 1 : 0)) * 8 + m * (u64)(Lo + 1) * 8);
+    k_project_rows<<<g, TB, 0, ctx->stream>>>(in, nk_in, n_in_lanes, w, n, proj, 1, nullptr, blk_base, t.c, t.w);
   }
   LAUNCH_COUNT(ctx);
-  u64 m;
-  TRY(read_back(ctx, counter, 1, &m));
-  if (pidx >= 0) ctx->prof[pidx].bytes = n * (u64)(used_lanes(proj, n_in_lanes) + (w ? 1 : 0)) * 8 + m * (u64)(Lo + 1) * 8;
-  return consolidate_rows(ctx, os, t.cc(), t.w, m, nullptr, out);
+  if (pidx >= 0) ctx->prof[pidx].bytes = proj.n_pred > 0 ? n * (u64)used_lanes(proj, n_in_lanes) * 8 : 0;
+  return consolidate_rows(ctx, os, t.cc(), t.w, m, &t.buf, out);
 }
 
 // Probe `delta` against every batch of `trace` and expand the matches.
@@ -471,30 +494,40 @@ static int32_t probe_spine(Ctx* ctx, const Batch* delta, int nk, const Spine* tr
   }
   if (grand == 0) { *out = batch_new_empty(ctx, out_schema); return DBSP_OK; }
   int Lo = out_schema.n_key_lanes + out_schema.n_val_lanes;
-  TmpRows t;
-  TRY(tmp_alloc(ctx, Lo, grand, &t));
-  u64* counter = ctx->d_scratch + 8;
-  CUDA_TRY(cudaMemsetAsync(counter, 0, 8, st));
   dbsp_proj pj;
   if (proj) pj = *proj; else memset(&pj, 0, sizeof(pj));
+  // One ordered run per trace batch, consolidated on its own (usually without a
+  // sort), then the runs are merged — the Batcher of join.rs:845-858.
+  Batch* acc = nullptr;
   for (size_t b = 0; b < nb; b++) {
     if (!totals[b]) continue;
     const Batch* T = trace->batches[b];
     u32* lo = (u32*)pb->p + per * b;
     u32* ex = lo + 2 * (nd + 1);
+    TmpRows t;
+    TRY(tmp_alloc(ctx, Lo, totals[b], &t));
     {
       // matched trace rows read once, delta rows read once, output rows written once
       ProfScope ps(ctx, KID_PROBE_FILL, totals[b] * (u64)(T->nl() - nk + 1) * 8 + nd * (u64)(delta->nl() + 1) * 8 +
                                             totals[b] * (u64)(Lo + 1) * 8);
       k_probe_fill<<<blocks(totals[b]), TB, 0, st>>>(delta->cols(), delta->w, nd, T->cols(), T->w, nk,
                                                      delta->nl() - nk, T->nl() - nk, lo, ex, totals[b], proj ? 1 : 0,
-                                                     delta_is_left, pj, t.c, t.w, counter);
+                                                     delta_is_left, pj, t.c, t.w);
     }
     LAUNCH_COUNT(ctx);
+    Batch* run = nullptr;
+    int32_t rc = consolidate_rows(ctx, out_schema, t.cc(), t.w, totals[b], &t.buf, &run);
+    if (rc) { if (acc) batch_unref(acc); return rc; }
+    if (!acc) { acc = run; continue; }
+    Batch* m = nullptr;
+    rc = merge_batches(ctx, acc, run, &m);
+    batch_unref(acc);
+    batch_unref(run);
+    if (rc) return rc;
+    acc = m;
   }
-  u64 m;
-  TRY(read_back(ctx, counter, 1, &m));
-  return consolidate_rows(ctx, out_schema, t.cc(), t.w, m, nullptr, out);
+  *out = acc ? acc : batch_new_empty(ctx, out_schema);
+  return DBSP_OK;
 }
 
 // JoinTrace::eval (operator/join.rs:732-863)
@@ -623,7 +656,7 @@ int32_t op_weigh(Ctx* ctx, const Batch* b, const dbsp_expr* f, int mode, Batch**
   TRY(tmp_alloc(ctx, os.n_key_lanes, m, &t));
   k_weigh<<<blocks(b->n), TB, 0, ctx->stream>>>(b->cols(), b->w, b->n, nk, nv, *f, mode, t.c, t.w);
   LAUNCH_COUNT(ctx);
-  return consolidate_rows(ctx, os, t.cc(), t.w, m, nullptr, out);
+  return consolidate_rows(ctx, os, t.cc(), t.w, m, &t.buf, out);
 }
 
 // DistinctIncrementalTotal::eval (operator/distinct.rs:196-254)
@@ -669,6 +702,28 @@ int32_t op_semijoin(Ctx* ctx, const Batch* pairs, const Batch* keys, Batch** out
                                                    pairs->s.n_key_lanes, pairs->flips(), (u32*)kb->p, (i64*)ab->p);
   LAUNCH_COUNT(ctx);
   return compact_ordered(ctx, pairs->s, pairs->cols(), (i64*)ab->p, (u32*)kb->p, n, out);
+}
+
+// Balanced merge of consolidated batches; consumes one reference of each part.
+static int32_t merge_tree(Ctx* ctx, std::vector<Batch*>& parts, const dbsp_schema& s, Batch** out) {
+  int32_t rc = DBSP_OK;
+  while (parts.size() > 1) {
+    std::vector<Batch*> nxt;
+    size_t i = 0;
+    for (; i + 1 < parts.size(); i += 2) {
+      Batch* m = nullptr;
+      if (rc == DBSP_OK) rc = merge_batches(ctx, parts[i], parts[i + 1], &m);
+      batch_unref(parts[i]);
+      batch_unref(parts[i + 1]);
+      if (m) nxt.push_back(m);
+    }
+    if (i < parts.size()) nxt.push_back(parts[i]);
+    parts.swap(nxt);
+    if (rc != DBSP_OK) { for (Batch* b : parts) batch_unref(b); parts.clear(); return rc; }
+  }
+  *out = parts.empty() ? batch_new_empty(ctx, s) : parts[0];
+  parts.clear();
+  return DBSP_OK;
 }
 
 // Window::eval (operator/time_series/window.rs:144-222)
@@ -721,19 +776,29 @@ int32_t op_window_delta(Ctx* ctx, const Spine* trace, const Batch* delta, int ha
   }
   TRY(bounds(delta, r));
   if (r[3] > r[1]) ranges.push_back({delta, r[1], r[3], 0});
-  u64 total = 0;
-  for (auto& g : ranges) total += g.hi - g.lo;
-  if (total == 0) { *out = batch_new_empty(ctx, s); return DBSP_OK; }
-  TmpRows t;
-  TRY(tmp_alloc(ctx, L, total, &t));
-  u64 dst = 0;
+  // Every range is a slice of a consolidated batch: a zero-copy view (negated
+  // for retractions), and Batch::from_tuples over their union is a merge tree.
+  std::vector<Batch*> parts;
+  int32_t rc = DBSP_OK;
   for (auto& g : ranges) {
-    u64 cnt = g.hi - g.lo;
-    k_copy_range<<<blocks(cnt), TB, 0, st>>>(g.b->cols(), g.b->w, L, g.lo, cnt, g.neg, t.c, t.w, dst);
-    LAUNCH_COUNT(ctx);
-    dst += cnt;
+    Batch* v = new Batch();
+    v->s = s;
+    v->ctx = ctx;
+    v->n = g.hi - g.lo;
+    for (int l = 0; l < L; l++) v->col[l] = g.b->col[l] + g.lo;
+    v->w = g.b->w + g.lo;
+    v->bufs = g.b->bufs;
+    if (g.neg) {
+      Batch* nv = nullptr;
+      rc = op_neg(ctx, v, &nv);
+      batch_unref(v);
+      if (rc) break;
+      v = nv;
+    }
+    parts.push_back(v);
   }
-  return consolidate_rows(ctx, s, t.cc(), t.w, total, nullptr, out);
+  if (rc != DBSP_OK) { for (Batch* b : parts) batch_unref(b); return rc; }
+  return merge_tree(ctx, parts, s, out);
 }
 
 // Map/FlatMap/Index::eval + from_tuples (operator/filter_map.rs:563-577,700-724)
