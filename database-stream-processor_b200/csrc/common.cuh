@@ -123,6 +123,10 @@ struct Ctx {
   // stream-ordered cudaMallocAsync pool cost ~25 ms/step in pool growth.)
   std::map<size_t, std::vector<void*>> free_blocks;
   size_t pool_reserved = 0, pool_cached = 0;
+  // slabs the blocks are carved from (bump pointer; blocks return to free_blocks)
+  std::vector<void*> slabs;
+  char* slab_cur = nullptr;
+  size_t slab_left = 0;
   // host-side overhead counters (printed at destroy when DBSP_HOST_STATS is set)
   double t_alloc_us = 0, t_sync_us = 0;
   u64 n_alloc = 0, n_sync = 0;

@@ -51,23 +51,25 @@ static size_t size_class(size_t b) {
   return (b + step - 1) / step * step;
 }
 
+// Blocks are carved from large slabs with a bump pointer (one cudaMalloc per
+// slab: a cudaMalloc per growing trace batch cost milliseconds each) and
+// recycled through per-class free lists.
+static const size_t SLAB_BYTES = (size_t)1 << 31;   // 2 GiB
+
 void pool_release_all(Ctx* ctx) {
-  for (auto& kv : ctx->free_blocks)
-    for (void* p : kv.second) cudaFree(p);
+  for (void* p : ctx->slabs) cudaFree(p);
+  ctx->slabs.clear();
   ctx->free_blocks.clear();
-  ctx->pool_reserved -= ctx->pool_cached;
-  ctx->pool_cached = 0;
+  ctx->slab_cur = nullptr;
+  ctx->slab_left = 0;
+  ctx->pool_reserved = ctx->pool_cached = 0;
 }
 
 DevBuf::~DevBuf() {
   if (!ctx) return;
-  if (p) {
-    if (ctx->destroyed) {
-      cudaFree(p);
-    } else {
-      ctx->free_blocks[cls].push_back(p);
-      ctx->pool_cached += cls;
-    }
+  if (p && !ctx->destroyed) {   // after ctx_destroy the slabs are already gone
+    ctx->free_blocks[cls].push_back(p);
+    ctx->pool_cached += cls;
   }
   if (ctx->live_bufs.fetch_sub(1) == 1 && ctx->destroyed) delete ctx;
 }
@@ -86,19 +88,30 @@ int32_t dev_alloc(Ctx* ctx, size_t bytes, BufP* out) {
     it->second.pop_back();
     ctx->pool_cached -= b->cls;
   } else {
-    cudaError_t e = cudaMalloc(&b->p, b->cls);
-    if (e != cudaSuccess) {   // out of memory: drop the cache and retry once
-      cudaGetLastError();
-      cudaStreamSynchronize(ctx->stream);
-      pool_release_all(ctx);
-      e = cudaMalloc(&b->p, b->cls);
+    size_t need = (b->cls + 255) & ~(size_t)255;
+    if (need > ctx->slab_left) {
+      size_t slab = need > SLAB_BYTES ? need : SLAB_BYTES;
+      void* p = nullptr;
+      cudaError_t e = cudaMalloc(&p, slab);
+      if (e != cudaSuccess && slab > need) {   // not enough room for a full slab: take just what is needed
+        cudaGetLastError();
+        slab = need;
+        e = cudaMalloc(&p, slab);
+      }
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error(std::string("cudaMalloc(") + std::to_string(slab) + "): " + cudaGetErrorString(e) +
+                  " (pool reserved " + std::to_string(ctx->pool_reserved) + " B, cached " + std::to_string(ctx->pool_cached) + " B)");
+        return DBSP_ERR_CUDA;
+      }
+      ctx->slabs.push_back(p);
+      ctx->slab_cur = (char*)p;
+      ctx->slab_left = slab;
+      ctx->pool_reserved += slab;
     }
-    if (e != cudaSuccess) {
-      b->p = nullptr;
-      set_error(std::string("cudaMalloc(") + std::to_string(b->cls) + "): " + cudaGetErrorString(e));
-      return DBSP_ERR_CUDA;
-    }
-    ctx->pool_reserved += b->cls;
+    b->p = ctx->slab_cur;
+    ctx->slab_cur += need;
+    ctx->slab_left -= need;
   }
   ctx->t_alloc_us += now_us() - t0;
   ctx->n_alloc++;
