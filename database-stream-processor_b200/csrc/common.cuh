@@ -117,16 +117,15 @@ struct Ctx {
   u64* h_scratch = nullptr;   // 256 u64
   u64* d_scratch = nullptr;   // 256 u64
   u64 kernel_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
-  // Device memory: size-classed cache of cudaMalloc blocks.  Everything runs on
-  // one stream, so a block freed by the host can be handed out again at once:
-  // later work is ordered after the work that last touched it.  (The
-  // stream-ordered cudaMallocAsync pool cost ~25 ms/step in pool growth.)
-  std::map<size_t, std::vector<void*>> free_blocks;
-  size_t pool_reserved = 0, pool_cached = 0;
-  // slabs the blocks are carved from (bump pointer; blocks return to free_blocks)
-  std::vector<void*> slabs;
-  char* slab_cur = nullptr;
-  size_t slab_left = 0;
+  // Device memory: best-fit allocator with coalescing over large cudaMalloc
+  // slabs.  Everything runs on one stream, so a block freed by the host can be
+  // handed out again at once: later work is ordered after the work that last
+  // touched it.  (The stream-ordered cudaMallocAsync pool cost ~25 ms/step in
+  // pool growth on q4; a cudaMalloc per slab costs ~10 ms, so slabs are big.)
+  std::map<char*, size_t> free_by_addr;        // free blocks, for coalescing
+  std::multimap<size_t, char*> free_by_size;   // the same blocks, for best fit
+  std::map<char*, size_t> slabs;               // slab start -> bytes
+  size_t pool_reserved = 0, pool_free = 0;
   // host-side overhead counters (printed at destroy when DBSP_HOST_STATS is set)
   double t_alloc_us = 0, t_sync_us = 0;
   u64 n_alloc = 0, n_sync = 0;

@@ -1,7 +1,9 @@
 // ctx.cu — context, stream-ordered memory, small host<->device plumbing.
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
 #include <chrono>
+#include <iterator>
 #include <cstdio>
 #include <cstdlib>
 
@@ -15,8 +17,8 @@ static thread_local std::string g_err;
 void set_error(const std::string& s) { g_err = s; }
 void print_host_stats(Ctx* c) {
   if (getenv("DBSP_HOST_STATS"))
-    fprintf(stderr, "[dbsp host] allocs %llu in %.1f ms; read-back syncs %llu waited %.1f ms; launches %llu\n",
-            (unsigned long long)c->n_alloc, c->t_alloc_us / 1e3, (unsigned long long)c->n_sync, c->t_sync_us / 1e3,
+    fprintf(stderr, "[dbsp host] allocs %llu in %.1f ms (pool %.2f GiB in %zu slabs); read-back syncs %llu waited %.1f ms; launches %llu\n",
+            (unsigned long long)c->n_alloc, c->t_alloc_us / 1e3, c->pool_reserved / 1073741824.0, c->slabs.size(), (unsigned long long)c->n_sync, c->t_sync_us / 1e3,
             (unsigned long long)c->kernel_launches);
 }
 const char* get_error() { return g_err.c_str(); }
@@ -43,33 +45,47 @@ ProfScope::~ProfScope() {
   if (idx >= 0) cudaEventRecord(c->prof[idx].b, c->stream);
 }
 
-// size classes: 8 per doubling above 4 KiB (<= 12.5% slack), 512-byte steps below
-static size_t size_class(size_t b) {
-  if (b <= 4096) return (b + 511) & ~(size_t)511;
-  size_t p = (size_t)1 << (63 - __builtin_clzll((unsigned long long)b));
-  size_t step = p >> 3;
-  return (b + step - 1) / step * step;
-}
-
-// Blocks are carved from large slabs with a bump pointer (one cudaMalloc per
-// slab: a cudaMalloc per growing trace batch cost milliseconds each) and
-// recycled through per-class free lists.
-static const size_t SLAB_BYTES = (size_t)1 << 31;   // 2 GiB
+static const size_t SLAB_BYTES = (size_t)8 << 30;   // 8 GiB per cudaMalloc
+static const size_t ALIGN = 512;
 
 void pool_release_all(Ctx* ctx) {
-  for (void* p : ctx->slabs) cudaFree(p);
+  for (auto& kv : ctx->slabs) cudaFree(kv.first);
   ctx->slabs.clear();
-  ctx->free_blocks.clear();
-  ctx->slab_cur = nullptr;
-  ctx->slab_left = 0;
-  ctx->pool_reserved = ctx->pool_cached = 0;
+  ctx->free_by_addr.clear();
+  ctx->free_by_size.clear();
+  ctx->pool_reserved = ctx->pool_free = 0;
+}
+
+static void pool_insert_free(Ctx* ctx, char* p, size_t sz) {
+  // coalesce with the free neighbours (never across a slab boundary)
+  auto nxt = ctx->free_by_addr.lower_bound(p);
+  if (nxt != ctx->free_by_addr.end() && nxt->first == p + sz && !ctx->slabs.count(nxt->first)) {
+    auto range = ctx->free_by_size.equal_range(nxt->second);
+    for (auto it = range.first; it != range.second; ++it)
+      if (it->second == nxt->first) { ctx->free_by_size.erase(it); break; }
+    sz += nxt->second;
+    nxt = ctx->free_by_addr.erase(nxt);
+  }
+  if (nxt != ctx->free_by_addr.begin() && !ctx->slabs.count(p)) {
+    auto prv = std::prev(nxt);
+    if (prv->first + prv->second == p) {
+      auto range = ctx->free_by_size.equal_range(prv->second);
+      for (auto it = range.first; it != range.second; ++it)
+        if (it->second == prv->first) { ctx->free_by_size.erase(it); break; }
+      p = prv->first;
+      sz += prv->second;
+      ctx->free_by_addr.erase(prv);
+    }
+  }
+  ctx->free_by_addr[p] = sz;
+  ctx->free_by_size.insert({sz, p});
 }
 
 DevBuf::~DevBuf() {
   if (!ctx) return;
   if (p && !ctx->destroyed) {   // after ctx_destroy the slabs are already gone
-    ctx->free_blocks[cls].push_back(p);
-    ctx->pool_cached += cls;
+    pool_insert_free(ctx, (char*)p, cls);
+    ctx->pool_free += cls;
   }
   if (ctx->live_bufs.fetch_sub(1) == 1 && ctx->destroyed) delete ctx;
 }
@@ -80,39 +96,43 @@ int32_t dev_alloc(Ctx* ctx, size_t bytes, BufP* out) {
   ctx->live_bufs.fetch_add(1);
   b->bytes = bytes;
   if (bytes == 0) bytes = 16;
-  b->cls = size_class(bytes);
+  size_t need = (bytes + ALIGN - 1) & ~(ALIGN - 1);
   double t0 = now_us();
-  auto it = ctx->free_blocks.find(b->cls);
-  if (it != ctx->free_blocks.end() && !it->second.empty()) {
-    b->p = it->second.back();
-    it->second.pop_back();
-    ctx->pool_cached -= b->cls;
-  } else {
-    size_t need = (b->cls + 255) & ~(size_t)255;
-    if (need > ctx->slab_left) {
-      size_t slab = need > SLAB_BYTES ? need : SLAB_BYTES;
-      void* p = nullptr;
-      cudaError_t e = cudaMalloc(&p, slab);
-      if (e != cudaSuccess && slab > need) {   // not enough room for a full slab: take just what is needed
-        cudaGetLastError();
-        slab = need;
-        e = cudaMalloc(&p, slab);
-      }
-      if (e != cudaSuccess) {
-        cudaGetLastError();
-        set_error(std::string("cudaMalloc(") + std::to_string(slab) + "): " + cudaGetErrorString(e) +
-                  " (pool reserved " + std::to_string(ctx->pool_reserved) + " B, cached " + std::to_string(ctx->pool_cached) + " B)");
-        return DBSP_ERR_CUDA;
-      }
-      ctx->slabs.push_back(p);
-      ctx->slab_cur = (char*)p;
-      ctx->slab_left = slab;
-      ctx->pool_reserved += slab;
+  auto it = ctx->free_by_size.lower_bound(need);
+  if (it == ctx->free_by_size.end()) {
+    size_t slab = need > SLAB_BYTES ? need : SLAB_BYTES;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, slab);
+    while (e != cudaSuccess && slab > need) {   // not enough room for a full slab: shrink towards the request
+      cudaGetLastError();
+      slab = std::max(need, slab / 2);
+      e = cudaMalloc(&p, slab);
     }
-    b->p = ctx->slab_cur;
-    ctx->slab_cur += need;
-    ctx->slab_left -= need;
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_error(std::string("cudaMalloc(") + std::to_string(slab) + "): " + cudaGetErrorString(e) + " (pool reserved " +
+                std::to_string(ctx->pool_reserved) + " B, free " + std::to_string(ctx->pool_free) + " B)");
+      return DBSP_ERR_CUDA;
+    }
+    ctx->slabs[(char*)p] = slab;
+    ctx->pool_reserved += slab;
+    ctx->pool_free += slab;
+    pool_insert_free(ctx, (char*)p, slab);
+    it = ctx->free_by_size.lower_bound(need);
   }
+  char* p = it->second;
+  size_t sz = it->first;
+  ctx->free_by_size.erase(it);
+  ctx->free_by_addr.erase(p);
+  if (sz - need >= ALIGN) {   // split
+    ctx->free_by_addr[p + need] = sz - need;
+    ctx->free_by_size.insert({sz - need, p + need});
+  } else {
+    need = sz;
+  }
+  b->p = p;
+  b->cls = need;
+  ctx->pool_free -= need;
   ctx->t_alloc_us += now_us() - t0;
   ctx->n_alloc++;
   *out = b;

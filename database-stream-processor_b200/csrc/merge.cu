@@ -28,6 +28,17 @@ namespace {
 constexpr int MERGE_THREADS = 256;
 constexpr u64 ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62, ST_MASK = (1ull << 62) - 1;
 
+// status words carry flag and value in one 64-bit word: relaxed device-scope
+// accesses (L2, never a stale L1 line) are all the protocol needs
+__device__ __forceinline__ u64 ld_relaxed(const u64* p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed(u64* p, u64 v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 template <int L>
 struct MergeCfg {
   // odd items/thread: the per-thread serial merge walks shared memory with a
@@ -94,19 +105,24 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
   const bool has_prev = a0 > 0, has_next = b1 < nB;
 
   // ---- stage: [0] = A[a0-1] halo, [1,1+na) = A, [1+na,1+na+nb) = B, then B[b1] halo
-  for (int x = tid; x < na + 1; x += MERGE_THREADS) {
-    if (x == 0 && !has_prev) continue;
-    u64 g = a0 + x - 1;
+  // One fixed-trip loop over the TILE+2 staged slots so that all of a thread's
+  // global loads are independent and in flight together.
+  {
+    const int nslots = na + nb + 2;
 #pragma unroll
-    for (int l = 0; l < L; l++) sl[l * S + x] = A.c[l][g] ^ f.f[l];
-    sw[x] = wA[g];
-  }
-  for (int x = tid; x < nb + 1; x += MERGE_THREADS) {
-    if (x == nb && !has_next) continue;
-    u64 g = b0 + x;
+    for (int k = 0; k < IPT + 1; k++) {
+      const int x = tid + k * MERGE_THREADS;
+      if (x < nslots) {
+        const bool from_a = x <= na;
+        const bool skip = (x == 0 && !has_prev) || (x == nslots - 1 && !has_next);
+        if (!skip) {
+          const u64 g = from_a ? (a0 + x - 1) : (b0 + (x - 1 - na));
 #pragma unroll
-    for (int l = 0; l < L; l++) sl[l * S + 1 + na + x] = B.c[l][g] ^ f.f[l];
-    sw[1 + na + x] = wB[g];
+          for (int l = 0; l < L; l++) sl[l * S + x] = (from_a ? A.c[l][g] : B.c[l][g]) ^ f.f[l];
+          sw[x] = from_a ? wA[g] : wB[g];
+        }
+      }
+    }
   }
   __syncthreads();
 
@@ -219,29 +235,37 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
   u32 off = warp_off + incl - cnt;
 
   // ---- decoupled look-back for the tile's global output offset -------------------
-  if (tid == 0) {
-    unsigned long long* vs = (unsigned long long*)status;
+  // Warp 0 inspects 32 predecessor status words per step (aggregates of tiles
+  // that have not resolved their own prefix yet are summed on the way).
+  if (tid < 32) {
     u64 base = 0;
     if (t == 0) {
-      atomicExch(&vs[0], ST_PREFIX | (u64)tile_total);
+      if (tid == 0) st_relaxed(&status[0], ST_PREFIX | (u64)tile_total);
     } else {
-      atomicExch(&vs[t], ST_AGG | (u64)tile_total);
-      u32 p = t - 1;
+      if (tid == 0) st_relaxed(&status[t], ST_AGG | (u64)tile_total);
+      long long p = (long long)t - 1;   // window = tiles p, p-1, ..., p-31
       while (true) {
-        u64 v;
-        do { v = atomicAdd(&vs[p], 0ull); } while ((v >> 62) == 0);
-        base += v & ST_MASK;
-        if ((v >> 62) == 2) break;
-        p--;
+        const long long q = p - tid;
+        u64 v = ST_PREFIX;               // tiles before 0 contribute an empty prefix
+        if (q >= 0) {
+          do { v = ld_relaxed(&status[q]); } while ((v >> 62) == 0);
+        }
+        const unsigned is_prefix = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+        const int first = is_prefix ? (__ffs(is_prefix) - 1) : 32;   // nearest tile with a full prefix
+        u64 contrib = (tid <= first) ? (v & ST_MASK) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        base += contrib;
+        if (is_prefix) break;
+        p -= 32;
       }
-      atomicExch(&vs[t], ST_PREFIX | (base + tile_total));
+      if (tid == 0) st_relaxed(&status[t], ST_PREFIX | (base + tile_total));
     }
-    s_base = base;
-    if (t == ntiles - 1) *n_out = base + tile_total;
+    if (tid == 0) {
+      s_base = base;
+      if (t == ntiles - 1) *n_out = base + tile_total;
+    }
   }
-  // Lane 0 may still be spinning above while lanes 1..31 run ahead: reconverge
-  // the warp before anything that ends in the (aligned) block barrier below.
-  __syncwarp();
 
   // ---- compact kept rows in shared memory -------------------------------------------
 #pragma unroll
