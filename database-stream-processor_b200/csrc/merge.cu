@@ -35,6 +35,13 @@ __device__ __forceinline__ u64 ld_relaxed(const u64* p) {
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
 __device__ __forceinline__ void st_relaxed(u64* p, u64 v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -91,6 +98,8 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
   __shared__ u32 s_tile;
   __shared__ u64 s_base;
   __shared__ u32 s_warp[MERGE_THREADS / 32];
+  __shared__ int s_lb_first[MERGE_THREADS / 32];
+  __shared__ u64 s_lb_all[MERGE_THREADS / 32], s_lb_upto[MERGE_THREADS / 32];
 
   const int tid = threadIdx.x;
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
@@ -103,10 +112,14 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
   const u64 b0 = d0 - a0, b1 = d1 - a1;
   const int na = (int)(a1 - a0), nb = (int)(b1 - b0);
   const bool has_prev = a0 > 0, has_next = b1 < nB;
+  bool any_flip = false;
+#pragma unroll
+  for (int l = 0; l < L; l++) any_flip = any_flip || (f.f[l] != 0);
 
   // ---- stage: [0] = A[a0-1] halo, [1,1+na) = A, [1+na,1+na+nb) = B, then B[b1] halo
-  // One fixed-trip loop over the TILE+2 staged slots so that all of a thread's
-  // global loads are independent and in flight together.
+  // cp.async (LDGSTS) copies global -> shared without a register round trip, so
+  // all of a thread's (IPT+1)*(L+1) 8-byte loads are in flight together; the
+  // sign flips of i64 lanes are applied in shared memory afterwards.
   {
     const int nslots = na + nb + 2;
 #pragma unroll
@@ -118,8 +131,20 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
         if (!skip) {
           const u64 g = from_a ? (a0 + x - 1) : (b0 + (x - 1 - na));
 #pragma unroll
-          for (int l = 0; l < L; l++) sl[l * S + x] = (from_a ? A.c[l][g] : B.c[l][g]) ^ f.f[l];
-          sw[x] = from_a ? wA[g] : wB[g];
+          for (int l = 0; l < L; l++) cp_async8(&sl[l * S + x], (from_a ? A.c[l] : B.c[l]) + g);
+          cp_async8(&sw[x], (from_a ? wA : wB) + g);
+        }
+      }
+    }
+    cp_async_wait_all();
+    if (any_flip) {
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < IPT + 1; k++) {
+        const int x = tid + k * MERGE_THREADS;
+        if (x < nslots) {
+#pragma unroll
+          for (int l = 0; l < L; l++) sl[l * S + x] ^= f.f[l];
         }
       }
     }
@@ -234,39 +259,6 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
   }
   u32 off = warp_off + incl - cnt;
 
-  // ---- decoupled look-back for the tile's global output offset -------------------
-  // Warp 0 inspects 32 predecessor status words per step (aggregates of tiles
-  // that have not resolved their own prefix yet are summed on the way).
-  if (tid < 32) {
-    u64 base = 0;
-    if (t == 0) {
-      if (tid == 0) st_relaxed(&status[0], ST_PREFIX | (u64)tile_total);
-    } else {
-      if (tid == 0) st_relaxed(&status[t], ST_AGG | (u64)tile_total);
-      long long p = (long long)t - 1;   // window = tiles p, p-1, ..., p-31
-      while (true) {
-        const long long q = p - tid;
-        u64 v = ST_PREFIX;               // tiles before 0 contribute an empty prefix
-        if (q >= 0) {
-          do { v = ld_relaxed(&status[q]); } while ((v >> 62) == 0);
-        }
-        const unsigned is_prefix = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-        const int first = is_prefix ? (__ffs(is_prefix) - 1) : 32;   // nearest tile with a full prefix
-        u64 contrib = (tid <= first) ? (v & ST_MASK) : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-        base += contrib;
-        if (is_prefix) break;
-        p -= 32;
-      }
-      if (tid == 0) st_relaxed(&status[t], ST_PREFIX | (base + tile_total));
-    }
-    if (tid == 0) {
-      s_base = base;
-      if (t == ntiles - 1) *n_out = base + tile_total;
-    }
-  }
-
   // ---- compact kept rows in shared memory -------------------------------------------
 #pragma unroll
   for (int k = 0; k < IPT; k++) {
@@ -276,6 +268,57 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
       off++;
     }
   }
+
+  // ---- decoupled look-back for the tile's global output offset -------------------
+  // The whole CTA inspects 256 predecessor status words per round trip (tile
+  // t-1-tid per thread): with ~600 tiles in flight the prefix reaches a tile in
+  // 2-3 L2 round trips instead of a 32-wide window's ~20.
+  if (t == 0) {
+    if (tid == 0) { st_relaxed(&status[0], ST_PREFIX | (u64)tile_total); s_base = 0; }
+  } else {
+    if (tid == 0) st_relaxed(&status[t], ST_AGG | (u64)tile_total);
+    u64 base_acc = 0;
+    long long p = (long long)t - 1;   // window = tiles p, p-1, ..., p-255
+    while (true) {
+      const long long q = p - tid;
+      u64 v = ST_PREFIX;               // tiles before 0 contribute an empty prefix
+      if (q >= 0) {
+        do { v = ld_relaxed(&status[q]); } while ((v >> 62) == 0);
+      }
+      const unsigned is_prefix = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+      const int wfirst = is_prefix ? (__ffs(is_prefix) - 1) : 32;
+      u64 all = v & ST_MASK, upto = ((tid & 31) <= wfirst) ? (v & ST_MASK) : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        all += __shfl_xor_sync(0xffffffffu, all, o);
+        upto += __shfl_xor_sync(0xffffffffu, upto, o);
+      }
+      if ((tid & 31) == 0) {
+        s_lb_first[tid >> 5] = wfirst;
+        s_lb_all[tid >> 5] = all;
+        s_lb_upto[tid >> 5] = upto;
+      }
+      __syncthreads();
+      bool found = false;
+      u64 add = 0;
+#pragma unroll
+      for (int wi = 0; wi < MERGE_THREADS / 32; wi++) {
+        if (!found) {
+          if (s_lb_first[wi] < 32) { add += s_lb_upto[wi]; found = true; }
+          else add += s_lb_all[wi];
+        }
+      }
+      base_acc += add;
+      __syncthreads();   // s_lb_* are rewritten by the next window
+      if (found) break;
+      p -= MERGE_THREADS;
+    }
+    if (tid == 0) {
+      st_relaxed(&status[t], ST_PREFIX | (base_acc + tile_total));
+      s_base = base_acc;
+    }
+  }
+  if (tid == 0 && t == ntiles - 1) *n_out = s_base + tile_total;
   __syncthreads();
   const u64 base = s_base;
   for (u32 o = tid; o < tile_total; o += MERGE_THREADS) {
