@@ -110,9 +110,20 @@ __global__ void k_probe_ranges(Cols D, u64 nd, Cols T, u64 nt, int nk, Flips f, 
   u64 q[MAXL];
   for (int l = 0; l < nk; l++) q[l] = D.c[l][i] ^ f.f[l];
   u64 lo = lower_bound_q(T, 0, nt, q, nk, f);
-  u64 hi = upper_bound_q(T, lo, nt, q, nk, f);
+  // a key's value group is short: gallop from lo (advance.rs:25-72) instead of
+  // a second full-range bisection
+  u64 hi = lo, step = 1;
+  while (hi + step <= nt && cmp_row_q(T, hi + step - 1, q, nk, f) == 0) { hi += step; step <<= 1; }
+  u64 top = hi + step <= nt ? hi + step : nt;
+  hi = upper_bound_q(T, hi, top, q, nk, f);
   lo_out[i] = (u32)lo;
   cnt_out[i] = (u32)(hi - lo);
+}
+
+// gather the per-batch match totals (last entry of each scanned count array)
+__global__ void k_gather_totals(const u32* base, u64 per, u64 off, int nb, u64* out) {
+  int b = threadIdx.x;
+  if (b < nb) out[b] = base[per * b + off];
 }
 
 // Expand the matches: output slot o -> (delta row i, trace row lo[i] + j).
@@ -297,6 +308,69 @@ __global__ void k_agg_pick(Cols G, const i64* wG, u64 n, int nk, int nv, int kin
   keep[i] = k;
   if (k)
     for (int l = 0; l < out_nv; l++) out.c[l][i] = v[l];
+}
+
+// Max / Min fast path.  Per key and per spine batch the only candidate is the
+// last (Max, max.rs:36-55 walks back from the end) or first (Min, min.rs:38-57)
+// value of the key's range; the winner's weight summed over the batches that
+// hold it is CursorList::weight (cursor_list.rs:200-210).  If that sum is zero
+// the extremum was cancelled and the key is flagged for the general path.
+struct BatchRef {
+  Cols c;
+  const i64* w;
+  u64 n;
+};
+constexpr int MAX_REFS = 16;
+struct BatchRefs {
+  BatchRef b[MAX_REFS];
+  int nb;
+};
+__global__ void k_agg_extremum(Cols K, u64 nkeys, int nk, int nv, BatchRefs tr, Flips f, int is_max, u32* keep,
+                               MCols outv, u64* slow_counter) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nkeys) return;
+  if (i == nkeys) { keep[nkeys] = 0; return; }
+  u64 q[MAXL], best[MAXL];
+  for (int l = 0; l < nk; l++) q[l] = K.c[l][i] ^ f.f[l];
+  bool have = false;
+  i64 wsum = 0;
+  for (int b = 0; b < tr.nb; b++) {
+    const Cols& T = tr.b[b].c;
+    u64 nt = tr.b[b].n, r;
+    if (is_max) {
+      u64 hi = upper_bound_q(T, 0, nt, q, nk, f);
+      if (hi == 0) continue;
+      r = hi - 1;
+    } else {
+      r = lower_bound_q(T, 0, nt, q, nk, f);
+      if (r >= nt) continue;
+    }
+    if (cmp_row_q(T, r, q, nk, f) != 0) continue;
+    int c = 0;   // cmp(candidate, best) over the value lanes
+    u64 cand[MAXL];
+    for (int l = 0; l < nv; l++) {
+      cand[l] = T.c[nk + l][r] ^ f.f[nk + l];
+      if (have && c == 0 && cand[l] != best[l]) c = cand[l] < best[l] ? -1 : 1;
+    }
+    bool better = !have || (is_max ? c > 0 : c < 0);
+    if (better) {
+      for (int l = 0; l < nv; l++) best[l] = cand[l];
+      wsum = tr.b[b].w[r];
+      have = true;
+    } else if (c == 0) {
+      wsum = (i64)((u64)wsum + (u64)tr.b[b].w[r]);
+    }
+  }
+  u32 k = 0;
+  if (have) {
+    if (wsum != 0) {
+      k = 1;
+      for (int l = 0; l < nv; l++) outv.c[l][i] = best[l] ^ f.f[nk + l];
+    } else {
+      atomicAdd((unsigned long long*)slow_counter, 1ull);
+    }
+  }
+  keep[i] = k;
 }
 
 // weigh (aggregate/mod.rs:297-323): per row f(k,v)*w; AVG mode emits the
@@ -485,12 +559,13 @@ static int32_t probe_spine(Ctx* ctx, const Batch* delta, int nk, const Spine* tr
     LAUNCH_COUNT(ctx);
     TRY(exclusive_scan_u32(ctx, cnt, ex, nd));
   }
-  for (size_t b = 0; b < nb; b++) {   // one sync for all totals would need a gather; nb is small
-    u32 tot;
-    u32* ex = (u32*)pb->p + per * b + 2 * (nd + 1);
-    TRY(read_back32(ctx, ex + nd, &tot));
-    totals[b] = tot;
-    grand += tot;
+  for (size_t b0 = 0; b0 < nb; b0 += 64) {   // one read-back for (up to 64) batch totals
+    int cnt = (int)std::min<size_t>(64, nb - b0);
+    k_gather_totals<<<1, 64, 0, st>>>((const u32*)pb->p + per * b0, per, 2 * (nd + 1) + nd, cnt, ctx->d_scratch + 128);
+    LAUNCH_COUNT(ctx);
+    u64 tt[64];
+    TRY(read_back(ctx, ctx->d_scratch + 128, cnt, tt));
+    for (int b = 0; b < cnt; b++) { totals[b0 + b] = tt[b]; grand += tt[b]; }
   }
   if (grand == 0) { *out = batch_new_empty(ctx, out_schema); return DBSP_OK; }
   int Lo = out_schema.n_key_lanes + out_schema.n_val_lanes;
@@ -571,13 +646,57 @@ int32_t op_aggregate_delta(Ctx* ctx, const Batch* delta, const Spine* in_tr, con
   // 1. affected keys
   Batch* keys = nullptr;
   TRY(distinct_keys(ctx, delta, nk, &keys));
-  // 2. their value groups in the input trace, weights summed over batches
-  Batch* G = nullptr;
-  int32_t rc = probe_spine(ctx, keys, nk, in_tr, nullptr, 1, in_tr->s, &G);
-  if (rc) { batch_unref(keys); return rc; }
-  // 3. aggregate per key -> rows (key, new value) with weight +1
+  int32_t rc;
   Batch* N = nullptr;
-  if (G->n) {
+  // 2a. Max / Min: candidates straight from the batches' range ends
+  if ((kind == DBSP_AGG_MAX || kind == DBSP_AGG_MIN) && in_tr->batches.size() <= (size_t)MAX_REFS && keys->n) {
+    BatchRefs refs;
+    refs.nb = (int)in_tr->batches.size();
+    for (int b = 0; b < refs.nb; b++) {
+      refs.b[b].c = in_tr->batches[b]->cols();
+      refs.b[b].w = in_tr->batches[b]->w;
+      refs.b[b].n = in_tr->batches[b]->n;
+    }
+    Flips tf;
+    for (int l = 0; l < MAXL; l++)
+      tf.f[l] = (l < nk + nov && in_tr->s.lane_types[l] == DBSP_I64) ? 0x8000000000000000ull : 0ull;
+    BufP kb;
+    TRY(dev_alloc(ctx, (size_t)(keys->n + 1) * 4, &kb));
+    TmpRows nvr;
+    TRY(tmp_alloc(ctx, nov, keys->n, &nvr));
+    u64* slow = ctx->d_scratch + 16;
+    CUDA_TRY(cudaMemsetAsync(slow, 0, 8, st));
+    {
+      u64 lg = 1; while ((1ull << lg) < in_tr->batches[0]->n + 1) lg++;
+      ProfScope ps(ctx, KID_AGG_PICK, keys->n * ((u64)nk * 8 + (u64)refs.nb * (lg * 8 + (u64)(nov + 1) * 8) + (u64)nov * 8));
+      k_agg_extremum<<<blocks(keys->n + 1), TB, 0, st>>>(keys->cols(), keys->n, nk, nov, refs, tf, kind == DBSP_AGG_MAX,
+                                                        (u32*)kb->p, nvr.c, slow);
+    }
+    LAUNCH_COUNT(ctx);
+    u64 nslow;
+    TRY(read_back(ctx, slow, 1, &nslow));
+    if (nslow == 0) {
+      Cols src;
+      for (int l = 0; l < MAXL; l++) src.c[l] = nullptr;
+      for (int l = 0; l < nk; l++) src.c[l] = keys->col[l];
+      for (int l = 0; l < nov; l++) src.c[nk + l] = nvr.c.c[l];
+      BufP ones;
+      TRY(dev_alloc(ctx, (size_t)keys->n * 8, &ones));
+      k_fill_i64<<<blocks(keys->n), TB, 0, st>>>((i64*)ones->p, keys->n, 1);
+      LAUNCH_COUNT(ctx);
+      rc = compact_ordered(ctx, os, src, (const i64*)ones->p, (u32*)kb->p, keys->n, &N);
+      if (rc) { batch_unref(keys); return rc; }
+    }
+  }
+  // 2b. general path: the keys' value groups, weights summed over batches
+  Batch* G = nullptr;
+  if (!N) {
+    rc = probe_spine(ctx, keys, nk, in_tr, nullptr, 1, in_tr->s, &G);
+    if (rc) { batch_unref(keys); return rc; }
+  }
+  // 3. aggregate per key -> rows (key, new value) with weight +1
+  if (N) {
+  } else if (G->n) {
     int gnk = nk, gnv = G->nl() - nk;
     if (kind == DBSP_AGG_WCOUNT2) gnv = 0;   // (K.., which) rows: `which` read as lane nk
     BufP kb, ps;
@@ -608,7 +727,7 @@ int32_t op_aggregate_delta(Ctx* ctx, const Batch* delta, const Spine* in_tr, con
   } else {
     N = batch_new_empty(ctx, os);
   }
-  batch_unref(G);
+  if (G) batch_unref(G);
   // 4. current values of those keys in the output trace, negated
   Batch* O = nullptr;
   rc = probe_spine(ctx, keys, nk, out_tr, nullptr, 1, os, &O);
