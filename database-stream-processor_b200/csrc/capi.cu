@@ -30,7 +30,7 @@ static int32_t stage_columns(Ctx* ctx, const u64* const* cols, int ncols, const 
     *dw = w;
     return DBSP_OK;
   }
-  u64 cap = (n + 31) & ~31ull;
+  u64 cap = (n + 32) & ~31ull;
   TRY(dev_alloc(ctx, (size_t)cap * 8 * (ncols + 1), hold));
   u64* base = (u64*)(*hold)->p;
   for (int l = 0; l < ncols; l++) {

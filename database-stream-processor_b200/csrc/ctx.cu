@@ -141,7 +141,7 @@ int32_t dev_alloc(Ctx* ctx, size_t bytes, BufP* out) {
 
 int32_t batch_alloc(Ctx* ctx, const dbsp_schema& s, u64 n, Batch** out, MCols* cols, i64** w) {
   int L = s.n_key_lanes + s.n_val_lanes;
-  u64 cap = (n + 31) & ~31ull;   // keep every lane 256-byte aligned
+  u64 cap = (n + 32) & ~31ull;   // >= n+1 rows (TMA tiles may over-read one row), lanes 256-byte aligned
   if (cap == 0) cap = 32;
   BufP buf;
   TRY(dev_alloc(ctx, (size_t)cap * 8 * (L + 1), &buf));

@@ -8,14 +8,16 @@
 // reference's key-then-value-range merge; equal rows have their weights
 // summed and zero sums are dropped.
 //
-// One pass over HBM: a merge-path partition kernel cuts the merged sequence
-// into tiles; each CTA stages its A and B segments in shared memory
-// (coalesced loads), every thread merge-path-searches its own diagonal and
-// serially merges IPT items, the kept rows are compacted in shared memory and
-// written back coalesced.  Because both inputs are consolidated, an equal pair
-// is always (a, b) adjacent in merged order: the A item absorbs its partner's
-// weight, the B item is skipped — also across thread and tile boundaries (one
-// halo element on each side).  The tile's global output offset comes from a
+// One pass over HBM.  A merge-path partition kernel cuts the merged sequence
+// into tiles.  Each CTA stages its A and B segments in shared memory with TMA
+// bulk copies (cp.async.bulk + mbarrier: one thread issues 2*(L+1) copies, no
+// registers, no per-thread address arithmetic); every thread
+// merge-path-searches its own diagonal and serially merges IPT rows with both
+// run heads in registers; kept rows are compacted in shared memory and written
+// back coalesced.  Because both inputs are consolidated, an equal pair is
+// always (a, b) adjacent in merged order: the A row absorbs its partner's
+// weight, the B row is skipped — also across thread and tile boundaries (one
+// halo row on each side).  The tile's global output offset comes from a
 // decoupled look-back over per-tile status words (tiles take their index from
 // an atomic ticket, so predecessors are always resident or done).
 #include <cstdio>
@@ -25,7 +27,10 @@
 
 namespace {
 
-constexpr int MERGE_THREADS = 256;
+#ifndef MERGE_THREADS_CFG
+#define MERGE_THREADS_CFG 256
+#endif
+constexpr int MERGE_THREADS = MERGE_THREADS_CFG;
 constexpr u64 ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62, ST_MASK = (1ull << 62) - 1;
 
 // status words carry flag and value in one 64-bit word: relaxed device-scope
@@ -35,6 +40,9 @@ __device__ __forceinline__ u64 ld_relaxed(const u64* p) {
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_relaxed(u64* p, u64 v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
   unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
@@ -42,17 +50,50 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
-__device__ __forceinline__ void st_relaxed(u64* p, u64 v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, u64* mbar) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  unsigned m = (unsigned)__cvta_generic_to_shared(mbar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+               "l"(gsrc), "r"(bytes), "r"(m)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init(u64* mbar, unsigned count) {
+  unsigned m = (unsigned)__cvta_generic_to_shared(mbar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(m), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* mbar, unsigned bytes) {
+  unsigned m = (unsigned)__cvta_generic_to_shared(mbar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* mbar, unsigned parity) {
+  unsigned m = (unsigned)__cvta_generic_to_shared(mbar);
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(m),
+      "r"(parity)
+      : "memory");
 }
 
 template <int L>
 struct MergeCfg {
-  // odd items/thread: the per-thread serial merge walks shared memory with a
+  // odd rows/thread: the per-thread serial merge walks shared memory with a
   // stride of IPT 64-bit words between lanes of a warp -> bank-conflict free
-  static constexpr int IPT = (L <= 2) ? 7 : (L <= 4 ? 5 : 3);
+#ifdef MERGE_IPT_CFG
+  static constexpr int IPT = (L <= 2) ? MERGE_IPT_CFG : (L <= 4 ? 5 : 3);
+#else
+  static constexpr int IPT = (L <= 2) ? 9 : (L <= 4 ? 5 : 3);
+#endif
   static constexpr int TILE = MERGE_THREADS * IPT;
-  static constexpr size_t SMEM = (size_t)(TILE + 2) * (L + 1) * 8 + (size_t)TILE * 4;
+  static constexpr int S = TILE + 8;   // staged slots per array (even; room for alignment slack + halos)
+  static constexpr size_t SMEM = (size_t)S * (L + 1) * 8 + (size_t)TILE * 4;
 };
 
 // a-count of the merge path at diagonal d: number of A rows among the first d
@@ -87,14 +128,16 @@ __global__ void k_merge_partition(Cols A, u64 nA, Cols B, u64 nB, Flips f, u32 t
 template <int L>
 __global__ void __launch_bounds__(MERGE_THREADS)
 k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __restrict__ wB, u64 nB, Flips f,
-              const u64* __restrict__ part, u32 ntiles, u32* ticket, u64* status, MCols O, i64* wO, u64* n_out) {
+              const u64* __restrict__ part, u32 ntiles, u32* ticket, u64* status, MCols O, i64* wO, u64* n_out,
+              int use_tma) {
   constexpr int IPT = MergeCfg<L>::IPT;
   constexpr int TILE = MergeCfg<L>::TILE;
-  constexpr int S = TILE + 2;   // stride of one staged lane
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  u64* sl = (u64*)smem_raw;                 // L lanes of S (flipped values)
+  constexpr int S = MergeCfg<L>::S;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  u64* sl = (u64*)smem_raw;                 // L lanes of S staged slots
   i64* sw = (i64*)(sl + (size_t)L * S);     // S weights; reused as output weights
-  u32* perm = (u32*)(sw + S);               // TILE staged-row indices of kept rows
+  u32* perm = (u32*)(sw + S);               // TILE staged-slot indices of kept rows
+  __shared__ __align__(8) u64 s_mbar;
   __shared__ u32 s_tile;
   __shared__ u64 s_base;
   __shared__ u32 s_warp[MERGE_THREADS / 32];
@@ -102,7 +145,10 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
   __shared__ u64 s_lb_all[MERGE_THREADS / 32], s_lb_upto[MERGE_THREADS / 32];
 
   const int tid = threadIdx.x;
-  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  if (tid == 0) {
+    s_tile = atomicAdd(ticket, 1u);
+    mbar_init(&s_mbar, 1);
+  }
   __syncthreads();
   const u32 t = s_tile;
   const u64 total = nA + nB;
@@ -116,11 +162,44 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
 #pragma unroll
   for (int l = 0; l < L; l++) any_flip = any_flip || (f.f[l] != 0);
 
-  // ---- stage: [0] = A[a0-1] halo, [1,1+na) = A, [1+na,1+na+nb) = B, then B[b1] halo
-  // cp.async (LDGSTS) copies global -> shared without a register round trip, so
-  // all of a thread's (IPT+1)*(L+1) 8-byte loads are in flight together; the
-  // sign flips of i64 lanes are applied in shared memory afterwards.
-  {
+  // ---- stage --------------------------------------------------------------------
+  // Slot map: A row a0+i lives at slot oa+i (i = -1 is the A halo), B row b0+j at
+  // slot ob+j (j = nb is the B halo).  The TMA path copies 16-byte aligned
+  // super-ranges, which fixes oa/ob; the fallback uses oa = 1, ob = 1+na.
+  int oa, ob;
+  if (use_tma) {
+    const long long fa = (long long)a0 - (has_prev ? 1 : 0);          // first A row needed
+    const long long pa = (long long)(((unsigned long long)(size_t)A.c[0]) >> 3) & 1;
+    const long long ga = fa - ((fa + pa) & 1);                        // aligned-down start (may be -1)
+    const long long ea = (long long)a1;                               // end (exclusive)
+    const int ca = (ea > fa) ? (int)(((ea - ga) + 1) & ~1ll) : 0;     // rows copied (even)
+    oa = (int)((long long)a0 - ga);
+    const int sb = (oa + na + 1) & ~1;                                // first slot of the B region (even)
+    const long long eb = (long long)b1 + (has_next ? 1 : 0);
+    const long long pb = (long long)(((unsigned long long)(size_t)B.c[0]) >> 3) & 1;
+    const long long gb = (long long)b0 - (((long long)b0 + pb) & 1);
+    const int cb = (eb > (long long)b0) ? (int)(((eb - gb) + 1) & ~1ll) : 0;
+    ob = sb + (int)((long long)b0 - gb);
+    if (tid == 0) {
+      const unsigned bytes = (unsigned)(ca + cb) * 8u * (L + 1);
+      if (bytes) {
+        mbar_expect_tx(&s_mbar, bytes);
+        if (ca) {
+#pragma unroll
+          for (int l = 0; l < L; l++) tma_bulk_g2s(sl + l * S, A.c[l] + ga, (unsigned)ca * 8u, &s_mbar);
+          tma_bulk_g2s(sw, wA + ga, (unsigned)ca * 8u, &s_mbar);
+        }
+        if (cb) {
+#pragma unroll
+          for (int l = 0; l < L; l++) tma_bulk_g2s(sl + l * S + sb, B.c[l] + gb, (unsigned)cb * 8u, &s_mbar);
+          tma_bulk_g2s(sw + sb, wB + gb, (unsigned)cb * 8u, &s_mbar);
+        }
+      }
+    }
+    if ((ca + cb) > 0) mbar_wait(&s_mbar, 0);
+  } else {
+    oa = 1;
+    ob = 1 + na;
     const int nslots = na + nb + 2;
 #pragma unroll
     for (int k = 0; k < IPT + 1; k++) {
@@ -137,16 +216,12 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
       }
     }
     cp_async_wait_all();
-    if (any_flip) {
-      __syncthreads();
+  }
+  if (any_flip) {   // i64 lanes: stage the order-preserving image
+    __syncthreads();
+    for (int x = tid; x < S; x += MERGE_THREADS) {
 #pragma unroll
-      for (int k = 0; k < IPT + 1; k++) {
-        const int x = tid + k * MERGE_THREADS;
-        if (x < nslots) {
-#pragma unroll
-          for (int l = 0; l < L; l++) sl[l * S + x] ^= f.f[l];
-        }
-      }
+      for (int l = 0; l < L; l++) sl[l * S + x] ^= f.f[l];
     }
   }
   __syncthreads();
@@ -159,12 +234,6 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
     }
     return true;
   };
-  auto eq = [&](int ia, int ib) {
-#pragma unroll
-    for (int l = 0; l < L; l++)
-      if (sl[l * S + ia] != sl[l * S + ib]) return false;
-    return true;
-  };
 
   // ---- per-thread merge path ------------------------------------------------
   const int n = na + nb;
@@ -173,33 +242,33 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
   int lo = dt > nb ? dt - nb : 0, hi = dt < na ? dt : na;
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
-    if (le(1 + mid, 1 + na + (dt - 1 - mid))) lo = mid + 1; else hi = mid;
+    if (le(oa + mid, ob + (dt - 1 - mid))) lo = mid + 1; else hi = mid;
   }
   int ai = lo, bi = dt - lo;
 
   // Serial merge with both run heads held in registers: one 3-way compare per
-  // item, only the advanced side is re-read from shared memory.  `prev_eq`
+  // row, only the advanced side is re-read from shared memory.  `prev_eq`
   // says the previous merged row was an A row equal to the current B head.
   u64 ka[L], kb[L];
   i64 wa = 0, wb = 0;
   auto load_a = [&](int i) {
 #pragma unroll
-    for (int l = 0; l < L; l++) ka[l] = sl[l * S + 1 + i];
-    wa = sw[1 + i];
+    for (int l = 0; l < L; l++) ka[l] = sl[l * S + oa + i];
+    wa = sw[oa + i];
   };
   auto load_b = [&](int j) {
 #pragma unroll
-    for (int l = 0; l < L; l++) kb[l] = sl[l * S + 1 + na + j];
-    wb = sw[1 + na + j];
+    for (int l = 0; l < L; l++) kb[l] = sl[l * S + ob + j];
+    wb = sw[ob + j];
   };
   bool b_readable = (bi < nb) || (bi == nb && has_next);
   if (ai < na) load_a(ai);
   if (b_readable) load_b(bi);
   bool prev_eq = false;
-  if ((ai > 0 || has_prev) && bi < nb) {   // A[ai-1] (index ai; halo at 0) vs B head
+  if ((ai > 0 || has_prev) && bi < nb) {   // A[ai-1] (slot oa+ai-1; halo at oa-1) vs B head
     prev_eq = true;
 #pragma unroll
-    for (int l = 0; l < L; l++) prev_eq = prev_eq && (sl[l * S + ai] == kb[l]);
+    for (int l = 0; l < L; l++) prev_eq = prev_eq && (sl[l * S + oa + ai - 1] == kb[l]);
   }
 
   u32 src[IPT];
@@ -222,14 +291,14 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
       if (take_a) {
         const bool partner = b_readable && c == 0;
         i64 w = partner ? (i64)((u64)wa + (u64)wb) : wa;
-        src[k] = 1 + ai;
+        src[k] = oa + ai;
         wv[k] = w;
         if (w != 0) keep |= 1u << k;
         prev_eq = partner;
         ai++;
         if (ai < na) load_a(ai);
       } else {
-        src[k] = 1 + na + bi;
+        src[k] = ob + bi;
         wv[k] = wb;
         if (!prev_eq && wb != 0) keep |= 1u << k;
         prev_eq = false;
@@ -270,15 +339,15 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
   }
 
   // ---- decoupled look-back for the tile's global output offset -------------------
-  // The whole CTA inspects 256 predecessor status words per round trip (tile
-  // t-1-tid per thread): with ~600 tiles in flight the prefix reaches a tile in
-  // 2-3 L2 round trips instead of a 32-wide window's ~20.
+  // The whole CTA inspects MERGE_THREADS predecessor status words per round trip
+  // (tile t-1-tid per thread); aggregates of tiles that have not resolved their
+  // own prefix yet are summed on the way.
   if (t == 0) {
     if (tid == 0) { st_relaxed(&status[0], ST_PREFIX | (u64)tile_total); s_base = 0; }
   } else {
     if (tid == 0) st_relaxed(&status[t], ST_AGG | (u64)tile_total);
     u64 base_acc = 0;
-    long long p = (long long)t - 1;   // window = tiles p, p-1, ..., p-255
+    long long p = (long long)t - 1;   // window = tiles p, p-1, ..., p-(MERGE_THREADS-1)
     while (true) {
       const long long q = p - tid;
       u64 v = ST_PREFIX;               // tiles before 0 contribute an empty prefix
@@ -329,6 +398,15 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
   }
 }
 
+// all arrays of the batch share the 16-byte phase of element 0 (true unless a
+// view mixes storage, e.g. a negated slice): precondition of the TMA path
+bool uniform_phase(const Batch* b) {
+  size_t ph = ((size_t)b->col[0] >> 3) & 1;
+  for (int l = 1; l < b->nl(); l++)
+    if ((((size_t)b->col[l] >> 3) & 1) != ph) return false;
+  return (((size_t)b->w >> 3) & 1) == ph;
+}
+
 template <int L>
 int32_t merge_launch(Ctx* ctx, const Batch* a, const Batch* b, Batch** out) {
   typedef MergeCfg<L> Cfg;
@@ -354,13 +432,15 @@ int32_t merge_launch(Ctx* ctx, const Batch* a, const Batch* b, Batch** out) {
     CUDA_TRY(cudaFuncSetAttribute(k_merge_tiles<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     attr_set = true;
   }
+  static const bool tma_off = getenv("DBSP_MERGE_NO_TMA") != nullptr;
+  const int use_tma = (!tma_off && uniform_phase(a) && uniform_phase(b)) ? 1 : 0;
   {
     ProfScope ps(ctx, KID_MERGE_PARTITION, (u64)(ntiles + 1) * 8);
     k_merge_partition<L><<<(ntiles + 1 + 127) / 128, 128, 0, st>>>(a->cols(), a->n, b->cols(), b->n, f, Cfg::TILE, ntiles, part);
   }
   ProfScope* ps = new ProfScope(ctx, KID_MERGE, 0);
   k_merge_tiles<L><<<ntiles, MERGE_THREADS, Cfg::SMEM, st>>>(a->cols(), a->w, a->n, b->cols(), b->w, b->n, f, part, ntiles,
-                                                           ticket, status, oc, ow, n_out);
+                                                           ticket, status, oc, ow, n_out, use_tma);
   long ps_idx = ps->idx;
   delete ps;   // records the end event
   ctx->kernel_launches += 2;

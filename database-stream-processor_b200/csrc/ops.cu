@@ -445,7 +445,7 @@ struct TmpRows {
   }
 };
 static int32_t tmp_alloc(Ctx* ctx, int L, u64 cap, TmpRows* t) {
-  u64 c = (cap + 31) & ~31ull;
+  u64 c = (cap + 32) & ~31ull;
   if (c == 0) c = 32;
   TRY(dev_alloc(ctx, (size_t)c * 8 * (L + 1), &t->buf));
   u64* base = (u64*)t->buf->p;
