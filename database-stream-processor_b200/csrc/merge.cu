@@ -89,7 +89,7 @@ struct MergeCfg {
 #ifdef MERGE_IPT_CFG
   static constexpr int IPT = (L <= 2) ? MERGE_IPT_CFG : (L <= 4 ? 5 : 3);
 #else
-  static constexpr int IPT = (L <= 2) ? 9 : (L <= 4 ? 5 : 3);
+  static constexpr int IPT = (L <= 2) ? 7 : (L <= 4 ? 5 : 3);
 #endif
   static constexpr int TILE = MERGE_THREADS * IPT;
   static constexpr int S = TILE + 8;   // staged slots per array (even; room for alignment slack + halos)
