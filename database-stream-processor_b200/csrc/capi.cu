@@ -22,7 +22,7 @@ static inline dbsp_batch* H(Batch* b) { return (dbsp_batch*)b; }
 // Stage host columns on the device (stream-ordered).  Host memory may be
 // pageable; pinned memory makes the copy asynchronous.
 static int32_t stage_columns(Ctx* ctx, const u64* const* cols, int ncols, const i64* w, u64 n, int on_device, BufP* hold,
-                             Cols* dc, const i64** dw) {
+                             Cols* dc, const i64** dw, unsigned col_mask = ~0u) {
   for (int l = 0; l < MAXL; l++) dc->c[l] = nullptr;
   *dw = nullptr;
   if (on_device || n == 0) {
@@ -34,6 +34,7 @@ static int32_t stage_columns(Ctx* ctx, const u64* const* cols, int ncols, const 
   TRY(dev_alloc(ctx, (size_t)cap * 8 * (ncols + 1), hold));
   u64* base = (u64*)(*hold)->p;
   for (int l = 0; l < ncols; l++) {
+    if (!((col_mask >> l) & 1)) continue;   // column never read by the closure: not copied
     CUDA_TRY(cudaMemcpyAsync(base + (size_t)l * cap, cols[l], n * 8, cudaMemcpyHostToDevice, ctx->stream));
     dc->c[l] = base + (size_t)l * cap;
     ctx->h2d_bytes += n * 8;
@@ -199,7 +200,7 @@ int32_t dbsp_batch_from_table(dbsp_ctx* ctx, const uint64_t* const* cols, uint32
   BufP hold;
   Cols dc;
   const i64* dw;
-  TRY(stage_columns(ctx, cols, (int)n_cols, w, n, on_device, &hold, &dc, &dw));
+  TRY(stage_columns(ctx, cols, (int)n_cols, w, n, on_device, &hold, &dc, &dw, proj_used_mask(*proj, 0)));
   Batch* b = nullptr;
   TRY(project_and_consolidate(ctx, dc, 0, (int)n_cols, dw, n, *proj, &b));
   *out = H(b);

@@ -191,6 +191,246 @@ __global__ void k_emit_seg(Cols cols, Plan p, const u64* key, const u32* idx, co
   out_w[o] = sums[s];
 }
 
+
+// ---------------------------------------------------------------------------
+// Reduce-by-key over rows that are already in sorted order (identity order, or
+// through the row ids of the radix sort): every run of equal rows becomes one
+// row carrying the sum of the run's weights; zero sums are dropped.  Two data
+// passes around a small per-tile scan:
+//   pass 0: per tile of RBK_TILE rows — #heads, weight of the rows before the
+//           first head (continuation of the run entering the tile), weight
+//           since the last head, #kept runs that lie entirely inside the tile;
+//   k_rbk_scan: carries the open run's weight across tiles (flag/sum monoid)
+//           and turns kept counts into output offsets;
+//   pass 1: recomputes the tile with its carry-in and writes the kept runs.
+// Replaces the dedup+retain of consolidate (consolidation/mod.rs:32-52).
+constexpr int RBK_THREADS = 256, RBK_R = 4, RBK_TILE = RBK_THREADS * RBK_R;
+struct RbkTile {
+  i64 pre, post;      // weight before the first head / since the last head (all rows if no head)
+  u32 nheads, inner_kept, closed_last, pad;
+};
+struct RbkCarry {
+  i64 carry_in;
+  u32 out_base, pad;
+};
+struct HS {
+  u32 h;
+  i64 s;
+};
+struct HSOp {
+  __device__ __forceinline__ HS operator()(const HS& a, const HS& b) const {
+    HS r;
+    r.h = a.h | b.h;
+    r.s = b.h ? b.s : (i64)((u64)a.s + (u64)b.s);
+    return r;
+  }
+};
+
+__device__ __forceinline__ bool rbk_differs(const Cols& cols, int L, int use_key, const u64* key, const u32* idx, u64 i,
+                                            u64 j) {
+  if (use_key) return key[i] != key[j];
+  u64 a = idx ? idx[i] : i, b = idx ? idx[j] : j;
+  for (int l = 0; l < L; l++)
+    if (cols.c[l][a] != cols.c[l][b]) return true;
+  return false;
+}
+
+template <int PHASE>
+__global__ void __launch_bounds__(RBK_THREADS)
+k_rbk(Cols cols, Plan p, const u64* key, const u32* idx, const i64* w, u64 n, RbkTile* tiles, const RbkCarry* carry,
+      MCols out, i64* out_w) {
+  __shared__ HS s_warp_hs[RBK_THREADS / 32];
+  __shared__ u32 s_warp_u[RBK_THREADS / 32];
+  __shared__ i64 s_pre;
+  __shared__ u32 s_inner, s_closed;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const u64 tile_s = (u64)blockIdx.x * RBK_TILE;
+  const u64 tile_e = tile_s + RBK_TILE < n ? tile_s + RBK_TILE : n;
+  const u64 r0 = tile_s + (u64)tid * RBK_R;
+  if (tid == 0) { s_pre = 0; s_inner = 0; s_closed = 0; }
+
+  // per-row head / tail flags and weights of this thread's rows
+  bool hd[RBK_R], tl[RBK_R], valid[RBK_R];
+  i64 wt[RBK_R];
+#pragma unroll
+  for (int k = 0; k < RBK_R; k++) {
+    const u64 i = r0 + k;
+    valid[k] = i < tile_e;
+    hd[k] = false; tl[k] = false; wt[k] = 0;
+    if (valid[k]) {
+      hd[k] = (i == 0) || rbk_differs(cols, p.L, p.use_key, key, idx, i, i - 1);
+      wt[k] = w ? w[idx ? idx[i] : i] : 1;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < RBK_R; k++) {
+    const u64 i = r0 + k;
+    if (valid[k]) {
+      if (k + 1 < RBK_R && r0 + k + 1 < tile_e) tl[k] = hd[k + 1];
+      else tl[k] = (i + 1 >= n) || rbk_differs(cols, p.L, p.use_key, key, idx, i + 1, i);
+    }
+  }
+  // thread aggregate: (has head, weight since last head / total)
+  HS agg; agg.h = 0; agg.s = 0;
+  i64 pre_t = 0;   // weight before this thread's first head
+#pragma unroll
+  for (int k = 0; k < RBK_R; k++) {
+    if (!valid[k]) continue;
+    if (hd[k]) { agg.h = 1; agg.s = wt[k]; }
+    else { agg.s = (i64)((u64)agg.s + (u64)wt[k]); if (!agg.h) pre_t = agg.s; }
+  }
+  // block exclusive scan of the aggregates with the flag/sum monoid
+  HSOp op;
+  HS incl = agg;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    HS v;
+    v.h = __shfl_up_sync(0xffffffffu, incl.h, o);
+    v.s = __shfl_up_sync(0xffffffffu, incl.s, o);
+    if (lane >= o) incl = op(v, incl);
+  }
+  if (lane == 31) s_warp_hs[wid] = incl;
+  __syncthreads();
+  HS wprefix; wprefix.h = 0; wprefix.s = 0;
+  for (int k = 0; k < wid; k++) wprefix = op(wprefix, s_warp_hs[k]);
+  HS excl_in_warp;
+  excl_in_warp.h = __shfl_up_sync(0xffffffffu, incl.h, 1);
+  excl_in_warp.s = __shfl_up_sync(0xffffffffu, incl.s, 1);
+  if (lane == 0) { excl_in_warp.h = 0; excl_in_warp.s = 0; }
+  const HS excl = op(wprefix, excl_in_warp);   // open run before this thread, within the tile
+
+  const i64 cin = PHASE ? carry[blockIdx.x].carry_in : 0;
+  // running weight of the run open at this thread's first row
+  i64 run = excl.h ? excl.s : (i64)((u64)excl.s + (u64)cin);
+  bool head_seen = excl.h != 0;
+  u32 kept = 0, inner = 0;
+  i64 tot[RBK_R];
+  bool kp[RBK_R];
+#pragma unroll
+  for (int k = 0; k < RBK_R; k++) {
+    kp[k] = false; tot[k] = 0;
+    if (!valid[k]) continue;
+    if (hd[k]) { run = wt[k]; head_seen = true; }
+    else run = (i64)((u64)run + (u64)wt[k]);
+    if (tl[k]) {
+      tot[k] = run;
+      if (PHASE) { kp[k] = run != 0; kept += kp[k]; }
+      else if (head_seen) inner += (run != 0);   // a run that lies entirely inside this tile
+    }
+  }
+
+  if (PHASE == 0) {
+    // tile aggregate
+    if (!excl.h) {   // no head before this thread in the tile: its leading rows continue the entering run
+      i64 c = agg.h ? pre_t : agg.s;
+      if (c) atomicAdd((unsigned long long*)&s_pre, (unsigned long long)c);
+    }
+    if (inner) atomicAdd(&s_inner, inner);
+    if (r0 < tile_e && r0 + RBK_R >= tile_e) {   // owner of the tile's last row
+      int lastk = (int)(tile_e - 1 - r0);
+      bool c = false;
+#pragma unroll
+      for (int k = 0; k < RBK_R; k++) if (k == lastk) c = tl[k];
+      s_closed = c ? 1u : 0u;
+    }
+    __syncthreads();
+    if (tid == RBK_THREADS - 1) {
+      HS tile = op(wprefix, incl);   // inclusive over the whole tile (this is the last thread)
+      RbkTile t;
+      t.pre = s_pre;
+      t.post = tile.s;
+      t.nheads = tile.h;
+      t.inner_kept = s_inner;
+      t.closed_last = s_closed;
+      t.pad = 0;
+      tiles[blockIdx.x] = t;
+    }
+    return;
+  }
+
+  // PHASE 1: ranks of the kept runs and output
+  u32 kincl = kept;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    u32 v = __shfl_up_sync(0xffffffffu, kincl, o);
+    if (lane >= o) kincl += v;
+  }
+  if (lane == 31) s_warp_u[wid] = kincl;
+  __syncthreads();
+  u32 woff = 0;
+  for (int k = 0; k < wid; k++) woff += s_warp_u[k];
+  u32 pos = carry[blockIdx.x].out_base + woff + kincl - kept;
+#pragma unroll
+  for (int k = 0; k < RBK_R; k++) {
+    if (!kp[k]) continue;
+    const u64 i = r0 + k;
+    if (p.use_key) {
+      const u64 kk = key[i];
+      for (int l = 0; l < p.L; l++) out.c[l][pos] = unpack_lane(p, l, kk);
+    } else {
+      const u64 r = idx ? idx[i] : i;
+      for (int l = 0; l < p.L; l++) out.c[l][pos] = cols.c[l][r];
+    }
+    out_w[pos] = tot[k];
+    pos++;
+  }
+}
+
+// One CTA: carry the open run's weight across tiles and prefix-sum the kept counts.
+__global__ void k_rbk_scan(const RbkTile* tiles, u32 ntiles, RbkCarry* carry, u32* total_out) {
+  __shared__ HS s_hs[1024];
+  __shared__ u32 s_cnt[1024];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const u32 chunk = (ntiles + nt - 1) / nt;
+  const u32 lo = min(ntiles, tid * chunk), hi = min(ntiles, lo + chunk);
+  HSOp op;
+  // element of tile t for the carry recurrence: carry_out = closes ? 0 : (h ? post : carry_in + pre)
+  auto elem = [&](const RbkTile& t) {
+    HS e;
+    const bool ends = t.closed_last != 0;
+    e.h = (t.nheads || ends) ? 1u : 0u;
+    e.s = ends ? 0 : (t.nheads ? t.post : t.pre);
+    return e;
+  };
+  HS agg; agg.h = 0; agg.s = 0;
+  for (u32 t = lo; t < hi; t++) agg = op(agg, elem(tiles[t]));
+  s_hs[tid] = agg;
+  __syncthreads();
+  if (tid == 0) {   // serial exclusive scan over <= 1024 chunk aggregates
+    HS run; run.h = 0; run.s = 0;
+    for (int k = 0; k < nt; k++) { HS v = s_hs[k]; s_hs[k] = run; run = op(run, v); }
+  }
+  __syncthreads();
+  HS cur = s_hs[tid];
+  u32 cnt = 0;
+  for (u32 t = lo; t < hi; t++) {
+    const RbkTile tl = tiles[t];
+    const i64 cin = cur.s;   // weight of the run open at the tile's first row (0 if none)
+    carry[t].carry_in = cin;
+    const bool ends_here = tl.nheads || tl.closed_last;
+    cnt += tl.inner_kept + ((ends_here && (i64)((u64)cin + (u64)tl.pre) != 0) ? 1u : 0u);
+    cur = op(cur, elem(tl));
+  }
+  s_cnt[tid] = cnt;
+  __syncthreads();
+  if (tid == 0) {
+    u32 run = 0;
+    for (int k = 0; k < nt; k++) { u32 v = s_cnt[k]; s_cnt[k] = run; run += v; }
+    *total_out = run;
+  }
+  __syncthreads();
+  u32 base = s_cnt[tid];
+  cur = s_hs[tid];
+  for (u32 t = lo; t < hi; t++) {
+    const RbkTile tl = tiles[t];
+    carry[t].out_base = base;
+    const i64 cin = cur.s;
+    const bool ends_here = tl.nheads || tl.closed_last;
+    base += tl.inner_kept + ((ends_here && (i64)((u64)cin + (u64)tl.pre) != 0) ? 1u : 0u);
+    cur = op(cur, elem(tl));
+  }
+}
+
 inline int bits_for(u64 range) { return range == 0 ? 0 : 64 - __builtin_clzll(range); }
 
 }  // namespace
@@ -336,38 +576,34 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
     return DBSP_OK;
   }
 
-  // duplicates and/or zero weights: segmented sum over runs of equal rows
-  ProfScope pseg(ctx, KID_SEG_REDUCE, n * (u64)(L + 1) * 8 * 2);
-  BufP fbuf, wbuf, sbuf;
-  TRY(dev_alloc(ctx, (size_t)(n + 1) * 4 * 2, &fbuf));
-  TRY(dev_alloc(ctx, (size_t)n * 8 * 2, &wbuf));
-  u32* flags = (u32*)fbuf->p;
-  u32* exscan = flags + (n + 1);
-  i64* ws = (i64*)wbuf->p;
-  i64* P = ws + n;
-  k_heads<<<nblk + 1, TB, 0, st>>>(cols, L, p.use_key, key_sorted, idx_cur, w, n, flags, ws, nullptr);
-  LAUNCH_COUNT(ctx);
-  TRY(exclusive_scan_u32(ctx, flags, exscan, n));
-  TRY(inclusive_scan_i64(ctx, ws, P, n));
-  u32 nseg;
-  TRY(read_back32(ctx, exscan + n, &nseg));
-  TRY(dev_alloc(ctx, (size_t)(nseg + 1) * (4 + 4 + 4 + 8) + 64, &sbuf));
-  i64* sums = (i64*)sbuf->p;
-  u32* segstart = (u32*)(sums + (nseg + 1));
-  u32* keep = segstart + (nseg + 1);
-  u32* pos = keep + (nseg + 1);
-  k_seg_start<<<nblk, TB, 0, st>>>(flags, exscan, n, segstart, nseg);
-  unsigned sblk = (nseg + 1 + TB - 1) / TB;
-  k_seg_sum<<<sblk, TB, 0, st>>>(P, segstart, nseg, keep, sums);
-  ctx->kernel_launches += 2;
-  TRY(exclusive_scan_u32(ctx, keep, pos, nseg));
+  // duplicates and/or zero weights: fused reduce-by-key over the sorted order
+  const u32 ntiles = (u32)((n + RBK_TILE - 1) / RBK_TILE);
+  BufP tbuf;
+  TRY(dev_alloc(ctx, (size_t)ntiles * (sizeof(RbkTile) + sizeof(RbkCarry)) + 64, &tbuf));
+  RbkTile* tiles = (RbkTile*)tbuf->p;
+  RbkCarry* carry = (RbkCarry*)(tiles + ntiles);
+  u32* d_total = (u32*)(carry + ntiles);
+  MCols none;
+  for (int l = 0; l < MAXL; l++) none.c[l] = nullptr;
+  long pidx;
+  {
+    ProfScope pseg(ctx, KID_SEG_REDUCE, 0);
+    pidx = pseg.idx;
+    k_rbk<0><<<ntiles, RBK_THREADS, 0, st>>>(cols, p, key_sorted, idx_cur, w, n, tiles, nullptr, none, nullptr);
+    k_rbk_scan<<<1, 1024, 0, st>>>(tiles, ntiles, carry, d_total);
+    ctx->kernel_launches += 2;
+  }
   u32 nout;
-  TRY(read_back32(ctx, pos + nseg, &nout));
+  TRY(read_back32(ctx, d_total, &nout));
   if (nout == 0) { *out = batch_new_empty(ctx, s); return DBSP_OK; }
   Batch* b;
   TRY(batch_alloc(ctx, s, nout, &b, &oc, &ow));
-  k_emit_seg<<<sblk, TB, 0, st>>>(cols, p, key_sorted, idx_cur, segstart, keep, pos, sums, nseg, oc, ow);
+  {
+    ProfScope pseg(ctx, KID_SEG_REDUCE, n * (u64)(L + 1) * 8 * 2 + (u64)nout * (L + 1) * 8);
+    k_rbk<1><<<ntiles, RBK_THREADS, 0, st>>>(cols, p, key_sorted, idx_cur, w, n, tiles, carry, oc, ow);
+  }
   LAUNCH_COUNT(ctx);
+  (void)pidx;
   *out = b;
   return DBSP_OK;
 }

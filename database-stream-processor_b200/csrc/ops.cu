@@ -67,8 +67,8 @@ __device__ __forceinline__ bool project(const dbsp_proj& p, const Env& e, u64* r
 // ordered on the output key (id-ordered event tables, monotone projections)
 // reach the sort-free path of consolidate_rows.
 constexpr int PROJ_ROWS = TB * 4;
-__global__ void k_project_rows(Cols in, int nk_in, int n_in_lanes, const i64* w, u64 n, dbsp_proj proj, int phase,
-                               u32* blk_cnt, const u32* blk_base, MCols out, i64* out_w) {
+__global__ void k_project_rows(Cols in, int nk_in, int n_in_lanes, unsigned used_mask, const i64* w, u64 n,
+                               dbsp_proj proj, int phase, u32* blk_cnt, const u32* blk_base, MCols out, i64* out_w) {
   __shared__ u32 s_warp[TB / 32];
   u64 base = (u64)blockIdx.x * PROJ_ROWS;
   u32 run = phase ? blk_base[blockIdx.x] : 0;
@@ -77,7 +77,7 @@ __global__ void k_project_rows(Cols in, int nk_in, int n_in_lanes, const i64* w,
     u64 lanes[MAXL], row[MAXL];
     bool ok = false;
     if (i < n) {
-      for (int l = 0; l < n_in_lanes; l++) lanes[l] = in.c[l][i];
+      for (int l = 0; l < n_in_lanes; l++) lanes[l] = ((used_mask >> l) & 1) ? in.c[l][i] : 0;   // untouched columns are never read
       Env e{lanes, lanes + nk_in, lanes + nk_in};
       ok = project(proj, e, row);
     }
@@ -474,18 +474,21 @@ int32_t compact_ordered(Ctx* ctx, const dbsp_schema& s, const Cols& in, const i6
   return DBSP_OK;
 }
 
-// number of distinct input lanes the closure reads (algorithmic bytes)
-static int used_lanes(const dbsp_proj& p, int n_in_lanes) {
+// input lanes the closure reads (bit l = lane l of the (key lanes, val lanes) row)
+unsigned proj_used_mask(const dbsp_proj& p, int nk_in) {
   unsigned mask = 0;
-  auto use = [&](const dbsp_src& s, int nk) {
+  auto use = [&](const dbsp_src& s) {
     if (s.kind == DBSP_SRC_KEY) mask |= 1u << s.idx;
-    else if (s.kind == DBSP_SRC_LVAL || s.kind == DBSP_SRC_RVAL) mask |= 1u << (nk + s.idx);
+    else if (s.kind == DBSP_SRC_LVAL || s.kind == DBSP_SRC_RVAL) mask |= 1u << (nk_in + s.idx);
   };
   int nl = p.out_schema.n_key_lanes + p.out_schema.n_val_lanes;
-  for (int l = 0; l < nl; l++) { use(p.out[l].a, 0); if (p.out[l].op >= DBSP_OP_ADD) use(p.out[l].b, 0); }
-  for (int i = 0; i < p.n_pred; i++) { use(p.pred[i].a, 0); use(p.pred[i].b, 0); }
-  int c = __builtin_popcount(mask);
-  return c > n_in_lanes ? n_in_lanes : c;
+  for (int l = 0; l < nl; l++) { use(p.out[l].a); if (p.out[l].op >= DBSP_OP_ADD) use(p.out[l].b); }
+  for (int i = 0; i < p.n_pred; i++) { use(p.pred[i].a); use(p.pred[i].b); }
+  return mask;
+}
+static int used_lanes(const dbsp_proj& p, int n_in_lanes, int nk_in = 0) {
+  int c = __builtin_popcount(proj_used_mask(p, nk_in) & ((1u << n_in_lanes) - 1));
+  return c;
 }
 
 // project rows of (in cols) through proj, then consolidate.
@@ -495,6 +498,7 @@ int32_t project_and_consolidate(Ctx* ctx, const Cols& in, int nk_in, int n_in_la
   int Lo = os.n_key_lanes + os.n_val_lanes;
   if (n == 0) { *out = batch_new_empty(ctx, os); return DBSP_OK; }
   unsigned g = (unsigned)((n + PROJ_ROWS - 1) / PROJ_ROWS);
+  const unsigned umask = proj_used_mask(proj, nk_in);
   BufP cb;
   TRY(dev_alloc(ctx, (size_t)(g + 1) * 4 * 2, &cb));
   u32* blk_cnt = (u32*)cb->p;
@@ -507,7 +511,7 @@ int32_t project_and_consolidate(Ctx* ctx, const Cols& in, int nk_in, int n_in_la
     ProfScope ps(ctx, KID_PROJECT, 0);
     pidx = ps.idx;
     if (proj.n_pred > 0) {
-      k_project_rows<<<g, TB, 0, ctx->stream>>>(in, nk_in, n_in_lanes, w, n, proj, 0, blk_cnt, nullptr, none, nullptr);
+      k_project_rows<<<g, TB, 0, ctx->stream>>>(in, nk_in, n_in_lanes, umask, w, n, proj, 0, blk_cnt, nullptr, none, nullptr);
       LAUNCH_COUNT(ctx);
       CUDA_TRY(cudaMemsetAsync(blk_cnt + g, 0, 4, ctx->stream));
       TRY(exclusive_scan_u32(ctx, blk_cnt, blk_base, g));
@@ -523,11 +527,11 @@ int32_t project_and_consolidate(Ctx* ctx, const Cols& in, int nk_in, int n_in_la
   TmpRows t;
   TRY(tmp_alloc(ctx, Lo, m, &t));
   {
-    ProfScope ps(ctx, KID_PROJECT, n * (u64)(used_lanes(proj, n_in_lanes) + (w ? 1 : 0)) * 8 + m * (u64)(Lo + 1) * 8);
-    k_project_rows<<<g, TB, 0, ctx->stream>>>(in, nk_in, n_in_lanes, w, n, proj, 1, nullptr, blk_base, t.c, t.w);
+    ProfScope ps(ctx, KID_PROJECT, n * (u64)(used_lanes(proj, n_in_lanes, nk_in) + (w ? 1 : 0)) * 8 + m * (u64)(Lo + 1) * 8);
+    k_project_rows<<<g, TB, 0, ctx->stream>>>(in, nk_in, n_in_lanes, umask, w, n, proj, 1, nullptr, blk_base, t.c, t.w);
   }
   LAUNCH_COUNT(ctx);
-  if (pidx >= 0) ctx->prof[pidx].bytes = proj.n_pred > 0 ? n * (u64)used_lanes(proj, n_in_lanes) * 8 : 0;
+  if (pidx >= 0) ctx->prof[pidx].bytes = proj.n_pred > 0 ? n * (u64)used_lanes(proj, n_in_lanes, nk_in) * 8 : 0;
   return consolidate_rows(ctx, os, t.cc(), t.w, m, &t.buf, out);
 }
 

@@ -6,6 +6,7 @@
 #include "common.cuh"
 
 int32_t compact_ordered(Ctx* ctx, const dbsp_schema& s, const Cols& in, const i64* w, const u32* keep, u64 n, Batch** out);
+unsigned proj_used_mask(const dbsp_proj& p, int nk_in);
 int32_t project_and_consolidate(Ctx* ctx, const Cols& in, int nk_in, int n_in_lanes, const i64* w, u64 n,
                                 const dbsp_proj& proj, Batch** out);
 int32_t op_join_delta_trace(Ctx* ctx, const Batch* delta, const Spine* trace, const dbsp_proj* proj, int delta_is_left,
