@@ -7,6 +7,18 @@ namespace {
 
 constexpr int TB = 256;
 
+// up to MAX_REFS spine batches passed to a kernel by value
+struct BatchRef {
+  Cols c;
+  const i64* w;
+  u64 n;
+};
+constexpr int MAX_REFS = 16;
+struct BatchRefs {
+  BatchRef b[MAX_REFS];
+  int nb;
+};
+
 // ---------------- declarative row expressions on the device ------------------
 struct Env {
   const u64* key;
@@ -100,75 +112,88 @@ __global__ void k_project_rows(Cols in, int nk_in, int n_in_lanes, unsigned used
 }
 
 // ---------------- delta x trace probes -----------------------------------------
-// For every delta row: [lo, lo+cnt) = rows of batch T whose first nk lanes
-// equal the delta row's first nk lanes (binary search, the `seek_key` of
-// cursor/mod.rs + advance.rs, once per delta row per trace batch).
-__global__ void k_probe_ranges(Cols D, u64 nd, Cols T, u64 nt, int nk, Flips f, u32* lo_out, u32* cnt_out) {
+// Per *distinct* delta key (delta rows are sorted, so a key's rows are one
+// segment [kstart[k], kstart[k+1])) and per trace batch: the range of trace rows
+// carrying that key — lower bound by bisection, upper bound by galloping (the
+// `seek_key` of cursor/mod.rs + advance.rs:25-72).  One search per key instead of
+// one per row; all spine batches in one launch.
+__global__ void k_probe_keys(Cols D, const u64* kstart, u64 nkeys, BatchRefs tr, int nk, Flips f, u32* lo_out,
+                             u32* cnt_out, u32* ktot) {
+  u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nkeys) return;
+  const u64 row = kstart[k];
+  u64 q[MAXL];
+  for (int l = 0; l < nk; l++) q[l] = D.c[l][row] ^ f.f[l];
+  u32 tot = 0;
+  for (int b = 0; b < tr.nb; b++) {
+    const Cols& T = tr.b[b].c;
+    const u64 nt = tr.b[b].n;
+    u64 lo = lower_bound_q(T, 0, nt, q, nk, f);
+    u64 hi = lo, step = 1;
+    while (hi + step <= nt && cmp_row_q(T, hi + step - 1, q, nk, f) == 0) { hi += step; step <<= 1; }
+    u64 top = hi + step <= nt ? hi + step : nt;
+    hi = upper_bound_q(T, hi, top, q, nk, f);
+    lo_out[k * tr.nb + b] = (u32)lo;
+    cnt_out[k * tr.nb + b] = (u32)(hi - lo);
+    tot += (u32)(hi - lo);
+  }
+  ktot[k] = tot;
+}
+
+// matches of every delta row = matches of its key; also the row -> key index
+__global__ void k_row_counts(const u32* head_exscan, const u32* ktot, u64 nd, u32* rowcnt, u32* ki) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i > nd) return;
-  if (i == nd) { cnt_out[nd] = 0; return; }
-  u64 q[MAXL];
-  for (int l = 0; l < nk; l++) q[l] = D.c[l][i] ^ f.f[l];
-  u64 lo = lower_bound_q(T, 0, nt, q, nk, f);
-  // a key's value group is short: gallop from lo (advance.rs:25-72) instead of
-  // a second full-range bisection
-  u64 hi = lo, step = 1;
-  while (hi + step <= nt && cmp_row_q(T, hi + step - 1, q, nk, f) == 0) { hi += step; step <<= 1; }
-  u64 top = hi + step <= nt ? hi + step : nt;
-  hi = upper_bound_q(T, hi, top, q, nk, f);
-  lo_out[i] = (u32)lo;
-  cnt_out[i] = (u32)(hi - lo);
+  if (i == nd) { rowcnt[nd] = 0; return; }
+  u32 k = head_exscan[i + 1] - 1;   // inclusive head count - 1
+  ki[i] = k;
+  rowcnt[i] = ktot[k];
 }
 
-// gather the per-batch match totals (last entry of each scanned count array)
-__global__ void k_gather_totals(const u32* base, u64 per, u64 off, int nb, u64* out) {
-  int b = threadIdx.x;
-  if (b < nb) out[b] = base[per * b + off];
-}
-
-// Expand the matches: output slot o -> (delta row i, trace row lo[i] + j).
-// proj_mode 1: join_func(k, v1, v2) with filter (join.rs:751-787), weight w1*w2;
-// proj_mode 0: copy the trace row (gather of a key group, weight = trace weight).
-__global__ void k_probe_fill(Cols D, const i64* wD, u64 nd, Cols T, const i64* wT, int nk, int nvD, int nvT,
-                             const u32* lo, const u32* exscan, u64 total, int proj_mode, int delta_is_left,
-                             dbsp_proj proj, MCols out, i64* out_w) {
+// Expand the matches: output slot o -> (delta row i, batch b, trace row).  Slots
+// are ordered by (delta row, batch, trace row): for a monotone join_func and keys
+// that live in a single batch that is already the output order, so consolidation
+// needs no sort.  proj_mode 1: join_func(k, v1, v2) with filter
+// (join.rs:751-787), weight w1*w2, rejected rows keep their slot with weight 0;
+// proj_mode 0: copy the trace row (gather of a key group).
+__global__ void k_probe_fill(Cols D, const i64* wD, u64 nd, BatchRefs tr, int nk, int nvD, int nvT, const u32* lo,
+                             const u32* cnt, const u32* ki, const u32* exscan, u64 total, int proj_mode,
+                             int delta_is_left, dbsp_proj proj, MCols out, i64* out_w) {
   u64 o = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  bool ok = false;
+  if (o >= total) return;
+  // largest i with exscan[i] <= o
+  u64 a = 0, b = nd;
+  while (b - a > 1) {
+    u64 mid = (a + b) >> 1;
+    if (exscan[mid] <= o) a = mid; else b = mid;
+  }
+  const u64 i = a;
+  u32 r = (u32)(o - exscan[i]);
+  const u64 kbase = (u64)ki[i] * tr.nb;
+  int bb = 0;
+  while (bb < tr.nb - 1 && r >= cnt[kbase + bb]) { r -= cnt[kbase + bb]; bb++; }
+  const Cols& T = tr.b[bb].c;
+  const u64 t = (u64)lo[kbase + bb] + r;
   u64 row[MAXL];
-  i64 wout = 0;
-  int nl_out = 0;
-  if (o < total) {
-    // largest i with exscan[i] <= o
-    u64 a = 0, b = nd;
-    while (b - a > 1) {
-      u64 mid = (a + b) >> 1;
-      if (exscan[mid] <= o) a = mid; else b = mid;
-    }
-    u64 i = a, t = (u64)lo[i] + (o - exscan[i]);
-    if (proj_mode == 0) {
-      nl_out = nk + nvT;
-      for (int l = 0; l < nl_out; l++) row[l] = T.c[l][t];
-      wout = wT[t];
-      ok = true;
-    } else {
-      u64 key[MAXL], dv[MAXL], tv[MAXL];
-      for (int l = 0; l < nk; l++) key[l] = D.c[l][i];
-      for (int l = 0; l < nvD; l++) dv[l] = D.c[nk + l][i];
-      for (int l = 0; l < nvT; l++) tv[l] = T.c[nk + l][t];
-      Env e = delta_is_left ? Env{key, dv, tv} : Env{key, tv, dv};
-      ok = project(proj, e, row);
-      nl_out = proj.out_schema.n_key_lanes + proj.out_schema.n_val_lanes;
-      wout = (i64)((u64)wD[i] * (u64)wT[t]);
-    }
+  i64 wout;
+  int nl_out;
+  bool ok = true;
+  if (proj_mode == 0) {
+    nl_out = nk + nvT;
+    for (int l = 0; l < nl_out; l++) row[l] = T.c[l][t];
+    wout = tr.b[bb].w[t];
+  } else {
+    u64 key[MAXL], dv[MAXL], tv[MAXL];
+    for (int l = 0; l < nk; l++) key[l] = D.c[l][i];
+    for (int l = 0; l < nvD; l++) dv[l] = D.c[nk + l][i];
+    for (int l = 0; l < nvT; l++) tv[l] = T.c[nk + l][t];
+    Env e = delta_is_left ? Env{key, dv, tv} : Env{key, tv, dv};
+    ok = project(proj, e, row);
+    nl_out = proj.out_schema.n_key_lanes + proj.out_schema.n_val_lanes;
+    wout = (i64)((u64)wD[i] * (u64)tr.b[bb].w[t]);
   }
-  // Ordered output: slot o keeps its place; a row rejected by the join filter
-  // stays as a zero-weight row, which consolidation drops.  For a monotone
-  // join_func the slots are already in output order (delta rows ascending,
-  // trace rows ascending within a key), so no sort is needed afterwards.
-  if (o < total) {
-    for (int l = 0; l < nl_out; l++) out.c[l][o] = row[l];
-    out_w[o] = ok ? wout : 0;
-  }
+  for (int l = 0; l < nl_out; l++) out.c[l][o] = row[l];
+  out_w[o] = ok ? wout : 0;
 }
 
 // Sum over one trace batch of the weight of the *exact* row (all L lanes).
@@ -315,16 +340,6 @@ __global__ void k_agg_pick(Cols G, const i64* wG, u64 n, int nk, int nv, int kin
 // value of the key's range; the winner's weight summed over the batches that
 // hold it is CursorList::weight (cursor_list.rs:200-210).  If that sum is zero
 // the extremum was cancelled and the key is flagged for the general path.
-struct BatchRef {
-  Cols c;
-  const i64* w;
-  u64 n;
-};
-constexpr int MAX_REFS = 16;
-struct BatchRefs {
-  BatchRef b[MAX_REFS];
-  int nb;
-};
 __global__ void k_agg_extremum(Cols K, u64 nkeys, int nk, int nv, BatchRefs tr, Flips f, int is_max, u32* keep,
                                MCols outv, u64* slow_counter) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -537,76 +552,102 @@ int32_t project_and_consolidate(Ctx* ctx, const Cols& in, int nk_in, int n_in_la
 
 // Probe `delta` against every batch of `trace` and expand the matches.
 // proj == nullptr: gather the matching trace rows unchanged.
-static int32_t probe_spine(Ctx* ctx, const Batch* delta, int nk, const Spine* trace, const dbsp_proj* proj,
-                           int delta_is_left, const dbsp_schema& out_schema, Batch** out) {
+// key segment starts of the first nk lanes: kstart[nkeys+1] (u64 row indices),
+// plus the exclusive scan of the head flags (u32[n+1]) used for row -> key.
+static int32_t key_segments(Ctx* ctx, const Batch* b, int nk, BufP* kstart, BufP* head_ex, u64* nkeys) {
+  BufP fb;
+  TRY(dev_alloc(ctx, (size_t)(b->n + 1) * 4, &fb));
+  TRY(dev_alloc(ctx, (size_t)(b->n + 1) * 4, head_ex));
+  u32* flags = (u32*)fb->p;
+  u32* pos = (u32*)(*head_ex)->p;
+  k_key_heads<<<blocks(b->n + 1), TB, 0, ctx->stream>>>(b->cols(), b->n, nk, flags);
+  LAUNCH_COUNT(ctx);
+  TRY(exclusive_scan_u32(ctx, flags, pos, b->n));
+  u32 nkk;
+  TRY(read_back32(ctx, pos + b->n, &nkk));
+  TRY(dev_alloc(ctx, (size_t)(nkk + 1) * 8, kstart));
+  k_scatter_index<<<blocks(b->n), TB, 0, ctx->stream>>>(flags, pos, b->n, (u64*)(*kstart)->p, nkk);
+  LAUNCH_COUNT(ctx);
+  *nkeys = nkk;
+  return DBSP_OK;
+}
+
+// Probe `delta` against (up to MAX_REFS) batches of `trace` and expand the matches.
+// proj == nullptr: gather the matching trace rows unchanged.
+static int32_t probe_chunk(Ctx* ctx, const Batch* delta, int nk, Batch* const* tb, int nb, const dbsp_proj* proj,
+                           int delta_is_left, const dbsp_schema& out_schema, const u64* kstart, const u32* head_ex,
+                           u64 nkeys, Batch** out) {
   cudaStream_t st = ctx->stream;
-  u64 nd = delta->n;
-  size_t nb = trace->batches.size();
-  if (nd == 0 || nb == 0) { *out = batch_new_empty(ctx, out_schema); return DBSP_OK; }
+  const u64 nd = delta->n;
   Flips f = delta->flips();
-  // per batch: lo[nd], cnt[nd+1], exscan[nd+1]
-  BufP pb;
-  size_t per = (size_t)(nd + 1) * 3;
-  TRY(dev_alloc(ctx, per * 4 * nb, &pb));
-  std::vector<u64> totals(nb);
-  u64 grand = 0;
-  for (size_t b = 0; b < nb; b++) {
-    const Batch* T = trace->batches[b];
-    u32* lo = (u32*)pb->p + per * b;
-    u32* cnt = lo + (nd + 1);
-    u32* ex = cnt + (nd + 1);
-    {
-      u64 lg = 1; while ((1ull << lg) < T->n + 1) lg++;
-      ProfScope ps(ctx, KID_PROBE_RANGES, nd * ((u64)nk * 8 + 8 + 2 * lg * (u64)std::max(nk, 1) * 8));
-      k_probe_ranges<<<blocks(nd + 1), TB, 0, st>>>(delta->cols(), nd, T->cols(), T->n, nk, f, lo, cnt);
-    }
-    LAUNCH_COUNT(ctx);
-    TRY(exclusive_scan_u32(ctx, cnt, ex, nd));
+  BatchRefs refs;
+  refs.nb = nb;
+  u64 trace_rows = 0;
+  for (int b = 0; b < nb; b++) {
+    refs.b[b].c = tb[b]->cols();
+    refs.b[b].w = tb[b]->w;
+    refs.b[b].n = tb[b]->n;
+    trace_rows += tb[b]->n;
   }
-  for (size_t b0 = 0; b0 < nb; b0 += 64) {   // one read-back for (up to 64) batch totals
-    int cnt = (int)std::min<size_t>(64, nb - b0);
-    k_gather_totals<<<1, 64, 0, st>>>((const u32*)pb->p + per * b0, per, 2 * (nd + 1) + nd, cnt, ctx->d_scratch + 128);
-    LAUNCH_COUNT(ctx);
-    u64 tt[64];
-    TRY(read_back(ctx, ctx->d_scratch + 128, cnt, tt));
-    for (int b = 0; b < cnt; b++) { totals[b0 + b] = tt[b]; grand += tt[b]; }
+  BufP kb, rb;
+  TRY(dev_alloc(ctx, (size_t)nkeys * nb * 4 * 2 + (size_t)nkeys * 4, &kb));
+  u32* lo = (u32*)kb->p;
+  u32* cnt = lo + (size_t)nkeys * nb;
+  u32* ktot = cnt + (size_t)nkeys * nb;
+  TRY(dev_alloc(ctx, (size_t)(nd + 1) * 4 * 3, &rb));
+  u32* rowcnt = (u32*)rb->p;
+  u32* ex = rowcnt + (nd + 1);
+  u32* ki = ex + (nd + 1);
+  {
+    // delta keys read once, ranges written once; every bisection step touches one
+    // trace key row (bounded by the trace's key bytes)
+    u64 lg = 1; while ((1ull << lg) < trace_rows / std::max(nb, 1) + 1) lg++;
+    u64 touched = std::min<u64>(nkeys * (u64)nb * 2 * lg, trace_rows) * (u64)std::max(nk, 1) * 8;
+    ProfScope ps(ctx, KID_PROBE_RANGES, nkeys * ((u64)nk * 8 + (u64)nb * 8 + 4) + touched);
+    k_probe_keys<<<blocks(nkeys), TB, 0, st>>>(delta->cols(), kstart, nkeys, refs, nk, f, lo, cnt, ktot);
   }
-  if (grand == 0) { *out = batch_new_empty(ctx, out_schema); return DBSP_OK; }
+  k_row_counts<<<blocks(nd + 1), TB, 0, st>>>(head_ex, ktot, nd, rowcnt, ki);
+  ctx->kernel_launches += 2;
+  TRY(exclusive_scan_u32(ctx, rowcnt, ex, nd));
+  u32 total;
+  TRY(read_back32(ctx, ex + nd, &total));
+  if (total == 0) { *out = batch_new_empty(ctx, out_schema); return DBSP_OK; }
   int Lo = out_schema.n_key_lanes + out_schema.n_val_lanes;
   dbsp_proj pj;
   if (proj) pj = *proj; else memset(&pj, 0, sizeof(pj));
-  // One ordered run per trace batch, consolidated on its own (usually without a
-  // sort), then the runs are merged — the Batcher of join.rs:845-858.
-  Batch* acc = nullptr;
-  for (size_t b = 0; b < nb; b++) {
-    if (!totals[b]) continue;
-    const Batch* T = trace->batches[b];
-    u32* lo = (u32*)pb->p + per * b;
-    u32* ex = lo + 2 * (nd + 1);
-    TmpRows t;
-    TRY(tmp_alloc(ctx, Lo, totals[b], &t));
-    {
-      // matched trace rows read once, delta rows read once, output rows written once
-      ProfScope ps(ctx, KID_PROBE_FILL, totals[b] * (u64)(T->nl() - nk + 1) * 8 + nd * (u64)(delta->nl() + 1) * 8 +
-                                            totals[b] * (u64)(Lo + 1) * 8);
-      k_probe_fill<<<blocks(totals[b]), TB, 0, st>>>(delta->cols(), delta->w, nd, T->cols(), T->w, nk,
-                                                     delta->nl() - nk, T->nl() - nk, lo, ex, totals[b], proj ? 1 : 0,
-                                                     delta_is_left, pj, t.c, t.w);
-    }
-    LAUNCH_COUNT(ctx);
-    Batch* run = nullptr;
-    int32_t rc = consolidate_rows(ctx, out_schema, t.cc(), t.w, totals[b], &t.buf, &run);
-    if (rc) { if (acc) batch_unref(acc); return rc; }
-    if (!acc) { acc = run; continue; }
-    Batch* m = nullptr;
-    rc = merge_batches(ctx, acc, run, &m);
-    batch_unref(acc);
-    batch_unref(run);
-    if (rc) return rc;
-    acc = m;
+  TmpRows t;
+  TRY(tmp_alloc(ctx, Lo, total, &t));
+  {
+    // matched trace rows read once, delta rows read once, output rows written once
+    ProfScope ps(ctx, KID_PROBE_FILL, (u64)total * (u64)(tb[0]->nl() - nk + 1) * 8 + nd * (u64)(delta->nl() + 1) * 8 +
+                                          (u64)total * (u64)(Lo + 1) * 8);
+    k_probe_fill<<<blocks(total), TB, 0, st>>>(delta->cols(), delta->w, nd, refs, nk, delta->nl() - nk, tb[0]->nl() - nk, lo,
+                                               cnt, ki, ex, total, proj ? 1 : 0, delta_is_left, pj, t.c, t.w);
   }
-  *out = acc ? acc : batch_new_empty(ctx, out_schema);
-  return DBSP_OK;
+  LAUNCH_COUNT(ctx);
+  // the Batcher of join.rs:845-858: usually sort-free (ordered slots)
+  return consolidate_rows(ctx, out_schema, t.cc(), t.w, total, &t.buf, out);
+}
+
+static int32_t merge_tree(Ctx* ctx, std::vector<Batch*>& parts, const dbsp_schema& s, Batch** out);
+
+static int32_t probe_spine(Ctx* ctx, const Batch* delta, int nk, const Spine* trace, const dbsp_proj* proj,
+                           int delta_is_left, const dbsp_schema& out_schema, Batch** out) {
+  const size_t nb = trace->batches.size();
+  if (delta->n == 0 || nb == 0) { *out = batch_new_empty(ctx, out_schema); return DBSP_OK; }
+  BufP kstart, head_ex;
+  u64 nkeys;
+  TRY(key_segments(ctx, delta, nk, &kstart, &head_ex, &nkeys));
+  std::vector<Batch*> parts;
+  for (size_t b0 = 0; b0 < nb; b0 += MAX_REFS) {
+    int cnt = (int)std::min<size_t>(MAX_REFS, nb - b0);
+    Batch* part = nullptr;
+    int32_t rc = probe_chunk(ctx, delta, nk, trace->batches.data() + b0, cnt, proj, delta_is_left, out_schema,
+                             (const u64*)kstart->p, (const u32*)head_ex->p, nkeys, &part);
+    if (rc) { for (Batch* p : parts) batch_unref(p); return rc; }
+    parts.push_back(part);
+  }
+  return merge_tree(ctx, parts, out_schema, out);
 }
 
 // JoinTrace::eval (operator/join.rs:732-863)
