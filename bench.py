@@ -162,6 +162,7 @@ def run_b200(args, query, rank, world, comm, device, do_e2e=True):
         return float(t.item())
 
     # ---- (1) device-resident inputs -------------------------------------------
+    os.environ.setdefault("DBSP_POOL_RESERVE_GB", "24")   # pool growth (cudaMalloc of slabs) stays out of the timed region
     be = Runtime(device.index)
     ext = torch.cuda.ExternalStream(be.stream_ptr, device=device)
     dev_steps = []
@@ -291,9 +292,17 @@ def merge_sweep(device_index, rows=50_000_000):
     peak, how = peaks()
     p = prof["merge_tiles"]
     ach = p["alg_bytes"] / (p["ms"] / 1e3) / 1e9
+    traffic = None
+    try:   # dram__bytes_read+write of one launch from the committed ncu --set full capture (2 x 20 M rows), scaled by rows
+        prof_j = json.load(open(os.path.join(ROOT, "profiles", "r1_merge_tiles_ncu_full.json")))
+        mb = float(prof_j["dram__bytes_read.sum"].split()[0]) + float(prof_j["dram__bytes_write.sum"].split()[0])
+        traffic = mb * 1e6 * (len(a) + len(b)) / 40_000_000
+    except Exception:
+        pass
     return {"workload": f"merge 2 x OrdIndexedZSet<u64,u64,i64>, {len(a)}+{len(b)} rows -> {len(m)}", "rows_per_s": (len(a) + len(b)) / (p["ms"] / 5 / 1e3),
             "roofline": {"bound": "hbm", "kernel": "merge_tiles", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "avg_launch_us": 1e3 * p["ms"] / p["launches"], "peak_source": how},
+                         "traffic": traffic, "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum, profiles/r1_merge_tiles_ncu_full.json (2x20M-row launch) scaled by rows",
+                         "alg_bytes_per_launch": p["alg_bytes"] / p["launches"], "avg_launch_us": 1e3 * p["ms"] / p["launches"], "peak_source": how},
             "inputs_larger_than_l2": True}
 
 

@@ -1,6 +1,8 @@
 // capi.cu — the extern "C" boundary declared in include/dbsp_b200.h, plus the
 // host-side Spine (trace) logic.  No CPU compute path lives here: every
 // data-touching call launches kernels from consolidate.cu / merge.cu / ops.cu.
+#include <cstdlib>
+
 #include "ops.cuh"
 
 const char* get_error();
@@ -121,6 +123,20 @@ int32_t dbsp_ctx_create(int32_t device, dbsp_ctx** out) {
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
+  // optional up-front pool reservation (GiB) so that slab growth never lands
+  // inside a timed region: DBSP_POOL_RESERVE_GB
+  if (const char* e = getenv("DBSP_POOL_RESERVE_GB")) {
+    double gb = atof(e);
+    if (gb > 0) {
+      std::vector<BufP> hold;   // released together at the end of this scope: the slabs stay pooled
+      size_t bytes = (size_t)(gb * 1073741824.0);
+      for (size_t done = 0; done < bytes; done += ((size_t)8 << 30)) {
+        BufP x;
+        if (dev_alloc(c, std::min<size_t>((size_t)8 << 30, bytes - done), &x) != DBSP_OK) break;
+        hold.push_back(x);
+      }
+    }
+  }
   *out = c;
   return DBSP_OK;
 }
