@@ -432,17 +432,41 @@ __device__ __forceinline__ u64 mix64(u64 x) {
   x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
   return x ^ (x >> 31);
 }
-// shard_batch (communication/shard.rs:165-199): keep[i] = hash(key) % P == p
-__global__ void k_shard_flags(Cols B, u64 n, int nk, u32 P, u32 p, u32* keep) {
+// shard_batch (communication/shard.rs:165-199): flags[p*(n+1) + i] = (hash(key) % P == p).
+// One exclusive scan over the concatenated flag arrays is a *stable* P-way
+// partition: shard p's rows follow shard p-1's, each shard keeps its order.
+__global__ void k_shard_flags(Cols B, u64 n, int nk, u32 P, u32* flags) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
-  if (i == n) { keep[n] = 0; return; }
-  u64 h = 0;
-  for (int l = 0; l < nk; l++) h = mix64(h ^ B.c[l][i]);
-  keep[i] = (u32)(h % P) == p ? 1u : 0u;
+  u32 dest = P;   // i == n: terminator slot of every shard
+  if (i < n) {
+    u64 h = 0;
+    for (int l = 0; l < nk; l++) h = mix64(h ^ B.c[l][i]);
+    dest = (u32)(h % P);
+  }
+  for (u32 p = 0; p < P; p++) flags[(u64)p * (n + 1) + i] = (p == dest) ? 1u : 0u;
+}
+__global__ void k_shard_scatter(Cols in, int L, const i64* w, const u32* flags, const u32* pos, u64 n, u32 P, MCols out,
+                                i64* out_w, u64* bounds) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P) bounds[i] = pos[i * (n + 1)];           // first output slot of shard i
+  if (i == P) bounds[P] = pos[(u64)P * (n + 1) - 1]; // total (= n)
+  if (i >= n) return;
+  for (u32 p = 0; p < P; p++) {
+    u64 j = (u64)p * (n + 1) + i;
+    if (flags[j]) {
+      u32 o = pos[j];
+      for (int l = 0; l < L; l++) out.c[l][o] = in.c[l][i];
+      out_w[o] = w[i];
+    }
+  }
 }
 
 inline unsigned blocks(u64 n) { return (unsigned)((n + TB - 1) / TB); }
+#define CHECK_P(c, msg)                                   \
+  do {                                                    \
+    if (!(c)) { set_error(msg); return DBSP_ERR_INVALID; } \
+  } while (0)
 
 }  // namespace
 
@@ -977,13 +1001,40 @@ int32_t op_shard_partition(Ctx* ctx, const Batch* b, u32 P, Batch** outs) {
     for (u32 p = 0; p < P; p++) outs[p] = batch_new_empty(ctx, b->s);
     return DBSP_OK;
   }
-  BufP kb;
-  TRY(dev_alloc(ctx, (size_t)(b->n + 1) * 4, &kb));
+  const u64 n = b->n;
+  const int L = b->nl();
+  CHECK_P(P <= 64, "shard_partition: at most 64 shards");
+  BufP fb;
+  const u64 m = (u64)P * (n + 1);
+  TRY(dev_alloc(ctx, (size_t)(m + 1) * 4 * 2, &fb));
+  u32* flags = (u32*)fb->p;
+  u32* pos = flags + (m + 1);
+  k_shard_flags<<<blocks(n + 1), TB, 0, ctx->stream>>>(b->cols(), n, b->s.n_key_lanes, P, flags);
+  LAUNCH_COUNT(ctx);
+  CUDA_TRY(cudaMemsetAsync(flags + m, 0, 4, ctx->stream));
+  TRY(exclusive_scan_u32(ctx, flags, pos, m));
+  Batch* all;   // one buffer holding the P shards back to back; the shards are views
+  MCols oc;
+  i64* ow;
+  TRY(batch_alloc(ctx, b->s, n, &all, &oc, &ow));
+  u64* bounds = ctx->d_scratch + 160;
+  k_shard_scatter<<<blocks(std::max<u64>(n, P + 1)), TB, 0, ctx->stream>>>(b->cols(), L, b->w, flags, pos, n, P, oc, ow, bounds);
+  LAUNCH_COUNT(ctx);
+  u64 hb[65];
+  int32_t rc = read_back(ctx, bounds, P + 1, hb);
+  if (rc) { batch_unref(all); return rc; }
   for (u32 p = 0; p < P; p++) {
-    k_shard_flags<<<blocks(b->n + 1), TB, 0, ctx->stream>>>(b->cols(), b->n, b->s.n_key_lanes, P, p, (u32*)kb->p);
-    LAUNCH_COUNT(ctx);
-    TRY(compact_ordered(ctx, b->s, b->cols(), b->w, (u32*)kb->p, b->n, &outs[p]));
+    Batch* v = new Batch();
+    v->s = b->s;
+    v->ctx = ctx;
+    v->n = hb[p + 1] - hb[p];
+    for (int l = 0; l < L; l++) v->col[l] = all->col[l] + hb[p];
+    v->w = all->w + hb[p];
+    v->bufs = all->bufs;
+    if (v->n == 0) v->nkeys = 0;
+    outs[p] = v;
   }
+  batch_unref(all);
   return DBSP_OK;
 }
 

@@ -57,8 +57,9 @@ class Comm:
         dist.all_to_all_single(recv_counts, send_counts, group=self.group)
         rc = recv_counts.tolist()
         segs = []
+        be.sync()   # the partition kernels ran on the library's stream; torch reads the columns on its own
         for p in parts:
-            cols, w = be.batch_flat_tensors(p)
+            cols, w = be.batch_flat_tensors(p, synced=True)
             segs.extend(cols)
             segs.append(w)
         send = torch.cat(segs) if sum(counts) else torch.empty(0, dtype=torch.int64, device=self.device)
@@ -66,13 +67,15 @@ class Comm:
         dist.all_to_all_single(recv, send, output_split_sizes=[c * L1 for c in rc],
                                input_split_sizes=[c * L1 for c in counts], group=self.group)
         self.bytes_sent += (sum(counts) - counts[self.rank]) * L1 * 8
+        if recv.is_cuda:
+            torch.cuda.current_stream(recv.device).synchronize()   # once, before the library adopts the segments
         out, off = [], 0
         for q in range(P):
             n = rc[q]
             seg = recv[off: off + n * L1]
             off += n * L1
             cols = [seg[l * n: (l + 1) * n] for l in range(schema.nl)]
-            out.append(be.batch_from_flat_tensors(schema, cols, seg[schema.nl * n: L1 * n]))
+            out.append(be.batch_from_flat_tensors(schema, cols, seg[schema.nl * n: L1 * n], synced=True))
         return out
 
     @staticmethod

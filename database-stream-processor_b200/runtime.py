@@ -60,7 +60,7 @@ class Runtime(Backend):
         self.api.call("batch_device_columns", b.h, cols, C.byref(w))
         return [cols[i] or 0 for i in range(b.schema.nl)], (w.value or 0)
 
-    def batch_flat_tensors(self, b: Batch):
+    def batch_flat_tensors(self, b: Batch, synced: bool = False):
         import torch
 
         n = len(b)
@@ -68,15 +68,17 @@ class Runtime(Backend):
         dev = torch.device("cuda", self.device)
         if n == 0:
             return [torch.empty(0, dtype=torch.int64, device=dev) for _ in cols], torch.empty(0, dtype=torch.int64, device=dev)
-        self.sync()
+        if not synced:
+            self.sync()
         ts = [torch.as_tensor(_DevArray(p, n, "<i8", b), device=dev) for p in cols]
         return ts, torch.as_tensor(_DevArray(w, n, "<i8", b), device=dev)
 
-    def batch_from_flat_tensors(self, schema: Schema, cols, weights) -> Batch:
+    def batch_from_flat_tensors(self, schema: Schema, cols, weights, synced: bool = False) -> Batch:
         import torch
 
         n = int(weights.numel())
         if n == 0:
             return self.batch_empty(schema)
-        torch.cuda.current_stream(self.device).synchronize()
+        if not synced:
+            torch.cuda.current_stream(self.device).synchronize()
         return self.batch_from_sorted(schema, [int(c.data_ptr()) for c in cols], int(weights.data_ptr()), n, True)

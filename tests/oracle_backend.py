@@ -40,11 +40,11 @@ class OracleBackend(Backend):
         keys = [np.repeat(np.asarray(k).view(np.uint64), counts) for k in d["keys"]]
         return keys + [np.asarray(v).view(np.uint64) for v in d["vals"]], d["diffs"]
 
-    def batch_flat_tensors(self, b: Batch):
+    def batch_flat_tensors(self, b: Batch, synced: bool = False):
         import torch
 
         cols, w = self.flat(b)
         return [torch.from_numpy(c.view(np.int64).copy()) for c in cols], torch.from_numpy(w.copy())
 
-    def batch_from_flat_tensors(self, schema: Schema, cols, weights) -> Batch:
+    def batch_from_flat_tensors(self, schema: Schema, cols, weights, synced: bool = False) -> Batch:
         return self.batch_from_sorted(schema, [c.numpy().view(np.uint64) for c in cols], weights.numpy(), int(weights.numel()), False)
