@@ -18,8 +18,8 @@
 //      preserving, injective) into as few 64-bit words as possible and only
 //      those bits are sorted, as (key word, row id) pairs.  The Nexmark
 //      schemas pack into one word of 30-60 bits.
-//  (4) Epilogue: runs of equal rows are summed with a prefix-sum difference,
-//      zero sums dropped; the duplicate-free case is one unpack/gather pass.
+//  (4) Epilogue: a two-pass reduce-by-key sums runs of equal rows and drops
+//      zero sums; the duplicate-free case is one unpack/gather pass.
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
@@ -157,40 +157,6 @@ __global__ void k_emit_unique(Cols cols, Plan p, const u64* key, const u32* idx,
   }
   out_w[i] = w ? w[r] : 1;
 }
-
-__global__ void k_seg_start(const u32* flags, const u32* exscan, u64 n, u32* segstart, u32 nseg) {
-  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && flags[i]) segstart[exscan[i]] = (u32)i;
-  if (i == 0) segstart[nseg] = (u32)n;
-}
-
-__global__ void k_seg_sum(const i64* P, const u32* segstart, u32 nseg, u32* keep, i64* sums) {
-  u32 s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < nseg) {
-    u32 a = segstart[s], b = segstart[s + 1];
-    i64 sum = (i64)((u64)P[b - 1] - (a ? (u64)P[a - 1] : 0ull));
-    sums[s] = sum;
-    keep[s] = sum != 0 ? 1u : 0u;
-  } else if (s == nseg) {
-    keep[nseg] = 0;
-  }
-}
-
-__global__ void k_emit_seg(Cols cols, Plan p, const u64* key, const u32* idx, const u32* segstart, const u32* keep,
-                           const u32* pos, const i64* sums, u32 nseg, MCols out, i64* out_w) {
-  u32 s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nseg || !keep[s]) return;
-  u32 a = segstart[s], o = pos[s];
-  if (p.use_key) {
-    u64 k = key[a];
-    for (int l = 0; l < p.L; l++) out.c[l][o] = unpack_lane(p, l, k);
-  } else {
-    u64 r = idx ? idx[a] : a;
-    for (int l = 0; l < p.L; l++) out.c[l][o] = cols.c[l][r];
-  }
-  out_w[o] = sums[s];
-}
-
 
 // ---------------------------------------------------------------------------
 // Reduce-by-key over rows that are already in sorted order (identity order, or
@@ -585,10 +551,8 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
   u32* d_total = (u32*)(carry + ntiles);
   MCols none;
   for (int l = 0; l < MAXL; l++) none.c[l] = nullptr;
-  long pidx;
   {
     ProfScope pseg(ctx, KID_SEG_REDUCE, 0);
-    pidx = pseg.idx;
     k_rbk<0><<<ntiles, RBK_THREADS, 0, st>>>(cols, p, key_sorted, idx_cur, w, n, tiles, nullptr, none, nullptr);
     k_rbk_scan<<<1, 1024, 0, st>>>(tiles, ntiles, carry, d_total);
     ctx->kernel_launches += 2;
@@ -603,7 +567,6 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
     k_rbk<1><<<ntiles, RBK_THREADS, 0, st>>>(cols, p, key_sorted, idx_cur, w, n, tiles, carry, oc, ow);
   }
   LAUNCH_COUNT(ctx);
-  (void)pidx;
   *out = b;
   return DBSP_OK;
 }

@@ -418,14 +418,6 @@ __global__ void k_lower_bounds(Cols T, u64 nt, int nk, Flips f, const u64* queri
   out[qi] = lower_bound_q(T, 0, nt, q, nk, f);
 }
 
-__global__ void k_copy_range(Cols T, const i64* wT, int L, u64 lo, u64 cnt, int negate, MCols out, i64* out_w, u64 dst) {
-  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= cnt) return;
-  for (int l = 0; l < L; l++) out.c[l][dst + i] = T.c[l][lo + i];
-  i64 w = wT[lo + i];
-  out_w[dst + i] = negate ? (i64)((u64)0 - (u64)w) : w;
-}
-
 __device__ __forceinline__ u64 mix64(u64 x) {
   x += 0x9e3779b97f4a7c15ull;
   x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
