@@ -20,6 +20,7 @@
 // halo row on each side).  The tile's global output offset comes from a
 // decoupled look-back over per-tile status words (tiles take their index from
 // an atomic ticket, so predecessors are always resident or done).
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -125,107 +126,31 @@ __global__ void k_merge_partition(Cols A, u64 nA, Cols B, u64 nB, Flips f, u32 t
   part[t] = diag_search_g<L>(A, nA, B, nB, f, d);
 }
 
+// Scratch shared by the phases of one tile (static shared memory of the kernel).
+struct TileScratch {
+  u64* s_base;
+  u32* s_warp;
+  int* s_lb_first;
+  u64* s_lb_all;
+  u64* s_lb_upto;
+};
+
+// Everything after staging: per-thread merge path, serial merge, compaction,
+// decoupled look-back, coalesced stores.  `sl`/`sw` hold the staged tile with
+// the slot map of k_merge_tiles (A row a0+i at oa+i, B row b0+j at ob+j).
 template <int L>
-__global__ void __launch_bounds__(MERGE_THREADS)
-k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __restrict__ wB, u64 nB, Flips f,
-              const u64* __restrict__ part, u32 ntiles, u32* ticket, u64* status, MCols O, i64* wO, u64* n_out,
-              int use_tma) {
+__device__ __forceinline__ void merge_process_tile(u64* sl, i64* sw, u32* perm, const int oa, const int ob, const int na,
+                                                   const int nb, const bool has_prev, const bool has_next, const u32 t,
+                                                   const u32 ntiles, u64* status, const MCols& O, i64* wO, u64* n_out,
+                                                   const Flips& f, const TileScratch& sc) {
   constexpr int IPT = MergeCfg<L>::IPT;
-  constexpr int TILE = MergeCfg<L>::TILE;
   constexpr int S = MergeCfg<L>::S;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  u64* sl = (u64*)smem_raw;                 // L lanes of S staged slots
-  i64* sw = (i64*)(sl + (size_t)L * S);     // S weights; reused as output weights
-  u32* perm = (u32*)(sw + S);               // TILE staged-slot indices of kept rows
-  __shared__ __align__(8) u64 s_mbar;
-  __shared__ u32 s_tile;
-  __shared__ u64 s_base;
-  __shared__ u32 s_warp[MERGE_THREADS / 32];
-  __shared__ int s_lb_first[MERGE_THREADS / 32];
-  __shared__ u64 s_lb_all[MERGE_THREADS / 32], s_lb_upto[MERGE_THREADS / 32];
-
   const int tid = threadIdx.x;
-  if (tid == 0) {
-    s_tile = atomicAdd(ticket, 1u);
-    mbar_init(&s_mbar, 1);
-  }
-  __syncthreads();
-  const u32 t = s_tile;
-  const u64 total = nA + nB;
-  const u64 d0 = (u64)t * TILE;
-  const u64 d1 = (d0 + TILE < total) ? d0 + TILE : total;
-  const u64 a0 = part[t], a1 = part[t + 1];
-  const u64 b0 = d0 - a0, b1 = d1 - a1;
-  const int na = (int)(a1 - a0), nb = (int)(b1 - b0);
-  const bool has_prev = a0 > 0, has_next = b1 < nB;
-  bool any_flip = false;
-#pragma unroll
-  for (int l = 0; l < L; l++) any_flip = any_flip || (f.f[l] != 0);
-
-  // ---- stage --------------------------------------------------------------------
-  // Slot map: A row a0+i lives at slot oa+i (i = -1 is the A halo), B row b0+j at
-  // slot ob+j (j = nb is the B halo).  The TMA path copies 16-byte aligned
-  // super-ranges, which fixes oa/ob; the fallback uses oa = 1, ob = 1+na.
-  int oa, ob;
-  if (use_tma) {
-    const long long fa = (long long)a0 - (has_prev ? 1 : 0);          // first A row needed
-    const long long pa = (long long)(((unsigned long long)(size_t)A.c[0]) >> 3) & 1;
-    const long long ga = fa - ((fa + pa) & 1);                        // aligned-down start (may be -1)
-    const long long ea = (long long)a1;                               // end (exclusive)
-    const int ca = (ea > fa) ? (int)(((ea - ga) + 1) & ~1ll) : 0;     // rows copied (even)
-    oa = (int)((long long)a0 - ga);
-    const int sb = (oa + na + 1) & ~1;                                // first slot of the B region (even)
-    const long long eb = (long long)b1 + (has_next ? 1 : 0);
-    const long long pb = (long long)(((unsigned long long)(size_t)B.c[0]) >> 3) & 1;
-    const long long gb = (long long)b0 - (((long long)b0 + pb) & 1);
-    const int cb = (eb > (long long)b0) ? (int)(((eb - gb) + 1) & ~1ll) : 0;
-    ob = sb + (int)((long long)b0 - gb);
-    if (tid == 0) {
-      const unsigned bytes = (unsigned)(ca + cb) * 8u * (L + 1);
-      if (bytes) {
-        mbar_expect_tx(&s_mbar, bytes);
-        if (ca) {
-#pragma unroll
-          for (int l = 0; l < L; l++) tma_bulk_g2s(sl + l * S, A.c[l] + ga, (unsigned)ca * 8u, &s_mbar);
-          tma_bulk_g2s(sw, wA + ga, (unsigned)ca * 8u, &s_mbar);
-        }
-        if (cb) {
-#pragma unroll
-          for (int l = 0; l < L; l++) tma_bulk_g2s(sl + l * S + sb, B.c[l] + gb, (unsigned)cb * 8u, &s_mbar);
-          tma_bulk_g2s(sw + sb, wB + gb, (unsigned)cb * 8u, &s_mbar);
-        }
-      }
-    }
-    if ((ca + cb) > 0) mbar_wait(&s_mbar, 0);
-  } else {
-    oa = 1;
-    ob = 1 + na;
-    const int nslots = na + nb + 2;
-#pragma unroll
-    for (int k = 0; k < IPT + 1; k++) {
-      const int x = tid + k * MERGE_THREADS;
-      if (x < nslots) {
-        const bool from_a = x <= na;
-        const bool skip = (x == 0 && !has_prev) || (x == nslots - 1 && !has_next);
-        if (!skip) {
-          const u64 g = from_a ? (a0 + x - 1) : (b0 + (x - 1 - na));
-#pragma unroll
-          for (int l = 0; l < L; l++) cp_async8(&sl[l * S + x], (from_a ? A.c[l] : B.c[l]) + g);
-          cp_async8(&sw[x], (from_a ? wA : wB) + g);
-        }
-      }
-    }
-    cp_async_wait_all();
-  }
-  if (any_flip) {   // i64 lanes: stage the order-preserving image
-    __syncthreads();
-    for (int x = tid; x < S; x += MERGE_THREADS) {
-#pragma unroll
-      for (int l = 0; l < L; l++) sl[l * S + x] ^= f.f[l];
-    }
-  }
-  __syncthreads();
-
+  u64& s_base = *sc.s_base;
+  u32* s_warp = sc.s_warp;
+  int* s_lb_first = sc.s_lb_first;
+  u64* s_lb_all = sc.s_lb_all;
+  u64* s_lb_upto = sc.s_lb_upto;
   auto le = [&](int ia, int ib) {   // staged row ia <= staged row ib
 #pragma unroll
     for (int l = 0; l < L; l++) {
@@ -398,6 +323,231 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
   }
 }
 
+template <int L>
+__global__ void __launch_bounds__(MERGE_THREADS)
+k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __restrict__ wB, u64 nB, Flips f,
+              const u64* __restrict__ part, u32 ntiles, u32* ticket, u64* status, MCols O, i64* wO, u64* n_out,
+              int use_tma) {
+  constexpr int IPT = MergeCfg<L>::IPT;
+  constexpr int TILE = MergeCfg<L>::TILE;
+  constexpr int S = MergeCfg<L>::S;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  u64* sl = (u64*)smem_raw;                 // L lanes of S staged slots
+  i64* sw = (i64*)(sl + (size_t)L * S);     // S weights; reused as output weights
+  u32* perm = (u32*)(sw + S);               // TILE staged-slot indices of kept rows
+  __shared__ __align__(8) u64 s_mbar;
+  __shared__ u32 s_tile;
+  __shared__ u64 s_base;
+  __shared__ u32 s_warp[MERGE_THREADS / 32];
+  __shared__ int s_lb_first[MERGE_THREADS / 32];
+  __shared__ u64 s_lb_all[MERGE_THREADS / 32], s_lb_upto[MERGE_THREADS / 32];
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    s_tile = atomicAdd(ticket, 1u);
+    mbar_init(&s_mbar, 1);
+  }
+  __syncthreads();
+  const u32 t = s_tile;
+  const u64 total = nA + nB;
+  const u64 d0 = (u64)t * TILE;
+  const u64 d1 = (d0 + TILE < total) ? d0 + TILE : total;
+  const u64 a0 = part[t], a1 = part[t + 1];
+  const u64 b0 = d0 - a0, b1 = d1 - a1;
+  const int na = (int)(a1 - a0), nb = (int)(b1 - b0);
+  const bool has_prev = a0 > 0, has_next = b1 < nB;
+  bool any_flip = false;
+#pragma unroll
+  for (int l = 0; l < L; l++) any_flip = any_flip || (f.f[l] != 0);
+
+  // ---- stage --------------------------------------------------------------------
+  // Slot map: A row a0+i lives at slot oa+i (i = -1 is the A halo), B row b0+j at
+  // slot ob+j (j = nb is the B halo).  The TMA path copies 16-byte aligned
+  // super-ranges, which fixes oa/ob; the fallback uses oa = 1, ob = 1+na.
+  int oa, ob;
+  if (use_tma) {
+    const long long fa = (long long)a0 - (has_prev ? 1 : 0);          // first A row needed
+    const long long pa = (long long)(((unsigned long long)(size_t)A.c[0]) >> 3) & 1;
+    const long long ga = fa - ((fa + pa) & 1);                        // aligned-down start (may be -1)
+    const long long ea = (long long)a1;                               // end (exclusive)
+    const int ca = (ea > fa) ? (int)(((ea - ga) + 1) & ~1ll) : 0;     // rows copied (even)
+    oa = (int)((long long)a0 - ga);
+    const int sb = (oa + na + 1) & ~1;                                // first slot of the B region (even)
+    const long long eb = (long long)b1 + (has_next ? 1 : 0);
+    const long long pb = (long long)(((unsigned long long)(size_t)B.c[0]) >> 3) & 1;
+    const long long gb = (long long)b0 - (((long long)b0 + pb) & 1);
+    const int cb = (eb > (long long)b0) ? (int)(((eb - gb) + 1) & ~1ll) : 0;
+    ob = sb + (int)((long long)b0 - gb);
+    if (tid == 0) {
+      const unsigned bytes = (unsigned)(ca + cb) * 8u * (L + 1);
+      if (bytes) {
+        mbar_expect_tx(&s_mbar, bytes);
+        if (ca) {
+#pragma unroll
+          for (int l = 0; l < L; l++) tma_bulk_g2s(sl + l * S, A.c[l] + ga, (unsigned)ca * 8u, &s_mbar);
+          tma_bulk_g2s(sw, wA + ga, (unsigned)ca * 8u, &s_mbar);
+        }
+        if (cb) {
+#pragma unroll
+          for (int l = 0; l < L; l++) tma_bulk_g2s(sl + l * S + sb, B.c[l] + gb, (unsigned)cb * 8u, &s_mbar);
+          tma_bulk_g2s(sw + sb, wB + gb, (unsigned)cb * 8u, &s_mbar);
+        }
+      }
+    }
+    if ((ca + cb) > 0) mbar_wait(&s_mbar, 0);
+  } else {
+    oa = 1;
+    ob = 1 + na;
+    const int nslots = na + nb + 2;
+#pragma unroll
+    for (int k = 0; k < IPT + 1; k++) {
+      const int x = tid + k * MERGE_THREADS;
+      if (x < nslots) {
+        const bool from_a = x <= na;
+        const bool skip = (x == 0 && !has_prev) || (x == nslots - 1 && !has_next);
+        if (!skip) {
+          const u64 g = from_a ? (a0 + x - 1) : (b0 + (x - 1 - na));
+#pragma unroll
+          for (int l = 0; l < L; l++) cp_async8(&sl[l * S + x], (from_a ? A.c[l] : B.c[l]) + g);
+          cp_async8(&sw[x], (from_a ? wA : wB) + g);
+        }
+      }
+    }
+    cp_async_wait_all();
+  }
+  if (any_flip) {   // i64 lanes: stage the order-preserving image
+    __syncthreads();
+    for (int x = tid; x < S; x += MERGE_THREADS) {
+#pragma unroll
+      for (int l = 0; l < L; l++) sl[l * S + x] ^= f.f[l];
+    }
+  }
+  __syncthreads();
+
+  TileScratch sc{&s_base, s_warp, s_lb_first, s_lb_all, s_lb_upto};
+  merge_process_tile<L>(sl, sw, perm, oa, ob, na, nb, has_prev, has_next, t, ntiles, status, O, wO, n_out, f, sc);
+}
+
+
+// ---- persistent, double-buffered variant -----------------------------------------
+// One CTA per resident slot loops over tiles (atomic ticket).  While tile t is
+// merged out of buffer `st`, the TMA copies of the CTA's next tile already fly
+// into buffer `st^1`, so neither the ticket/partition lookups nor the HBM
+// latency of the staging is exposed.  Needs the TMA path (uniform 16-byte phase).
+template <int L>
+struct PersistCfg {
+  static constexpr int IPT = MergeCfg<L>::IPT;
+  static constexpr int TILE = MergeCfg<L>::TILE;
+  static constexpr int S = MergeCfg<L>::S;
+  static constexpr size_t BUF = (size_t)S * (L + 1) * 8;
+  static constexpr size_t SMEM = 2 * BUF + (size_t)TILE * 4;
+};
+
+template <int L>
+__global__ void __launch_bounds__(MERGE_THREADS)
+k_merge_persist(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __restrict__ wB, u64 nB, Flips f,
+                const u64* __restrict__ part, u32 ntiles, u32* ticket, u64* status, MCols O, i64* wO, u64* n_out) {
+  constexpr int TILE = PersistCfg<L>::TILE;
+  constexpr int S = PersistCfg<L>::S;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  u32* perm = (u32*)(smem_raw + 2 * PersistCfg<L>::BUF);
+  __shared__ __align__(8) u64 s_mbar[2];
+  __shared__ u32 s_next;
+  __shared__ u64 s_base;
+  __shared__ u32 s_warp[MERGE_THREADS / 32];
+  __shared__ int s_lb_first[MERGE_THREADS / 32];
+  __shared__ u64 s_lb_all[MERGE_THREADS / 32], s_lb_upto[MERGE_THREADS / 32];
+  TileScratch sc{&s_base, s_warp, s_lb_first, s_lb_all, s_lb_upto};
+
+  const int tid = threadIdx.x;
+  const u64 total = nA + nB;
+  bool any_flip = false;
+#pragma unroll
+  for (int l = 0; l < L; l++) any_flip = any_flip || (f.f[l] != 0);
+  const long long pa = (long long)(((unsigned long long)(size_t)A.c[0]) >> 3) & 1;
+  const long long pb = (long long)(((unsigned long long)(size_t)B.c[0]) >> 3) & 1;
+
+  // geometry of a tile + (thread 0) issue of its TMA copies into buffer `st`
+  struct Geo { int oa, ob, na, nb; bool has_prev, has_next; };
+  auto stage_tile = [&](u32 t, int st) {
+    Geo g;
+    const u64 d0 = (u64)t * TILE;
+    const u64 d1 = (d0 + TILE < total) ? d0 + TILE : total;
+    const u64 a0 = part[t], a1 = part[t + 1];
+    const u64 b0 = d0 - a0, b1 = d1 - a1;
+    g.na = (int)(a1 - a0);
+    g.nb = (int)(b1 - b0);
+    g.has_prev = a0 > 0;
+    g.has_next = b1 < nB;
+    const long long fa = (long long)a0 - (g.has_prev ? 1 : 0);
+    const long long ga = fa - ((fa + pa) & 1);
+    const int ca = ((long long)a1 > fa) ? (int)((((long long)a1 - ga) + 1) & ~1ll) : 0;
+    g.oa = (int)((long long)a0 - ga);
+    const int sb = (g.oa + g.na + 1) & ~1;
+    const long long eb = (long long)b1 + (g.has_next ? 1 : 0);
+    const long long gb = (long long)b0 - (((long long)b0 + pb) & 1);
+    const int cb = (eb > (long long)b0) ? (int)(((eb - gb) + 1) & ~1ll) : 0;
+    g.ob = sb + (int)((long long)b0 - gb);
+    if (tid == 0) {
+      u64* sl = (u64*)(smem_raw + (size_t)st * PersistCfg<L>::BUF);
+      i64* sw = (i64*)(sl + (size_t)L * S);
+      const unsigned bytes = (unsigned)(ca + cb) * 8u * (L + 1);   // > 0: a tile has at least one row
+      // the buffer was last written through the generic proxy (output weights,
+      // sign flips): order those writes before the async-proxy (TMA) writes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&s_mbar[st], bytes);
+      if (ca) {
+#pragma unroll
+        for (int l = 0; l < L; l++) tma_bulk_g2s(sl + l * S, A.c[l] + ga, (unsigned)ca * 8u, &s_mbar[st]);
+        tma_bulk_g2s(sw, wA + ga, (unsigned)ca * 8u, &s_mbar[st]);
+      }
+      if (cb) {
+#pragma unroll
+        for (int l = 0; l < L; l++) tma_bulk_g2s(sl + l * S + sb, B.c[l] + gb, (unsigned)cb * 8u, &s_mbar[st]);
+        tma_bulk_g2s(sw + sb, wB + gb, (unsigned)cb * 8u, &s_mbar[st]);
+      }
+    }
+    return g;
+  };
+
+  if (tid == 0) {
+    mbar_init(&s_mbar[0], 1);
+    mbar_init(&s_mbar[1], 1);
+    s_next = atomicAdd(ticket, 1u);
+  }
+  __syncthreads();
+  u32 t = s_next;
+  if (t >= ntiles) return;
+  Geo cur = stage_tile(t, 0);
+  unsigned phase0 = 0, phase1 = 0;
+  for (int it = 0;; it++) {
+    const int st = it & 1;
+    __syncthreads();   // every thread has left the previous tile: buffer st^1 and s_next are free
+    if (tid == 0) s_next = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const u32 tn = s_next;
+    Geo nxt = cur;
+    if (tn < ntiles) nxt = stage_tile(tn, st ^ 1);
+    // current tile
+    if (st == 0) { mbar_wait(&s_mbar[0], phase0); phase0 ^= 1; }
+    else { mbar_wait(&s_mbar[1], phase1); phase1 ^= 1; }
+    u64* sl = (u64*)(smem_raw + (size_t)st * PersistCfg<L>::BUF);
+    i64* sw = (i64*)(sl + (size_t)L * S);
+    if (any_flip) {
+      for (int x = tid; x < S; x += MERGE_THREADS) {
+#pragma unroll
+        for (int l = 0; l < L; l++) sl[l * S + x] ^= f.f[l];
+      }
+      __syncthreads();
+    }
+    merge_process_tile<L>(sl, sw, perm, cur.oa, cur.ob, cur.na, cur.nb, cur.has_prev, cur.has_next, t, ntiles, status, O, wO,
+                          n_out, f, sc);
+    if (tn >= ntiles) break;
+    t = tn;
+    cur = nxt;
+  }
+}
+
 // all arrays of the batch share the 16-byte phase of element 0 (true unless a
 // view mixes storage, e.g. a negated slice): precondition of the TMA path
 bool uniform_phase(const Batch* b) {
@@ -438,9 +588,24 @@ int32_t merge_launch(Ctx* ctx, const Batch* a, const Batch* b, Batch** out) {
     ProfScope ps(ctx, KID_MERGE_PARTITION, (u64)(ntiles + 1) * 8);
     k_merge_partition<L><<<(ntiles + 1 + 127) / 128, 128, 0, st>>>(a->cols(), a->n, b->cols(), b->n, f, Cfg::TILE, ntiles, part);
   }
+  static const bool persist_on = getenv("DBSP_MERGE_PERSISTENT") != nullptr;
   ProfScope* ps = new ProfScope(ctx, KID_MERGE, 0);
-  k_merge_tiles<L><<<ntiles, MERGE_THREADS, Cfg::SMEM, st>>>(a->cols(), a->w, a->n, b->cols(), b->w, b->n, f, part, ntiles,
-                                                           ticket, status, oc, ow, n_out, use_tma);
+  if (persist_on && use_tma) {
+    static bool pattr = false;
+    static int per_sm = 1;
+    if (!pattr) {
+      CUDA_TRY(cudaFuncSetAttribute(k_merge_persist<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PersistCfg<L>::SMEM));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_persist<L>, MERGE_THREADS, PersistCfg<L>::SMEM));
+      if (per_sm < 1) per_sm = 1;
+      pattr = true;
+    }
+    u32 grid = std::min<u32>(ntiles, (u32)(ctx->sm_count * per_sm));
+    k_merge_persist<L><<<grid, MERGE_THREADS, PersistCfg<L>::SMEM, st>>>(a->cols(), a->w, a->n, b->cols(), b->w, b->n, f, part,
+                                                                       ntiles, ticket, status, oc, ow, n_out);
+  } else {
+    k_merge_tiles<L><<<ntiles, MERGE_THREADS, Cfg::SMEM, st>>>(a->cols(), a->w, a->n, b->cols(), b->w, b->n, f, part, ntiles,
+                                                             ticket, status, oc, ow, n_out, use_tma);
+  }
   long ps_idx = ps->idx;
   delete ps;   // records the end event
   ctx->kernel_launches += 2;
