@@ -118,6 +118,15 @@ int32_t dbsp_ctx_create(int32_t device, dbsp_ctx** out) {
   c->device = device;
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaMallocHost(&c->h_scratch, 256 * 8));
+  {
+    void* hm = nullptr;
+    CUDA_TRY(cudaHostAlloc(&hm, 320 * 8, cudaHostAllocMapped));
+    memset(hm, 0, 320 * 8);
+    c->h_mail = (volatile u64*)hm;
+    void* dm = nullptr;
+    CUDA_TRY(cudaHostGetDevicePointer(&dm, hm, 0));
+    c->d_mail = (u64*)dm;
+  }
   CUDA_TRY(cudaMalloc(&c->d_scratch, 256 * 8));
   CUDA_TRY(cudaMemset(c->d_scratch, 0, 256 * 8));
   cudaDeviceProp prop;
@@ -145,6 +154,7 @@ int32_t dbsp_ctx_destroy(dbsp_ctx* c) {
   print_host_stats(c);
   cudaStreamSynchronize(c->stream);
   cudaFreeHost(c->h_scratch);
+  cudaFreeHost((void*)c->h_mail);
   cudaFree(c->d_scratch);
   pool_release_all(c);
   for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

@@ -115,6 +115,10 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   // pinned scratch for small D2H readbacks (counts, min/max)
   u64* h_scratch = nullptr;   // 256 u64
+  // zero-copy mailbox for small read-backs: [0] = sequence flag, [8..] = payload
+  volatile u64* h_mail = nullptr;   // mapped pinned host memory (320 u64)
+  u64* d_mail = nullptr;            // its device alias
+  u64 mail_seq = 0;
   u64* d_scratch = nullptr;   // 256 u64
   u64 kernel_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   // Device memory: best-fit allocator with coalescing over large cudaMalloc
