@@ -146,6 +146,7 @@ def run_b200(args, query, rank, world, comm, device, do_e2e=True):
         c = dbsp_b200.RootCircuit(be, comm)
         inp, handles = nq.add_nexmark_input(c)
         out = nq.QUERIES[query](inp).output()
+        build.tables = inp
         return c, handles, out
 
     def sync_all(be):
@@ -212,8 +213,22 @@ def run_b200(args, query, rank, world, comm, device, do_e2e=True):
     if do_e2e:
         be2, ext2 = be, ext   # same context / stream / memory pool, fresh circuit state
         c, handles, out = build(be2)
+        tabs = {"person": build.tables.person, "auction": build.tables.auction, "bid": build.tables.bid}
+        masks = {k: tabs[k].table_mask() for k in tabs}
+
+        def start_uploads(t):
+            """H2D of one step's tables on the copy stream (only the columns the query reads)."""
+            return {k: (be2.upload_begin(t[k], masks[k]) if (t[k] is not None and masks[k]) else None) for k in tabs}
+
+        def feed_uploads(ups):
+            for k in tabs:
+                if ups[k] is None:
+                    handles[k].set(empty_cols())
+                else:
+                    handles[k].set_upload(ups[k])
+
         for s in range(W):
-            feed_host(handles, steps[s])
+            feed_uploads(start_uploads(steps[s]))
             c.step()
             out.value.download()
         sync_all(be2)
@@ -221,10 +236,13 @@ def run_b200(args, query, rank, world, comm, device, do_e2e=True):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(ext2)
+        nxt = start_uploads(steps[W])             # every step's H2D copy is inside the timed region ...
         for s in range(W, W + K):
-            feed_host(handles, steps[s])      # host (pinned) columns: H2D happens inside the ABI call
+            cur = nxt
+            nxt = start_uploads(steps[s + 1]) if s + 1 < W + K else None   # ... and overlaps the previous step's kernels
+            feed_uploads(cur)
             c.step()
-            out.value.download()              # D2H of the step's result Z-set
+            out.value.download()                  # D2H of the step's result Z-set
         e1.record(ext2)
         sync_all(be2)
         wall2 = time.perf_counter() - t0

@@ -70,6 +70,9 @@ _SIGS = {
     "batch_from_tuples": [_P, C.POINTER(CSchema), _PP, _P, C.c_uint64, C.c_int32, _PP],
     "batch_from_table": [_P, _PP, C.c_uint32, _P, C.c_uint64, C.c_int32, C.POINTER(CProj), _PP],
     "batch_from_sorted": [_P, C.POINTER(CSchema), _PP, _P, C.c_uint64, C.c_int32, _PP],
+    "upload_begin": [_P, _PP, C.c_uint32, C.c_uint32, _P, C.c_uint64, _PP],
+    "batch_from_upload": [_P, _P, C.POINTER(CProj), _PP],
+    "upload_free": [_P],
     "batch_empty": [_P, C.POINTER(CSchema), _PP],
     "batch_merge": [_P, _P, _P, _PP],
     "batch_neg": [_P, _P, _PP],
@@ -118,10 +121,13 @@ class CApi:
         self._ctx_stream = getattr(lib, prefix + "ctx_stream")
         self._ctx_stream.restype = C.c_void_p
         self._ctx_stream.argtypes = [_P]
+        self._proj_table_mask = getattr(lib, prefix + "proj_table_mask")
+        self._proj_table_mask.restype = C.c_uint32
+        self._proj_table_mask.argtypes = [C.POINTER(CProj)]
 
     @staticmethod
     def symbols(prefix: str = "dbsp_"):
-        return [prefix + n for n in list(_SIGS) + ["last_error", "ctx_stream"]]
+        return [prefix + n for n in list(_SIGS) + ["last_error", "ctx_stream", "proj_table_mask"]]
 
     def check(self, rc: int, what: str):
         if rc != OK:

@@ -77,6 +77,11 @@ class TableHandle:
     def set_device(self, ptrs, n, weights=None):
         self.cur = ("dev", list(ptrs), weights, int(n))
 
+    def set_upload(self, upload):
+        """upload: an `Upload` started with Backend.upload_begin for this step
+        (pipelined ingest; its column mask must cover `TableStream.table_mask()`)."""
+        self.cur = ("upload", upload, None, None)
+
     def _take(self):
         cur, self.cur = self.cur, None
         return cur
@@ -126,16 +131,27 @@ class RootCircuit:
 class TableStream:
     def __init__(self, circuit, node, n_cols):
         self.circuit, self.node, self.n_cols = circuit, node, n_cols
+        self.projs = []   # projections consuming this table, in creation order
+
+    def table_mask(self) -> int:
+        """Columns read by any consumer of this table (bit l = column l)."""
+        m = 0
+        for p in self.projs:
+            m |= self.circuit.be.proj_table_mask(p)
+        return m
 
     def flat_map_index(self, proj: Proj) -> "Stream":
         """flat_map_index on the event stream (filter_map.rs:143-152,700-724):
         filter + project + from_tuples, straight from the raw columns."""
         be = self.circuit.be
+        self.projs.append(proj)
 
         def fn(t):
             if t is None:
                 return be.batch_empty(proj.schema)
             kind, cols, w, n = t
+            if kind == "upload":
+                return be.batch_from_upload(cols, proj)
             return be.batch_from_table(cols, proj, weights=w, n=n, on_device=(kind == "dev"))
 
         return Stream(self.circuit, Node(self.circuit, [self.node], fn, "flat_map_index"), proj.schema)

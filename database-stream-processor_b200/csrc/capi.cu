@@ -117,6 +117,7 @@ int32_t dbsp_ctx_create(int32_t device, dbsp_ctx** out) {
   dbsp_ctx* c = new dbsp_ctx();
   c->device = device;
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaMallocHost(&c->h_scratch, 256 * 8));
   {
     void* hm = nullptr;
@@ -162,6 +163,7 @@ int32_t dbsp_ctx_destroy(dbsp_ctx* c) {
   c->prof.clear();
   c->ev_pool.clear();
   cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->copy_stream);
   c->stream = nullptr;
   c->destroyed = true;
   if (c->live_bufs.load() == 0) delete c;   // else the last DevBuf deletes it
@@ -230,6 +232,74 @@ int32_t dbsp_batch_from_table(dbsp_ctx* ctx, const uint64_t* const* cols, uint32
   Batch* b = nullptr;
   TRY(project_and_consolidate(ctx, dc, 0, (int)n_cols, dw, n, *proj, &b));
   *out = H(b);
+  return DBSP_OK;
+}
+
+struct dbsp_upload {
+  Ctx* ctx;
+  BufP buf;
+  Cols dc;
+  const i64* dw;
+  u64 n;
+  int n_cols;
+  cudaEvent_t done;
+};
+
+uint32_t dbsp_proj_table_mask(const dbsp_proj* proj) { return proj_used_mask(*proj, 0); }
+
+int32_t dbsp_upload_begin(dbsp_ctx* ctx, const uint64_t* const* cols, uint32_t n_cols, uint32_t col_mask,
+                          const int64_t* w, uint64_t n, dbsp_upload** out) {
+  CHECK_ARG(n_cols >= 1 && n_cols <= MAXL, "table must have 1..8 columns");
+  dbsp_upload* u = new dbsp_upload();
+  u->ctx = ctx;
+  u->n = n;
+  u->n_cols = (int)n_cols;
+  u->dw = nullptr;
+  for (int l = 0; l < MAXL; l++) u->dc.c[l] = nullptr;
+  CUDA_TRY(cudaEventCreateWithFlags(&u->done, cudaEventDisableTiming));
+  if (n) {
+    u64 cap = (n + 32) & ~31ull;
+    TRY(dev_alloc(ctx, (size_t)cap * 8 * (n_cols + 1), &u->buf));
+    // the block may have been used by work still queued on the compute stream
+    cudaEvent_t ev;
+    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(ev, ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
+    CUDA_TRY(cudaEventDestroy(ev));
+    u64* base = (u64*)u->buf->p;
+    for (uint32_t l = 0; l < n_cols; l++) {
+      if (!((col_mask >> l) & 1)) continue;
+      CUDA_TRY(cudaMemcpyAsync(base + (size_t)l * cap, cols[l], n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+      u->dc.c[l] = base + (size_t)l * cap;
+      ctx->h2d_bytes += n * 8;
+    }
+    if (w) {
+      i64* p = (i64*)(base + (size_t)n_cols * cap);
+      CUDA_TRY(cudaMemcpyAsync(p, w, n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+      ctx->h2d_bytes += n * 8;
+      u->dw = p;
+    }
+  }
+  CUDA_TRY(cudaEventRecord(u->done, ctx->copy_stream));
+  *out = u;
+  return DBSP_OK;
+}
+
+int32_t dbsp_batch_from_upload(dbsp_ctx* ctx, dbsp_upload* u, const dbsp_proj* proj, dbsp_batch** out) {
+  CUDA_TRY(cudaStreamWaitEvent(ctx->stream, u->done, 0));   // compute stream waits for the copy
+  Batch* b = nullptr;
+  TRY(project_and_consolidate(ctx, u->dc, 0, u->n_cols, u->dw, u->n, *proj, &b));
+  *out = H(b);
+  return DBSP_OK;
+}
+
+int32_t dbsp_upload_free(dbsp_upload* u) {
+  if (!u) return DBSP_OK;
+  // a consumed upload's buffer is only reused by later work on the compute
+  // stream (ordered after the consumer); an unconsumed one must drain first
+  cudaEventSynchronize(u->done);
+  cudaEventDestroy(u->done);
+  delete u;
   return DBSP_OK;
 }
 

@@ -113,6 +113,7 @@ struct Ctx {
   std::vector<cudaEvent_t> ev_pool;
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // pipelined H2D uploads (dbsp_upload_begin)
   // pinned scratch for small D2H readbacks (counts, min/max)
   u64* h_scratch = nullptr;   // 256 u64
   // zero-copy mailbox for small read-backs: [0] = sequence flag, [8..] = payload

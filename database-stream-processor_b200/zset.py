@@ -286,6 +286,21 @@ class Batch:
         return f"Batch<{self.schema.key}|{self.schema.val}>({body})"
 
 
+class Upload:
+    """In-flight H2D copy of a raw table (keeps the host arrays alive)."""
+
+    def __init__(self, be, handle, cols, weights):
+        self.be, self.h, self._cols, self._w = be, handle, cols, weights
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.be.api._upload_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
 class Spine:
     """Owning handle of a trace (trace/spine_fueled.rs:107-119)."""
 
@@ -405,6 +420,25 @@ class Backend:
         out = self._out()
         self.api.call("batch_from_table", self.ctx, col_ptrs(cols), len(cols), wptr, n, int(on_device), proj.c(), C.byref(out))
         return Batch(self, out.value, proj.schema)
+
+    def upload_begin(self, cols: Sequence, col_mask: int = 0xFF, weights=None):
+        """Start the H2D copy of a future step's table (pinned host columns)."""
+        cols = [as_u64(c) for c in cols]
+        n = len(cols[0])
+        if weights is not None:
+            weights = np.ascontiguousarray(np.asarray(weights, dtype=np.int64))
+        up = C.c_void_p()
+        self.api.call("upload_begin", self.ctx, col_ptrs(cols), len(cols), col_mask,
+                      weights.ctypes.data if weights is not None else None, n, C.byref(up))
+        return Upload(self, up.value, cols, weights)
+
+    def batch_from_upload(self, up: "Upload", proj: Proj) -> Batch:
+        out = self._out()
+        self.api.call("batch_from_upload", self.ctx, up.h, proj.c(), C.byref(out))
+        return Batch(self, out.value, proj.schema)
+
+    def proj_table_mask(self, proj: Proj) -> int:
+        return int(self.api._proj_table_mask(proj.c()))
 
     def batch_from_sorted(self, schema: Schema, cols: Sequence, weights, n: int, on_device: bool) -> Batch:
         out = self._out()

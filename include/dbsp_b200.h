@@ -166,6 +166,24 @@ int32_t dbsp_batch_from_table(dbsp_ctx* ctx, const uint64_t* const* cols,
                               uint32_t n_cols, const int64_t* weights,
                               uint64_t n, int32_t on_device,
                               const dbsp_proj* proj, dbsp_batch** out);
+/* Pipelined ingest of a raw event table: start copying the host columns of a
+ * *future* step to the device on the context's copy stream (pinned host
+ * memory makes it overlap with the kernels of the current step); the handle
+ * is then consumed by dbsp_batch_from_upload.  `col_mask` bit l = column l is
+ * needed (the others are not copied).  The host buffers must stay valid until
+ * the upload is consumed or freed.  This is the double-buffered input queue of
+ * the reference's source operators (crates/nexmark/src/lib.rs:105-231 feeds
+ * batches ahead of the circuit) moved to the PCIe boundary. */
+typedef struct dbsp_upload dbsp_upload;
+int32_t dbsp_upload_begin(dbsp_ctx* ctx, const uint64_t* const* cols,
+                          uint32_t n_cols, uint32_t col_mask,
+                          const int64_t* weights, uint64_t n,
+                          dbsp_upload** out);
+int32_t dbsp_batch_from_upload(dbsp_ctx* ctx, dbsp_upload* up,
+                               const dbsp_proj* proj, dbsp_batch** out);
+int32_t dbsp_upload_free(dbsp_upload* up);
+/* Columns of the table a projection reads (bit l = SRC_LVAL idx l). */
+uint32_t dbsp_proj_table_mask(const dbsp_proj* proj);
 int32_t dbsp_batch_empty(dbsp_ctx* ctx, const dbsp_schema* schema,
                          dbsp_batch** out);
 /* Batch::merge / Merger::work run to completion (trace/mod.rs:371-396;

@@ -499,6 +499,23 @@ int32_t orc_batch_from_table(orc_ctx*, const u64* const* cols, uint32_t ncols, c
   return DBSP_OK;
 }
 
+// pipelined ingest: on the CPU there is nothing to overlap, keep the pointers
+struct orc_upload { const u64* const* cols; uint32_t n_cols; const i64* w; u64 n; std::vector<const u64*> own; };
+int32_t orc_batch_from_table(orc_ctx*, const u64* const* cols, uint32_t ncols, const i64* w, u64 n, int32_t,
+                             const dbsp_proj* proj, orc_batch** out);
+int32_t orc_upload_begin(orc_ctx*, const u64* const* cols, uint32_t n_cols, uint32_t, const i64* w, u64 n, orc_upload** out) {
+  orc_upload* u = new orc_upload();
+  u->own.assign(cols, cols + n_cols);
+  u->cols = u->own.data(); u->n_cols = n_cols; u->w = w; u->n = n;
+  *out = u;
+  return DBSP_OK;
+}
+int32_t orc_batch_from_upload(orc_ctx* c, orc_upload* u, const dbsp_proj* proj, orc_batch** out) {
+  return orc_batch_from_table(c, u->cols, u->n_cols, u->w, u->n, 0, proj, out);
+}
+int32_t orc_upload_free(orc_upload* u) { delete u; return DBSP_OK; }
+uint32_t orc_proj_table_mask(const dbsp_proj*) { return 0xffu; }
+
 int32_t orc_batch_empty(orc_ctx*, const dbsp_schema* s, orc_batch** out) {
   *out = wrap(std::make_shared<Batch>(*s));
   return DBSP_OK;

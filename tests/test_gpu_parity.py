@@ -127,3 +127,21 @@ def test_shard_partition_union(cuda, oracle):
         assert_batches_equal(p, q, "shard part")
         acc = cuda.merge(acc, p)
     assert_batches_equal(acc, b, "union of shards")
+
+
+def test_pipelined_upload_equals_from_table(cuda, oracle):
+    """dbsp_upload_begin + dbsp_batch_from_upload == dbsp_batch_from_table (and the oracle)."""
+    from dbsp_b200 import col
+    from dbsp_b200.nexmark import NexmarkGenerator
+
+    t = NexmarkGenerator().tables(0, 300_000)
+    proj = Proj(Schema("u", "uu"), [col(0), col(2), col(3)])
+    ups = [cuda.upload_begin(t["bid"], cuda.proj_table_mask(proj)) for _ in range(3)]   # several in flight
+    ref = oracle.batch_from_table(t["bid"], proj)
+    direct = cuda.batch_from_table(t["bid"], proj)
+    assert_batches_equal(direct, ref, "from_table")
+    for u in ups:
+        assert_batches_equal(cuda.batch_from_upload(u, proj), ref, "from_upload")
+    filt = Proj(Schema("u", "u"), [col(1), col(0)], where=[col(2).eq(10)])
+    u = cuda.upload_begin(t["auction"], cuda.proj_table_mask(filt))
+    assert_batches_equal(cuda.batch_from_upload(u, filt), oracle.batch_from_table(t["auction"], filt), "filtered upload")
