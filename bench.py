@@ -57,45 +57,61 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, ~2 ms period)."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    HW_SLOWDOWN, SW_THERMAL, HW_THERMAL, SW_POWER_CAP = 0x8, 0x20, 0x40, 0x4
 
     def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.idx, self.rows, self.stop, self.t = gpu_index, [], False, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # CUDA_VISIBLE_DEVICES may remap indices: NVML enumerates physical devices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def __enter__(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+        if self.nv is not None:
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
     def __exit__(self, *a):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self.stop = True
+        if self.t is not None:
+            self.t.join(timeout=1)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        if not sm:
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        sm = [r[0] for r in self.rows]
+        bits = 0
+        for r in self.rows:
+            bits |= r[1]
+        names = [("hw_slowdown", self.HW_SLOWDOWN), ("hw_thermal_slowdown", self.HW_THERMAL),
+                 ("sw_thermal_slowdown", self.SW_THERMAL), ("sw_power_cap", self.SW_POWER_CAP)]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.max_sm), "reasons": [n for n, b in names if bits & b],
+                "samples": len(sm)}
 
 
 def gen_steps(query, rank, world, n_steps, events_per_step, pinned):
@@ -104,7 +120,7 @@ def gen_steps(query, rank, world, n_steps, events_per_step, pinned):
     distribution at batch granularity, operator/input.rs:664-703)."""
     from dbsp_b200.nexmark import NexmarkGenerator
 
-    gen = NexmarkGenerator()
+    gen = NexmarkGenerator(threads=max(1, (os.cpu_count() or 8) // max(world, 1)))
     want = QUERY_COLS[query]
     if pinned:
         import torch
