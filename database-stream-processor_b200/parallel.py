@@ -69,6 +69,15 @@ class Comm:
         self.bytes_sent += (sum(counts) - counts[self.rank]) * L1 * 8
         if recv.is_cuda:
             torch.cuda.current_stream(recv.device).synchronize()   # once, before the library adopts the segments
+        total = sum(rc)
+        if 0 < total <= self.SORT_THRESHOLD and P > 2:
+            # Small deltas: P-1 merges cost more in launches and read-backs than one
+            # consolidation of the concatenated segments (Batch::from_tuples).
+            cols = []
+            for l in range(schema.nl):
+                cols.append(torch.cat([recv[off + l * n: off + (l + 1) * n] for off, n in self._segments(rc, L1)]))
+            w = torch.cat([recv[off + schema.nl * n: off + L1 * n] for off, n in self._segments(rc, L1)])
+            return [be.batch_from_device_tensors(schema, cols, w)]
         out, off = [], 0
         for q in range(P):
             n = rc[q]
@@ -77,6 +86,15 @@ class Comm:
             cols = [seg[l * n: (l + 1) * n] for l in range(schema.nl)]
             out.append(be.batch_from_flat_tensors(schema, cols, seg[schema.nl * n: L1 * n], synced=True))
         return out
+
+    SORT_THRESHOLD = 1 << 20
+
+    @staticmethod
+    def _segments(rc, L1):
+        off = 0
+        for n in rc:
+            yield off, n
+            off += n * L1
 
     @staticmethod
     def _merge_all(be: Backend, batches: list[Batch]) -> Batch:

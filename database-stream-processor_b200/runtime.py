@@ -82,3 +82,15 @@ class Runtime(Backend):
         if not synced:
             torch.cuda.current_stream(self.device).synchronize()
         return self.batch_from_sorted(schema, [int(c.data_ptr()) for c in cols], int(weights.data_ptr()), n, True)
+
+    def batch_from_device_tensors(self, schema: Schema, cols, weights) -> Batch:
+        """Batch::from_tuples over unsorted device-resident torch columns."""
+        import torch
+
+        n = int(weights.numel())
+        if n == 0:
+            return self.batch_empty(schema)
+        torch.cuda.current_stream(self.device).synchronize()
+        b = self.batch_from_columns(schema, [int(c.data_ptr()) for c in cols], int(weights.data_ptr()), n=n, on_device=True)
+        self.sync()   # the torch tensors may be freed as soon as this returns
+        return b

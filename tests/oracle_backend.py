@@ -48,3 +48,6 @@ class OracleBackend(Backend):
 
     def batch_from_flat_tensors(self, schema: Schema, cols, weights, synced: bool = False) -> Batch:
         return self.batch_from_sorted(schema, [c.numpy().view(np.uint64) for c in cols], weights.numpy(), int(weights.numel()), False)
+
+    def batch_from_device_tensors(self, schema: Schema, cols, weights) -> Batch:
+        return self.batch_from_columns(schema, [c.numpy().view(np.uint64) for c in cols], weights.numpy())

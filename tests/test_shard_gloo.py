@@ -16,6 +16,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
+WORLD = 3   # > 2 so that the small-delta consolidation path of the receiver is exercised too
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -69,7 +72,7 @@ def test_sharded_equals_single(tmp_path, oracle, query):
 
     n_events, step = (120_000, 40_000) if query != "q7" else (400_000, 100_000)
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, query, n_events, step, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(WORLD, port, query, n_events, step, str(tmp_path)), nprocs=WORLD, join=True)
     sharded = np.load(os.path.join(tmp_path, "sharded.npy"), allow_pickle=True)
     c, handles, out = build_query(oracle, query)
     gen = NexmarkGenerator()
