@@ -237,20 +237,108 @@ int32_t read_back32(Ctx* ctx, const void* dsrc, u32* hdst) {
   return DBSP_OK;
 }
 
-// Device-wide prefix sums are plumbing between the hand-written kernels (the
-// hot merge kernel carries its own decoupled look-back instead).
+// Device-wide exclusive prefix sum of u32 counts: one pass over HBM with a
+// decoupled look-back across tiles (same protocol as the merge kernel: status
+// word = 2-bit state | 62-bit value, tiles ordered by an atomic ticket, warp 0
+// inspects 32 predecessors per round trip).
+constexpr int SCAN_THREADS = 256, SCAN_IPT = 8, SCAN_TILE = SCAN_THREADS * SCAN_IPT;
+constexpr u64 SC_AGG = 1ull << 62, SC_PREFIX = 2ull << 62, SC_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ u64 sc_ld(const u64* p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sc_st(u64* p, u64 v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_exscan_u32(const u32* __restrict__ in, u32* __restrict__ out, u64 m,
+                                                            u32* ticket, u64* status) {
+  __shared__ u32 s_tile, s_warp[SCAN_THREADS / 32];
+  __shared__ u64 s_base;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const u32 t = s_tile;
+  const u64 base_i = (u64)t * SCAN_TILE + (u64)tid * SCAN_IPT;
+  u32 v[SCAN_IPT];
+  u32 sum = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_IPT; k++) {
+    v[k] = (base_i + k < m) ? in[base_i + k] : 0u;
+    sum += v[k];
+  }
+  u32 incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    u32 x = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += x;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  u32 woff = 0, tile_total = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_THREADS / 32; k++) {
+    u32 x = s_warp[k];
+    if (k < wid) woff += x;
+    tile_total += x;
+  }
+  if (wid == 0) {
+    u64 base = 0;
+    if (t == 0) {
+      if (lane == 0) sc_st(&status[0], SC_PREFIX | (u64)tile_total);
+    } else {
+      if (lane == 0) sc_st(&status[t], SC_AGG | (u64)tile_total);
+      long long p = (long long)t - 1;
+      while (true) {
+        const long long q = p - lane;
+        u64 x = SC_PREFIX;
+        if (q >= 0) {
+          do { x = sc_ld(&status[q]); } while ((x >> 62) == 0);
+        }
+        const unsigned isp = __ballot_sync(0xffffffffu, (x >> 62) == 2);
+        const int first = isp ? (__ffs(isp) - 1) : 32;
+        u64 c = (lane <= first) ? (x & SC_MASK) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        base += c;
+        if (isp) break;
+        p -= 32;
+      }
+      if (lane == 0) sc_st(&status[t], SC_PREFIX | (base + tile_total));
+    }
+    if (lane == 0) s_base = base;
+  }
+  __syncthreads();
+  u32 run = (u32)s_base + woff + incl - sum;
+#pragma unroll
+  for (int k = 0; k < SCAN_IPT; k++) {
+    if (base_i + k < m) out[base_i + k] = run;
+    run += v[k];
+  }
+}
+
 int32_t exclusive_scan_u32(Ctx* ctx, const u32* in, u32* out, u64 n) {
-  // out has n+1 entries: out[n] = total.  Scan n+1 inputs where in[n] is
-  // ignored by construction: callers allocate in with n+1 entries.
-  size_t tmp_bytes = 0;
-  CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (size_t)(n + 1), ctx->stream));
-  BufP tmp;
-  TRY(dev_alloc(ctx, tmp_bytes, &tmp));
-  CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp->p, tmp_bytes, in, out, (size_t)(n + 1), ctx->stream));
+  // out has n+1 entries: out[n] = total.  Scans the n+1 inputs (callers keep
+  // in[n] == 0).
+  const u64 m = n + 1;
+  const u32 ntiles = (u32)((m + SCAN_TILE - 1) / SCAN_TILE);
+  BufP aux;
+  TRY(dev_alloc(ctx, (size_t)(ntiles + 1) * 8, &aux));
+  CUDA_TRY(cudaMemsetAsync(aux->p, 0, (size_t)(ntiles + 1) * 8, ctx->stream));
+  u64* status = (u64*)aux->p;
+  u32* ticket = (u32*)(status + ntiles);
+  {
+    ProfScope ps(ctx, KID_SCAN, m * 8);
+    k_exscan_u32<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(in, out, m, ticket, status);
+  }
   LAUNCH_COUNT(ctx);
   return DBSP_OK;
 }
 
+// i64 running sums are only needed by the Fold-sum aggregator (rare path): the
+// one library prefix sum left.
 int32_t inclusive_scan_i64(Ctx* ctx, const i64* in, i64* out, u64 n) {
   size_t tmp_bytes = 0;
   CUDA_TRY(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, in, out, (size_t)n, ctx->stream));
