@@ -145,3 +145,41 @@ def test_pipelined_upload_equals_from_table(cuda, oracle):
     filt = Proj(Schema("u", "u"), [col(1), col(0)], where=[col(2).eq(10)])
     u = cuda.upload_begin(t["auction"], cuda.proj_table_mask(filt))
     assert_batches_equal(cuda.batch_from_upload(u, filt), oracle.batch_from_table(t["auction"], filt), "filtered upload")
+
+
+def test_large_scale_properties(cuda):
+    """Size-independent properties at a size the oracle is too slow for
+    (2 x 8 M rows): sortedness, weight conservation, linearity, cancellation,
+    idempotence of consolidation."""
+    rng = np.random.default_rng(2024)
+    s = Schema("u", "u")
+    n = 8_000_000
+    def mk():
+        k = rng.zipf(1.3, n).astype(np.uint64) % np.uint64(n // 4)
+        v = rng.integers(0, 1 << 40, n).astype(np.uint64)
+        w = rng.choice(np.array([-2, -1, 1, 2], dtype=np.int64), n)
+        return k, v, w
+    ka, va, wa = mk()
+    kb, vb, wb = mk()
+    a = cuda.batch_from_columns(s, [ka, va], wa)
+    b = cuda.batch_from_columns(s, [kb, vb], wb)
+    m = cuda.merge(a, b)
+    d = m.download()
+    keys = np.repeat(d["keys"][0], np.diff(d["offs"].astype(np.int64)))
+    vals = d["vals"][0]
+    # strictly increasing (key, val) rows, no zero weights
+    dk = np.diff(keys.astype(np.int64))
+    assert np.all(dk >= 0)
+    assert np.all((dk > 0) | (np.diff(vals.astype(np.int64)) > 0))
+    assert np.all(d["diffs"] != 0)
+    # weight conservation (wrapping i64 sums)
+    assert int(d["diffs"].sum()) == int(wa.sum() + wb.sum())
+    # linearity and cancellation
+    da = a.download()
+    dd = cuda.merge(a, a).download()
+    assert np.array_equal(dd["diffs"], 2 * da["diffs"]) and np.array_equal(dd["vals"][0], da["vals"][0])
+    assert len(cuda.merge(m, cuda.neg(m))) == 0
+    # consolidating a consolidated batch is the identity
+    flat_k = np.repeat(da["keys"][0], np.diff(da["offs"].astype(np.int64)))
+    again = cuda.batch_from_columns(s, [flat_k, da["vals"][0]], da["diffs"])
+    assert_batches_equal(again, a, "idempotence")
