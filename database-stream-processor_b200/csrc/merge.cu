@@ -151,49 +151,62 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, i64* sw, u32* perm, 
   int* s_lb_first = sc.s_lb_first;
   u64* s_lb_all = sc.s_lb_all;
   u64* s_lb_upto = sc.s_lb_upto;
-  auto le = [&](int ia, int ib) {   // staged row ia <= staged row ib
-#pragma unroll
-    for (int l = 0; l < L; l++) {
-      u64 a = sl[l * S + ia], b = sl[l * S + ib];
-      if (a != b) return a < b;
-    }
-    return true;
-  };
-
   // ---- per-thread merge path ------------------------------------------------
+  // Straight-line code throughout (no data-dependent branches): lanes of a warp
+  // take A and B rows in arbitrary interleavings, and divergent paths would be
+  // executed one after the other.
   const int n = na + nb;
   int dt = tid * IPT;
   if (dt > n) dt = n;
   int lo = dt > nb ? dt - nb : 0, hi = dt < na ? dt : na;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (le(oa + mid, ob + (dt - 1 - mid))) lo = mid + 1; else hi = mid;
+  {
+    // fixed trip count: the search range is at most TILE wide
+    constexpr int STEPS = 32 - __builtin_clz((unsigned)MergeCfg<L>::TILE);
+#pragma unroll 1
+    for (int it = 0; it < STEPS; it++) {
+      const bool active = lo < hi;
+      const int mid = (lo + hi) >> 1;
+      const int ia = oa + (active ? mid : 0), ib = ob + (active ? (dt - 1 - mid) : 0);
+      bool lt = false, eq = true;   // staged row ia vs ib
+#pragma unroll
+      for (int l = 0; l < L; l++) {
+        const u64 a = sl[l * S + ia], b = sl[l * S + ib];
+        lt = lt || (eq && a < b);
+        eq = eq && (a == b);
+      }
+      const bool le = lt || eq;
+      lo = (active && le) ? mid + 1 : lo;
+      hi = (active && !le) ? mid : hi;
+    }
   }
   int ai = lo, bi = dt - lo;
 
   // Serial merge with both run heads held in registers: one 3-way compare per
-  // row, only the advanced side is re-read from shared memory.  `prev_eq`
-  // says the previous merged row was an A row equal to the current B head.
+  // row; the head of the advanced side is re-read from shared memory through a
+  // single (selected) address.  `prev_eq` says the previous merged row was an A
+  // row equal to the current B head.
   u64 ka[L], kb[L];
   i64 wa = 0, wb = 0;
-  auto load_a = [&](int i) {
 #pragma unroll
-    for (int l = 0; l < L; l++) ka[l] = sl[l * S + oa + i];
-    wa = sw[oa + i];
-  };
-  auto load_b = [&](int j) {
+  for (int l = 0; l < L; l++) { ka[l] = 0; kb[l] = 0; }
+  bool a_ok = ai < na;
+  bool b_in = bi < nb;
+  bool b_readable = b_in || (bi == nb && has_next);
+  {
+    const int ia = oa + (a_ok ? ai : 0), ib = ob + (b_readable ? bi : 0);
 #pragma unroll
-    for (int l = 0; l < L; l++) kb[l] = sl[l * S + ob + j];
-    wb = sw[ob + j];
-  };
-  bool b_readable = (bi < nb) || (bi == nb && has_next);
-  if (ai < na) load_a(ai);
-  if (b_readable) load_b(bi);
-  bool prev_eq = false;
-  if ((ai > 0 || has_prev) && bi < nb) {   // A[ai-1] (slot oa+ai-1; halo at oa-1) vs B head
-    prev_eq = true;
+    for (int l = 0; l < L; l++) { ka[l] = sl[l * S + ia]; kb[l] = sl[l * S + ib]; }
+    wa = sw[ia];
+    wb = sw[ib];
+  }
+  bool prev_eq;
+  {
+    const bool chk = (ai > 0 || has_prev) && b_in;   // A[ai-1] (slot oa+ai-1; halo at oa-1) vs B head
+    const int ip = chk ? (oa + ai - 1) : oa;
+    bool eq = true;
 #pragma unroll
-    for (int l = 0; l < L; l++) prev_eq = prev_eq && (sl[l * S + oa + ai - 1] == kb[l]);
+    for (int l = 0; l < L; l++) eq = eq && (sl[l * S + ip] == kb[l]);
+    prev_eq = chk && eq;
   }
 
   u32 src[IPT];
@@ -201,37 +214,43 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, i64* sw, u32* perm, 
   u32 keep = 0;
 #pragma unroll
   for (int k = 0; k < IPT; k++) {
-    src[k] = 0;
-    wv[k] = 0;
-    if (ai + bi < n) {
-      const bool a_ok = ai < na, b_in = bi < nb;
-      int c = 0;   // cmp3(A head, B head) when both are readable
-      if (a_ok && b_readable) {
+    const bool live = ai + bi < n;
+    bool lt = false, eq = true;   // A head vs B head
 #pragma unroll
-        for (int l = 0; l < L; l++) {
-          if (c == 0 && ka[l] != kb[l]) c = ka[l] < kb[l] ? -1 : 1;
-        }
-      }
-      const bool take_a = !b_in || (a_ok && c <= 0);
-      if (take_a) {
-        const bool partner = b_readable && c == 0;
-        i64 w = partner ? (i64)((u64)wa + (u64)wb) : wa;
-        src[k] = oa + ai;
-        wv[k] = w;
-        if (w != 0) keep |= 1u << k;
-        prev_eq = partner;
-        ai++;
-        if (ai < na) load_a(ai);
-      } else {
-        src[k] = ob + bi;
-        wv[k] = wb;
-        if (!prev_eq && wb != 0) keep |= 1u << k;
-        prev_eq = false;
-        bi++;
-        b_readable = (bi < nb) || (bi == nb && has_next);
-        if (b_readable) load_b(bi);
-      }
+    for (int l = 0; l < L; l++) {
+      lt = lt || (eq && ka[l] < kb[l]);
+      eq = eq && (ka[l] == kb[l]);
     }
+    const bool both = a_ok && b_readable;
+    const bool take_a = !b_in || (a_ok && (lt || eq));   // b_readable implies comparable heads; !b_in forces A
+    const bool partner = take_a && both && eq;
+    const i64 w = take_a ? (partner ? (i64)((u64)wa + (u64)wb) : wa) : wb;
+    src[k] = take_a ? (u32)(oa + ai) : (u32)(ob + bi);
+    wv[k] = w;
+    const bool kept = live && (take_a ? (w != 0) : (!prev_eq && wb != 0));
+    keep |= kept ? (1u << k) : 0u;
+    prev_eq = live ? partner : prev_eq;
+    ai += (live && take_a) ? 1 : 0;
+    bi += (live && !take_a) ? 1 : 0;
+    // reload the advanced head (one address, predicated)
+    const bool na_ok = ai < na;
+    const bool nb_in = bi < nb;
+    const bool nb_rd = nb_in || (bi == nb && has_next);
+    const bool adv_a = live && take_a, adv_b = live && !take_a;
+    const bool ld_ok = adv_a ? na_ok : (adv_b ? nb_rd : false);
+    const int nidx = ld_ok ? (adv_a ? oa + ai : ob + bi) : oa;
+    i64 nw = sw[nidx];
+#pragma unroll
+    for (int l = 0; l < L; l++) {
+      const u64 v = sl[l * S + nidx];
+      ka[l] = (adv_a && ld_ok) ? v : ka[l];
+      kb[l] = (adv_b && ld_ok) ? v : kb[l];
+    }
+    wa = (adv_a && ld_ok) ? nw : wa;
+    wb = (adv_b && ld_ok) ? nw : wb;
+    a_ok = na_ok;
+    b_in = nb_in;
+    b_readable = nb_rd;
   }
 
   // ---- block exclusive scan of kept counts ------------------------------------
@@ -429,125 +448,6 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
 }
 
 
-// ---- persistent, double-buffered variant -----------------------------------------
-// One CTA per resident slot loops over tiles (atomic ticket).  While tile t is
-// merged out of buffer `st`, the TMA copies of the CTA's next tile already fly
-// into buffer `st^1`, so neither the ticket/partition lookups nor the HBM
-// latency of the staging is exposed.  Needs the TMA path (uniform 16-byte phase).
-template <int L>
-struct PersistCfg {
-  static constexpr int IPT = MergeCfg<L>::IPT;
-  static constexpr int TILE = MergeCfg<L>::TILE;
-  static constexpr int S = MergeCfg<L>::S;
-  static constexpr size_t BUF = (size_t)S * (L + 1) * 8;
-  static constexpr size_t SMEM = 2 * BUF + (size_t)TILE * 4;
-};
-
-template <int L>
-__global__ void __launch_bounds__(MERGE_THREADS)
-k_merge_persist(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __restrict__ wB, u64 nB, Flips f,
-                const u64* __restrict__ part, u32 ntiles, u32* ticket, u64* status, MCols O, i64* wO, u64* n_out) {
-  constexpr int TILE = PersistCfg<L>::TILE;
-  constexpr int S = PersistCfg<L>::S;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  u32* perm = (u32*)(smem_raw + 2 * PersistCfg<L>::BUF);
-  __shared__ __align__(8) u64 s_mbar[2];
-  __shared__ u32 s_next;
-  __shared__ u64 s_base;
-  __shared__ u32 s_warp[MERGE_THREADS / 32];
-  __shared__ int s_lb_first[MERGE_THREADS / 32];
-  __shared__ u64 s_lb_all[MERGE_THREADS / 32], s_lb_upto[MERGE_THREADS / 32];
-  TileScratch sc{&s_base, s_warp, s_lb_first, s_lb_all, s_lb_upto};
-
-  const int tid = threadIdx.x;
-  const u64 total = nA + nB;
-  bool any_flip = false;
-#pragma unroll
-  for (int l = 0; l < L; l++) any_flip = any_flip || (f.f[l] != 0);
-  const long long pa = (long long)(((unsigned long long)(size_t)A.c[0]) >> 3) & 1;
-  const long long pb = (long long)(((unsigned long long)(size_t)B.c[0]) >> 3) & 1;
-
-  // geometry of a tile + (thread 0) issue of its TMA copies into buffer `st`
-  struct Geo { int oa, ob, na, nb; bool has_prev, has_next; };
-  auto stage_tile = [&](u32 t, int st) {
-    Geo g;
-    const u64 d0 = (u64)t * TILE;
-    const u64 d1 = (d0 + TILE < total) ? d0 + TILE : total;
-    const u64 a0 = part[t], a1 = part[t + 1];
-    const u64 b0 = d0 - a0, b1 = d1 - a1;
-    g.na = (int)(a1 - a0);
-    g.nb = (int)(b1 - b0);
-    g.has_prev = a0 > 0;
-    g.has_next = b1 < nB;
-    const long long fa = (long long)a0 - (g.has_prev ? 1 : 0);
-    const long long ga = fa - ((fa + pa) & 1);
-    const int ca = ((long long)a1 > fa) ? (int)((((long long)a1 - ga) + 1) & ~1ll) : 0;
-    g.oa = (int)((long long)a0 - ga);
-    const int sb = (g.oa + g.na + 1) & ~1;
-    const long long eb = (long long)b1 + (g.has_next ? 1 : 0);
-    const long long gb = (long long)b0 - (((long long)b0 + pb) & 1);
-    const int cb = (eb > (long long)b0) ? (int)(((eb - gb) + 1) & ~1ll) : 0;
-    g.ob = sb + (int)((long long)b0 - gb);
-    if (tid == 0) {
-      u64* sl = (u64*)(smem_raw + (size_t)st * PersistCfg<L>::BUF);
-      i64* sw = (i64*)(sl + (size_t)L * S);
-      const unsigned bytes = (unsigned)(ca + cb) * 8u * (L + 1);   // > 0: a tile has at least one row
-      // the buffer was last written through the generic proxy (output weights,
-      // sign flips): order those writes before the async-proxy (TMA) writes
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(&s_mbar[st], bytes);
-      if (ca) {
-#pragma unroll
-        for (int l = 0; l < L; l++) tma_bulk_g2s(sl + l * S, A.c[l] + ga, (unsigned)ca * 8u, &s_mbar[st]);
-        tma_bulk_g2s(sw, wA + ga, (unsigned)ca * 8u, &s_mbar[st]);
-      }
-      if (cb) {
-#pragma unroll
-        for (int l = 0; l < L; l++) tma_bulk_g2s(sl + l * S + sb, B.c[l] + gb, (unsigned)cb * 8u, &s_mbar[st]);
-        tma_bulk_g2s(sw + sb, wB + gb, (unsigned)cb * 8u, &s_mbar[st]);
-      }
-    }
-    return g;
-  };
-
-  if (tid == 0) {
-    mbar_init(&s_mbar[0], 1);
-    mbar_init(&s_mbar[1], 1);
-    s_next = atomicAdd(ticket, 1u);
-  }
-  __syncthreads();
-  u32 t = s_next;
-  if (t >= ntiles) return;
-  Geo cur = stage_tile(t, 0);
-  unsigned phase0 = 0, phase1 = 0;
-  for (int it = 0;; it++) {
-    const int st = it & 1;
-    __syncthreads();   // every thread has left the previous tile: buffer st^1 and s_next are free
-    if (tid == 0) s_next = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const u32 tn = s_next;
-    Geo nxt = cur;
-    if (tn < ntiles) nxt = stage_tile(tn, st ^ 1);
-    // current tile
-    if (st == 0) { mbar_wait(&s_mbar[0], phase0); phase0 ^= 1; }
-    else { mbar_wait(&s_mbar[1], phase1); phase1 ^= 1; }
-    u64* sl = (u64*)(smem_raw + (size_t)st * PersistCfg<L>::BUF);
-    i64* sw = (i64*)(sl + (size_t)L * S);
-    if (any_flip) {
-      for (int x = tid; x < S; x += MERGE_THREADS) {
-#pragma unroll
-        for (int l = 0; l < L; l++) sl[l * S + x] ^= f.f[l];
-      }
-      __syncthreads();
-    }
-    merge_process_tile<L>(sl, sw, perm, cur.oa, cur.ob, cur.na, cur.nb, cur.has_prev, cur.has_next, t, ntiles, status, O, wO,
-                          n_out, f, sc);
-    if (tn >= ntiles) break;
-    t = tn;
-    cur = nxt;
-  }
-}
-
 // all arrays of the batch share the 16-byte phase of element 0 (true unless a
 // view mixes storage, e.g. a negated slice): precondition of the TMA path
 bool uniform_phase(const Batch* b) {
@@ -588,24 +488,9 @@ int32_t merge_launch(Ctx* ctx, const Batch* a, const Batch* b, Batch** out) {
     ProfScope ps(ctx, KID_MERGE_PARTITION, (u64)(ntiles + 1) * 8);
     k_merge_partition<L><<<(ntiles + 1 + 127) / 128, 128, 0, st>>>(a->cols(), a->n, b->cols(), b->n, f, Cfg::TILE, ntiles, part);
   }
-  static const bool persist_on = getenv("DBSP_MERGE_PERSISTENT") != nullptr;
   ProfScope* ps = new ProfScope(ctx, KID_MERGE, 0);
-  if (persist_on && use_tma) {
-    static bool pattr = false;
-    static int per_sm = 1;
-    if (!pattr) {
-      CUDA_TRY(cudaFuncSetAttribute(k_merge_persist<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PersistCfg<L>::SMEM));
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_persist<L>, MERGE_THREADS, PersistCfg<L>::SMEM));
-      if (per_sm < 1) per_sm = 1;
-      pattr = true;
-    }
-    u32 grid = std::min<u32>(ntiles, (u32)(ctx->sm_count * per_sm));
-    k_merge_persist<L><<<grid, MERGE_THREADS, PersistCfg<L>::SMEM, st>>>(a->cols(), a->w, a->n, b->cols(), b->w, b->n, f, part,
-                                                                       ntiles, ticket, status, oc, ow, n_out);
-  } else {
-    k_merge_tiles<L><<<ntiles, MERGE_THREADS, Cfg::SMEM, st>>>(a->cols(), a->w, a->n, b->cols(), b->w, b->n, f, part, ntiles,
-                                                             ticket, status, oc, ow, n_out, use_tma);
-  }
+  k_merge_tiles<L><<<ntiles, MERGE_THREADS, Cfg::SMEM, st>>>(a->cols(), a->w, a->n, b->cols(), b->w, b->n, f, part, ntiles,
+                                                           ticket, status, oc, ow, n_out, use_tma);
   long ps_idx = ps->idx;
   delete ps;   // records the end event
   ctx->kernel_launches += 2;
