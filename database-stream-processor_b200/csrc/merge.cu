@@ -151,62 +151,49 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, i64* sw, u32* perm, 
   int* s_lb_first = sc.s_lb_first;
   u64* s_lb_all = sc.s_lb_all;
   u64* s_lb_upto = sc.s_lb_upto;
+  auto le = [&](int ia, int ib) {   // staged row ia <= staged row ib
+#pragma unroll
+    for (int l = 0; l < L; l++) {
+      u64 a = sl[l * S + ia], b = sl[l * S + ib];
+      if (a != b) return a < b;
+    }
+    return true;
+  };
+
   // ---- per-thread merge path ------------------------------------------------
-  // Straight-line code throughout (no data-dependent branches): lanes of a warp
-  // take A and B rows in arbitrary interleavings, and divergent paths would be
-  // executed one after the other.
   const int n = na + nb;
   int dt = tid * IPT;
   if (dt > n) dt = n;
   int lo = dt > nb ? dt - nb : 0, hi = dt < na ? dt : na;
-  {
-    // fixed trip count: the search range is at most TILE wide
-    constexpr int STEPS = 32 - __builtin_clz((unsigned)MergeCfg<L>::TILE);
-#pragma unroll 1
-    for (int it = 0; it < STEPS; it++) {
-      const bool active = lo < hi;
-      const int mid = (lo + hi) >> 1;
-      const int ia = oa + (active ? mid : 0), ib = ob + (active ? (dt - 1 - mid) : 0);
-      bool lt = false, eq = true;   // staged row ia vs ib
-#pragma unroll
-      for (int l = 0; l < L; l++) {
-        const u64 a = sl[l * S + ia], b = sl[l * S + ib];
-        lt = lt || (eq && a < b);
-        eq = eq && (a == b);
-      }
-      const bool le = lt || eq;
-      lo = (active && le) ? mid + 1 : lo;
-      hi = (active && !le) ? mid : hi;
-    }
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (le(oa + mid, ob + (dt - 1 - mid))) lo = mid + 1; else hi = mid;
   }
   int ai = lo, bi = dt - lo;
 
   // Serial merge with both run heads held in registers: one 3-way compare per
-  // row; the head of the advanced side is re-read from shared memory through a
-  // single (selected) address.  `prev_eq` says the previous merged row was an A
-  // row equal to the current B head.
+  // row, only the advanced side is re-read from shared memory.  `prev_eq`
+  // says the previous merged row was an A row equal to the current B head.
   u64 ka[L], kb[L];
   i64 wa = 0, wb = 0;
+  auto load_a = [&](int i) {
 #pragma unroll
-  for (int l = 0; l < L; l++) { ka[l] = 0; kb[l] = 0; }
-  bool a_ok = ai < na;
-  bool b_in = bi < nb;
-  bool b_readable = b_in || (bi == nb && has_next);
-  {
-    const int ia = oa + (a_ok ? ai : 0), ib = ob + (b_readable ? bi : 0);
+    for (int l = 0; l < L; l++) ka[l] = sl[l * S + oa + i];
+    wa = sw[oa + i];
+  };
+  auto load_b = [&](int j) {
 #pragma unroll
-    for (int l = 0; l < L; l++) { ka[l] = sl[l * S + ia]; kb[l] = sl[l * S + ib]; }
-    wa = sw[ia];
-    wb = sw[ib];
-  }
-  bool prev_eq;
-  {
-    const bool chk = (ai > 0 || has_prev) && b_in;   // A[ai-1] (slot oa+ai-1; halo at oa-1) vs B head
-    const int ip = chk ? (oa + ai - 1) : oa;
-    bool eq = true;
+    for (int l = 0; l < L; l++) kb[l] = sl[l * S + ob + j];
+    wb = sw[ob + j];
+  };
+  bool b_readable = (bi < nb) || (bi == nb && has_next);
+  if (ai < na) load_a(ai);
+  if (b_readable) load_b(bi);
+  bool prev_eq = false;
+  if ((ai > 0 || has_prev) && bi < nb) {   // A[ai-1] (slot oa+ai-1; halo at oa-1) vs B head
+    prev_eq = true;
 #pragma unroll
-    for (int l = 0; l < L; l++) eq = eq && (sl[l * S + ip] == kb[l]);
-    prev_eq = chk && eq;
+    for (int l = 0; l < L; l++) prev_eq = prev_eq && (sl[l * S + oa + ai - 1] == kb[l]);
   }
 
   u32 src[IPT];
@@ -214,43 +201,37 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, i64* sw, u32* perm, 
   u32 keep = 0;
 #pragma unroll
   for (int k = 0; k < IPT; k++) {
-    const bool live = ai + bi < n;
-    bool lt = false, eq = true;   // A head vs B head
+    src[k] = 0;
+    wv[k] = 0;
+    if (ai + bi < n) {
+      const bool a_ok = ai < na, b_in = bi < nb;
+      int c = 0;   // cmp3(A head, B head) when both are readable
+      if (a_ok && b_readable) {
 #pragma unroll
-    for (int l = 0; l < L; l++) {
-      lt = lt || (eq && ka[l] < kb[l]);
-      eq = eq && (ka[l] == kb[l]);
+        for (int l = 0; l < L; l++) {
+          if (c == 0 && ka[l] != kb[l]) c = ka[l] < kb[l] ? -1 : 1;
+        }
+      }
+      const bool take_a = !b_in || (a_ok && c <= 0);
+      if (take_a) {
+        const bool partner = b_readable && c == 0;
+        i64 w = partner ? (i64)((u64)wa + (u64)wb) : wa;
+        src[k] = oa + ai;
+        wv[k] = w;
+        if (w != 0) keep |= 1u << k;
+        prev_eq = partner;
+        ai++;
+        if (ai < na) load_a(ai);
+      } else {
+        src[k] = ob + bi;
+        wv[k] = wb;
+        if (!prev_eq && wb != 0) keep |= 1u << k;
+        prev_eq = false;
+        bi++;
+        b_readable = (bi < nb) || (bi == nb && has_next);
+        if (b_readable) load_b(bi);
+      }
     }
-    const bool both = a_ok && b_readable;
-    const bool take_a = !b_in || (a_ok && (lt || eq));   // b_readable implies comparable heads; !b_in forces A
-    const bool partner = take_a && both && eq;
-    const i64 w = take_a ? (partner ? (i64)((u64)wa + (u64)wb) : wa) : wb;
-    src[k] = take_a ? (u32)(oa + ai) : (u32)(ob + bi);
-    wv[k] = w;
-    const bool kept = live && (take_a ? (w != 0) : (!prev_eq && wb != 0));
-    keep |= kept ? (1u << k) : 0u;
-    prev_eq = live ? partner : prev_eq;
-    ai += (live && take_a) ? 1 : 0;
-    bi += (live && !take_a) ? 1 : 0;
-    // reload the advanced head (one address, predicated)
-    const bool na_ok = ai < na;
-    const bool nb_in = bi < nb;
-    const bool nb_rd = nb_in || (bi == nb && has_next);
-    const bool adv_a = live && take_a, adv_b = live && !take_a;
-    const bool ld_ok = adv_a ? na_ok : (adv_b ? nb_rd : false);
-    const int nidx = ld_ok ? (adv_a ? oa + ai : ob + bi) : oa;
-    i64 nw = sw[nidx];
-#pragma unroll
-    for (int l = 0; l < L; l++) {
-      const u64 v = sl[l * S + nidx];
-      ka[l] = (adv_a && ld_ok) ? v : ka[l];
-      kb[l] = (adv_b && ld_ok) ? v : kb[l];
-    }
-    wa = (adv_a && ld_ok) ? nw : wa;
-    wb = (adv_b && ld_ok) ? nw : wb;
-    a_ok = na_ok;
-    b_in = nb_in;
-    b_readable = nb_rd;
   }
 
   // ---- block exclusive scan of kept counts ------------------------------------
