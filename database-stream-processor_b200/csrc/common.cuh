@@ -167,8 +167,10 @@ int32_t inclusive_scan_i64(Ctx* ctx, const i64* in, i64* out, u64 n);
 // `cols`/`w` are device arrays of n rows; w == nullptr means all +1.
 // `adopt` (optional): the buffer that owns cols/w; when the rows turn out to be
 // canonical already (ordered, duplicate- and zero-free) it becomes the batch.
+// `d_n` (optional): the exact row count lives on the device and `n` is only an
+// upper bound; the census returns it (saves the producer a read-back).
 int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const i64* w, u64 n, const BufP* adopt,
-                         Batch** out);
+                         Batch** out, const u32* d_n = nullptr);
 
 // ---- merge.cu --------------------------------------------------------------
 int32_t merge_batches(Ctx* ctx, const Batch* a, const Batch* b, Batch** out);

@@ -36,7 +36,11 @@ struct Plan {
 
 // mm[l] = min, mm[L+l] = max of flipped lane l; mm[2L] = # inversions
 // (row i-1 > row i), mm[2L+1] = # adjacent duplicates, mm[2L+2] = # zero weights.
-__global__ void k_props(Cols cols, Flips f, int L, const i64* w, u64 n, u64* mm) {
+__global__ void k_props(Cols cols, Flips f, int L, const i64* w, u64 n_host, const u32* dn, u64* mm) {
+  // the producer may have left the exact row count on the device (dn): the
+  // census then returns it with the lane ranges in the same read-back
+  const u64 n = dn ? (u64)*dn : n_host;
+  if (dn && blockIdx.x == 0 && threadIdx.x == 0) mm[2 * L + 3] = n;
   __shared__ u64 smin[MAXL], smax[MAXL];
   __shared__ unsigned s_cnt[3];
   if (threadIdx.x < MAXL) { smin[threadIdx.x] = ~0ull; smax[threadIdx.x] = 0; }
@@ -92,7 +96,7 @@ __global__ void k_props(Cols cols, Flips f, int L, const i64* w, u64 n, u64* mm)
 __global__ void k_init_props(u64* mm, int L) {
   int t = threadIdx.x;
   if (t < L) mm[t] = ~0ull;
-  else if (t < 2 * L + 3) mm[t] = 0;
+  else if (t < 2 * L + 4) mm[t] = 0;
 }
 
 // key[i] = word `wd` of row (idx ? idx[i] : i); writes idx_out[i] = i when idx == nullptr.
@@ -402,30 +406,34 @@ inline int bits_for(u64 range) { return range == 0 ? 0 : 64 - __builtin_clzll(ra
 }  // namespace
 
 int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const i64* w, u64 n, const BufP* adopt,
-                         Batch** out) {
+                         Batch** out, const u32* d_n) {
   const int L = s.n_key_lanes + s.n_val_lanes;
-  if (n == 0) { *out = batch_new_empty(ctx, s); return DBSP_OK; }
+  if (n == 0) { *out = batch_new_empty(ctx, s); return DBSP_OK; }   // with d_n: n is an upper bound
   if (n >= (1ull << 32)) { set_error("consolidate: more than 2^32-1 rows in one batch"); return DBSP_ERR_UNSUPPORTED; }
   cudaStream_t st = ctx->stream;
   const int TB = 256;
-  const unsigned nblk = (unsigned)((n + TB - 1) / TB);
 
   Flips f;
   for (int l = 0; l < MAXL; l++) f.f[l] = (l < L && s.lane_types[l] == DBSP_I64) ? 0x8000000000000000ull : 0;
 
   // ---- (1) lane ranges + order / duplicate / zero-weight census ---------------
-  u64 mm[2 * MAXL + 3];
+  u64 mm[2 * MAXL + 4];
   {
     u64* dmm = ctx->d_scratch + 64;
     k_init_props<<<1, 32, 0, st>>>(dmm, L);
     int g = (int)std::min<u64>((n + TB - 1) / TB, (u64)ctx->sm_count * 8);
     {
       ProfScope ps(ctx, KID_MINMAX, n * (u64)(L + (w ? 1 : 0)) * 8);
-      k_props<<<g, TB, 0, st>>>(cols, f, L, w, n, dmm);
+      k_props<<<g, TB, 0, st>>>(cols, f, L, w, n, d_n, dmm);
     }
     ctx->kernel_launches += 2;
-    TRY(read_back(ctx, dmm, 2 * L + 3, mm));
+    TRY(read_back(ctx, dmm, 2 * L + 4, mm));
+    if (d_n) {
+      n = mm[2 * L + 3];
+      if (n == 0) { *out = batch_new_empty(ctx, s); return DBSP_OK; }
+    }
   }
+  const unsigned nblk = (unsigned)((n + TB - 1) / TB);
   const u64 n_inv = mm[2 * L], n_dup = mm[2 * L + 1], n_zero = mm[2 * L + 2];
 
   Plan p;

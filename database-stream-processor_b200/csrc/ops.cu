@@ -534,7 +534,8 @@ int32_t project_and_consolidate(Ctx* ctx, const Cols& in, int nk_in, int n_in_la
   TRY(dev_alloc(ctx, (size_t)(g + 1) * 4 * 2, &cb));
   u32* blk_cnt = (u32*)cb->p;
   u32* blk_base = blk_cnt + (g + 1);
-  u64 m = n;
+  u64 m = n;   // upper bound when a filter is present
+  const u32* d_m = nullptr;
   MCols none;
   for (int l = 0; l < MAXL; l++) none.c[l] = nullptr;
   long pidx;
@@ -546,14 +547,11 @@ int32_t project_and_consolidate(Ctx* ctx, const Cols& in, int nk_in, int n_in_la
       LAUNCH_COUNT(ctx);
       CUDA_TRY(cudaMemsetAsync(blk_cnt + g, 0, 4, ctx->stream));
       TRY(exclusive_scan_u32(ctx, blk_cnt, blk_base, g));
-      u32 tot;
-      TRY(read_back32(ctx, blk_base + g, &tot));
-      m = tot;
+      d_m = blk_base + g;   // surviving-row count stays on the device; the census of consolidate_rows returns it
     } else {
       k_iota_u32<<<(g + TB - 1) / TB, TB, 0, ctx->stream>>>(blk_base, g, PROJ_ROWS);
       LAUNCH_COUNT(ctx);
     }
-    if (m == 0) { *out = batch_new_empty(ctx, os); return DBSP_OK; }
   }
   TmpRows t;
   TRY(tmp_alloc(ctx, Lo, m, &t));
@@ -563,7 +561,7 @@ int32_t project_and_consolidate(Ctx* ctx, const Cols& in, int nk_in, int n_in_la
   }
   LAUNCH_COUNT(ctx);
   if (pidx >= 0) ctx->prof[pidx].bytes = proj.n_pred > 0 ? n * (u64)used_lanes(proj, n_in_lanes, nk_in) * 8 : 0;
-  return consolidate_rows(ctx, os, t.cc(), t.w, m, &t.buf, out);
+  return consolidate_rows(ctx, os, t.cc(), t.w, m, &t.buf, out, d_m);
 }
 
 // Probe `delta` against every batch of `trace` and expand the matches.
