@@ -293,11 +293,15 @@ class Stream:
 
         return l._binary(r, fn, "join_incremental", proj.schema)
 
-    def aggregate(self, aggregator) -> "Stream":
+    def aggregate(self, aggregator, local: bool = False) -> "Stream":
         """aggregate (operator/aggregate/mod.rs:204-244): AggregateIncremental
-        over stream.trace(), then upsert into the output trace."""
+        over stream.trace(), then upsert into the output trace.
+        `local=True` skips the shard(): every worker aggregates its own rows —
+        the first level of a two-level aggregate for semigroup aggregators
+        (MinSemigroup / MaxSemigroup, aggregate/min.rs:17-27), whose partial
+        results are then aggregated again after a shard of <= P rows per key."""
         be = self.circuit.be
-        s = self.shard()
+        s = Stream(self.circuit, self.node, self.schema, True) if local else self.shard()
         kind = aggregator.kind
         if kind in (capi.AGG_MAX, capi.AGG_MIN):
             out_schema = s.schema
@@ -311,7 +315,7 @@ class Stream:
             out_tr.insert(out)
             return out
 
-        return s._unary(fn, "aggregate", out_schema, True)
+        return s._unary(fn, "aggregate", out_schema, not local)
 
     def weigh(self, f, mode=capi.WEIGH_LINEAR) -> "Stream":
         """weigh (operator/aggregate/mod.rs:285-323)."""
@@ -322,7 +326,7 @@ class Stream:
     def aggregate_linear(self, f) -> "Stream":
         """aggregate_linear (aggregate/mod.rs:253-273) = weigh(f).aggregate(WeightedCount)."""
         be = self.circuit.be
-        w = self.shard().weigh(f)
+        w = self.weigh(f).shard()   # weigh first (linear): only one row per key crosses the exchange
         out_schema = Schema(self.schema.key, "i")
         in_tr, out_tr = Spine(be, w.schema), Spine(be, out_schema)
 
@@ -343,7 +347,10 @@ class Stream:
         result is re-consolidated, which only removes +1/-1 pairs that the
         reference's downstream map/from_tuples would cancel anyway."""
         be = self.circuit.be
-        w = self.shard().weigh(f, capi.WEIGH_AVG)
+        # weigh first (linear): <= 2 rows per key cross the exchange; shard on K only so that
+        # the (K,0) and (K,1) rows of a key meet on one worker (index() is a zero-copy view)
+        nk0 = self.schema.nk
+        w = self.weigh(f, capi.WEIGH_AVG).index(nk0).shard().index(nk0 + 1)
         pair_schema = Schema(self.schema.key, "ii")
         out_schema = Schema(self.schema.key, "i")
         in_tr, out_tr = Spine(be, w.schema), Spine(be, pair_schema)

@@ -79,6 +79,11 @@ def q7(inp: NexmarkTables) -> Stream:
     bids_by_price = windowed.map_index(Proj(Schema("u", "uuuuu"), [lval(2), lval(0), lval(1), lval(2), key(0), lval(3)]))
     # ((), -price) -> Min -> max price  (q7.rs:82-91)
     neg_price = windowed.map_index(Proj(Schema("", "i"), [-lval(2)]))
+    if windowed.circuit.workers > 1:
+        # The single group () would shard every windowed bid to one worker.  Min is a
+        # semigroup (aggregate/min.rs:17-27): aggregate per worker first, then
+        # aggregate the <= P partial minima.
+        neg_price = neg_price.aggregate(Min, local=True)
     max_price = neg_price.aggregate(Min).map(Proj(Schema("u"), [-lval(0)]))
     # all bids with the max price  (q7.rs:92-93)
     return max_price.join(bids_by_price, Proj(Schema("uuuuu"), [rval(0), rval(1), rval(2), rval(3), rval(4)]))
