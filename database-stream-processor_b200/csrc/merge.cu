@@ -94,7 +94,9 @@ struct MergeCfg {
 #endif
   static constexpr int TILE = MERGE_THREADS * IPT;
   static constexpr int S = TILE + 8;   // staged slots per array (even; room for alignment slack + halos)
-  static constexpr size_t SMEM = (size_t)S * (L + 1) * 8 + (size_t)TILE * 4;
+  // shared memory holds the staged lanes and 16-bit slot ids only; the weights
+  // never enter it (read from and written to HBM by the threads that need them)
+  static constexpr size_t SMEM = (size_t)S * L * 8 + (size_t)TILE * 2;
 };
 
 // a-count of the merge path at diagonal d: number of A rows among the first d
@@ -136,10 +138,14 @@ struct TileScratch {
 };
 
 // Everything after staging: per-thread merge path, serial merge, compaction,
-// decoupled look-back, coalesced stores.  `sl`/`sw` hold the staged tile with
-// the slot map of k_merge_tiles (A row a0+i at oa+i, B row b0+j at ob+j).
+// decoupled look-back, coalesced stores.  `sl` holds the staged lanes with the
+// slot map of k_merge_tiles (A row a0+i at oa+i, B row b0+j at ob+j); `wAg` /
+// `wBg` are the weight arrays offset to a0 / b0.  Input weights are never zero
+// (batch invariant), so only a partner sum can cancel: the weight loads stay
+// off the serial merge's critical path.
 template <int L>
-__device__ __forceinline__ void merge_process_tile(u64* sl, i64* sw, u32* perm, const int oa, const int ob, const int na,
+__device__ __forceinline__ void merge_process_tile(u64* sl, const i64* __restrict__ wAg, const i64* __restrict__ wBg,
+                                                   unsigned short* perm, const int oa, const int ob, const int na,
                                                    const int nb, const bool has_prev, const bool has_next, const u32 t,
                                                    const u32 ntiles, u64* status, const MCols& O, i64* wO, u64* n_out,
                                                    const Flips& f, const TileScratch& sc) {
@@ -179,12 +185,12 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, i64* sw, u32* perm, 
   auto load_a = [&](int i) {
 #pragma unroll
     for (int l = 0; l < L; l++) ka[l] = sl[l * S + oa + i];
-    wa = sw[oa + i];
+    wa = wAg[i];
   };
   auto load_b = [&](int j) {
 #pragma unroll
     for (int l = 0; l < L; l++) kb[l] = sl[l * S + ob + j];
-    wb = sw[ob + j];
+    wb = wBg[j];
   };
   bool b_readable = (bi < nb) || (bi == nb && has_next);
   if (ai < na) load_a(ai);
@@ -215,17 +221,22 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, i64* sw, u32* perm, 
       const bool take_a = !b_in || (a_ok && c <= 0);
       if (take_a) {
         const bool partner = b_readable && c == 0;
-        i64 w = partner ? (i64)((u64)wa + (u64)wb) : wa;
         src[k] = oa + ai;
-        wv[k] = w;
-        if (w != 0) keep |= 1u << k;
+        if (partner) {   // rare: the only place a weight value steers control flow
+          const i64 w = (i64)((u64)wa + (u64)wb);
+          wv[k] = w;
+          if (w != 0) keep |= 1u << k;
+        } else {
+          wv[k] = wa;
+          keep |= 1u << k;
+        }
         prev_eq = partner;
         ai++;
         if (ai < na) load_a(ai);
       } else {
         src[k] = ob + bi;
         wv[k] = wb;
-        if (!prev_eq && wb != 0) keep |= 1u << k;
+        if (!prev_eq) keep |= 1u << k;
         prev_eq = false;
         bi++;
         b_readable = (bi < nb) || (bi == nb && has_next);
@@ -243,7 +254,7 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, i64* sw, u32* perm, 
     if ((tid & 31) >= o) incl += v;
   }
   if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
-  __syncthreads();   // also: every thread is done reading sw (weights are in registers)
+  __syncthreads();
   u32 warp_off = 0, tile_total = 0;
 #pragma unroll
   for (int wi = 0; wi < MERGE_THREADS / 32; wi++) {
@@ -257,8 +268,7 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, i64* sw, u32* perm, 
 #pragma unroll
   for (int k = 0; k < IPT; k++) {
     if (keep & (1u << k)) {
-      perm[off] = src[k];
-      sw[off] = wv[k];
+      perm[off] = (unsigned short)src[k];
       off++;
     }
   }
@@ -319,12 +329,25 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, i64* sw, u32* perm, 
     u32 s = perm[o];
 #pragma unroll
     for (int l = 0; l < L; l++) O.c[l][base + o] = sl[l * S + s] ^ f.f[l];
-    wO[base + o] = sw[o];
+  }
+  {   // weights: straight from registers to the thread's own (contiguous) output slots
+    u64 wpos = base + (off - cnt);
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+      if (keep & (1u << k)) wO[wpos++] = wv[k];
+    }
   }
 }
 
+// min CTAs/SM: caps registers at 42 for the narrow rows (6 CTAs fit their 32 KB tiles);
+// measured: without the cap ptxas' 48-register schedule runs 2.5x slower
+#ifdef MERGE_MIN_CTAS
+#define MERGE_MIN_CTAS_FOR(L) MERGE_MIN_CTAS
+#else
+#define MERGE_MIN_CTAS_FOR(L) ((L) <= 2 ? 6 : 3)
+#endif
 template <int L>
-__global__ void __launch_bounds__(MERGE_THREADS)
+__global__ void __launch_bounds__(MERGE_THREADS, MERGE_MIN_CTAS_FOR(L))
 k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __restrict__ wB, u64 nB, Flips f,
               const u64* __restrict__ part, u32 ntiles, u32* ticket, u64* status, MCols O, i64* wO, u64* n_out,
               int use_tma) {
@@ -332,9 +355,8 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
   constexpr int TILE = MergeCfg<L>::TILE;
   constexpr int S = MergeCfg<L>::S;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  u64* sl = (u64*)smem_raw;                 // L lanes of S staged slots
-  i64* sw = (i64*)(sl + (size_t)L * S);     // S weights; reused as output weights
-  u32* perm = (u32*)(sw + S);               // TILE staged-slot indices of kept rows
+  u64* sl = (u64*)smem_raw;                                   // L lanes of S staged slots
+  unsigned short* perm = (unsigned short*)(sl + (size_t)L * S);   // TILE staged-slot ids of kept rows
   __shared__ __align__(8) u64 s_mbar;
   __shared__ u32 s_tile;
   __shared__ u64 s_base;
@@ -379,18 +401,16 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
     const int cb = (eb > (long long)b0) ? (int)(((eb - gb) + 1) & ~1ll) : 0;
     ob = sb + (int)((long long)b0 - gb);
     if (tid == 0) {
-      const unsigned bytes = (unsigned)(ca + cb) * 8u * (L + 1);
+      const unsigned bytes = (unsigned)(ca + cb) * 8u * L;
       if (bytes) {
         mbar_expect_tx(&s_mbar, bytes);
         if (ca) {
 #pragma unroll
           for (int l = 0; l < L; l++) tma_bulk_g2s(sl + l * S, A.c[l] + ga, (unsigned)ca * 8u, &s_mbar);
-          tma_bulk_g2s(sw, wA + ga, (unsigned)ca * 8u, &s_mbar);
         }
         if (cb) {
 #pragma unroll
           for (int l = 0; l < L; l++) tma_bulk_g2s(sl + l * S + sb, B.c[l] + gb, (unsigned)cb * 8u, &s_mbar);
-          tma_bulk_g2s(sw + sb, wB + gb, (unsigned)cb * 8u, &s_mbar);
         }
       }
     }
@@ -409,7 +429,6 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
           const u64 g = from_a ? (a0 + x - 1) : (b0 + (x - 1 - na));
 #pragma unroll
           for (int l = 0; l < L; l++) cp_async8(&sl[l * S + x], (from_a ? A.c[l] : B.c[l]) + g);
-          cp_async8(&sw[x], (from_a ? wA : wB) + g);
         }
       }
     }
@@ -425,17 +444,17 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
   __syncthreads();
 
   TileScratch sc{&s_base, s_warp, s_lb_first, s_lb_all, s_lb_upto};
-  merge_process_tile<L>(sl, sw, perm, oa, ob, na, nb, has_prev, has_next, t, ntiles, status, O, wO, n_out, f, sc);
+  merge_process_tile<L>(sl, wA + a0, wB + b0, perm, oa, ob, na, nb, has_prev, has_next, t, ntiles, status, O, wO, n_out, f, sc);
 }
 
 
-// all arrays of the batch share the 16-byte phase of element 0 (true unless a
-// view mixes storage, e.g. a negated slice): precondition of the TMA path
+// all lanes of the batch share the 16-byte phase of element 0 (lanes of one
+// allocation always do): precondition of the TMA path
 bool uniform_phase(const Batch* b) {
   size_t ph = ((size_t)b->col[0] >> 3) & 1;
   for (int l = 1; l < b->nl(); l++)
     if ((((size_t)b->col[l] >> 3) & 1) != ph) return false;
-  return (((size_t)b->w >> 3) & 1) == ph;
+  return true;   // the weights are not staged
 }
 
 template <int L>
