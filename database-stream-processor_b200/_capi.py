@@ -75,6 +75,12 @@ _SIGS = {
     "upload_free": [_P],
     "batch_empty": [_P, C.POINTER(CSchema), _PP],
     "batch_merge": [_P, _P, _P, _PP],
+    "batch_merge_bounded": [_P, _P, _P, _U64P, _PP],
+    "merger_new": [_P, _P, _P, _U64P, _PP],
+    "merger_work": [_P, _P, _I64P],
+    "merger_done": [_P, _P, _PP],
+    "merger_free": [_P],
+    "batch_truncate_keys_below": [_P, _P, _U64P, _PP],
     "batch_neg": [_P, _P, _PP],
     "batch_reindex": [_P, _P, C.c_uint32, _PP],
     "batch_len": [_P, _U64P],
@@ -89,6 +95,8 @@ _SIGS = {
     "spine_insert": [_P, _P, _P],
     "spine_consolidate": [_P, _P, _PP],
     "spine_truncate_keys_below": [_P, _P, _U64P],
+    "spine_truncate_values_below": [_P, _P, _U64P],
+    "spine_exert": [_P, _P, _I64P],
     "spine_len": [_P, _U64P, C.POINTER(C.c_uint32)],
     "spine_free": [_P],
     "join_delta_trace": [_P, _P, _P, C.POINTER(CProj), C.c_int32, _PP],

@@ -275,6 +275,18 @@ class Stream:
 
     join_index = join
 
+    def antijoin(self, other: "Stream") -> "Stream":
+        """antijoin (operator/join.rs:294-320): the rows of `self` whose key is
+        absent from `other` = self - self |x| distinct(other) with the identity
+        closure (k, v1)."""
+        s1 = self.shard()
+        s2 = other.distinct().shard()
+        nk, nv = self.schema.nk, self.schema.nv
+        ident = Proj(self.schema, [key(i) for i in range(nk)] + [lval(i) for i in range(nv)])
+        out = s1.minus(s1.join(s2, ident))
+        out.sharded = True   # mark_sharded (join.rs:316)
+        return out
+
     def join_incremental(self, other: "Stream", proj: Proj) -> "Stream":
         """join_incremental (operator/join.rs:136-155):
         I(a) |x| I(b) - z^-1(I(a)) |x| z^-1(I(b)), via stateless joins."""

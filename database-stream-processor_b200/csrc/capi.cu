@@ -12,6 +12,8 @@ void pool_release_all(Ctx* ctx);
 struct dbsp_ctx : Ctx {};
 struct dbsp_batch : Batch {};
 struct dbsp_spine : Spine {};
+struct Merger;
+struct dbsp_merger;
 
 static inline Batch* B(const dbsp_batch* b) { return (Batch*)b; }
 static inline dbsp_batch* H(Batch* b) { return (dbsp_batch*)b; }
@@ -57,6 +59,7 @@ static int32_t stage_columns(Ctx* ctx, const u64* const* cols, int ncols, const 
 // geometric invariant with whole merges on the stream: while the two newest
 // batches are within 2x of each other they are merged (K3/K4).
 static int32_t spine_truncate_batch(Ctx* ctx, Spine* s, Batch* b, Batch** out);
+static int32_t spine_merge_newest(Ctx* ctx, Spine* s);
 static int32_t spine_insert(Ctx* ctx, Spine* s, Batch* b) {
   if (b->n == 0) return DBSP_OK;
   Batch* nb = nullptr;
@@ -73,14 +76,33 @@ static int32_t spine_insert(Ctx* ctx, Spine* s, Batch* b) {
     Batch* x = s->batches[m - 2];
     Batch* y = s->batches[m - 1];
     if (x->n >= 2 * y->n) break;
-    Batch* merged = nullptr;
-    TRY(merge_batches(ctx, x, y, &merged));
-    s->batches.pop_back();
-    s->batches.pop_back();
-    batch_unref(x);
-    batch_unref(y);
-    if (merged->n) s->batches.push_back(merged); else batch_unref(merged);
+    TRY(spine_merge_newest(ctx, s));
   }
+  return DBSP_OK;
+}
+
+// Merge of two batches with the spine's lower value bound applied to the
+// result (Merger::work(.., lower_val_bound, ..), spine_fueled.rs:866,911,981).
+static int32_t merge_bounded(Ctx* ctx, const Batch* x, const Batch* y, const u64* vbound, Batch** out) {
+  Batch* merged = nullptr;
+  TRY(merge_batches(ctx, x, y, &merged));
+  if (!vbound || merged->s.n_val_lanes == 0) { *out = merged; return DBSP_OK; }
+  int32_t rc = op_truncate_values(ctx, merged, vbound, out);
+  batch_unref(merged);
+  return rc;
+}
+
+static int32_t spine_merge_newest(Ctx* ctx, Spine* s) {
+  size_t m = s->batches.size();
+  Batch* x = s->batches[m - 2];
+  Batch* y = s->batches[m - 1];
+  Batch* merged = nullptr;
+  TRY(merge_bounded(ctx, x, y, s->has_vbound ? s->vbound : nullptr, &merged));
+  s->batches.pop_back();
+  s->batches.pop_back();
+  batch_unref(x);
+  batch_unref(y);
+  if (merged->n) s->batches.push_back(merged); else batch_unref(merged);
   return DBSP_OK;
 }
 
@@ -90,17 +112,23 @@ static int32_t spine_truncate_batch(Ctx* ctx, Spine* s, Batch* b, Batch** out) {
   u64 pos;
   TRY(batch_lower_bound(ctx, b, s->bound, &pos));
   if (pos == 0) { batch_ref(b); *out = b; return DBSP_OK; }
-  Batch* v = new Batch();
-  v->s = b->s;
-  v->ctx = ctx;
-  v->n = b->n - pos;
-  for (int l = 0; l < b->nl(); l++) v->col[l] = b->col[l] + pos;
-  v->w = b->w + pos;
-  v->bufs = b->bufs;
-  if (v->n == 0) v->nkeys = 0;
-  *out = v;
+  *out = batch_slice(ctx, b, pos, b->n);
   return DBSP_OK;
 }
+
+// The fuelled Merger (trace/mod.rs:371-396).  On the device a unit of fuel is
+// one input row: work() cuts the merge path `fuel` rows further along, merges
+// the two row ranges in between with the tile kernel and keeps the chunk; the
+// chunks are ordered and disjoint, done() concatenates them.
+struct Merger {
+  Ctx* ctx;
+  Batch *a, *b;
+  u64 ai = 0, bi = 0;
+  bool has_vb = false;
+  u64 vb[MAXL];
+  std::vector<Batch*> chunks;
+  bool complete() const { return ai == a->n && bi == b->n; }
+};
 
 extern "C" {
 
@@ -331,6 +359,80 @@ int32_t dbsp_batch_merge(dbsp_ctx* ctx, const dbsp_batch* a, const dbsp_batch* b
   return DBSP_OK;
 }
 
+int32_t dbsp_batch_merge_bounded(dbsp_ctx* ctx, const dbsp_batch* a, const dbsp_batch* b, const uint64_t* vb,
+                                 dbsp_batch** out) {
+  Batch* o = nullptr;
+  TRY(merge_bounded(ctx, B(a), B(b), vb, &o));
+  *out = H(o);
+  return DBSP_OK;
+}
+
+int32_t dbsp_batch_truncate_keys_below(dbsp_ctx* ctx, const dbsp_batch* b, const uint64_t* key, dbsp_batch** out) {
+  u64 pos;
+  TRY(batch_lower_bound(ctx, B(b), key, &pos));
+  if (pos == 0) { batch_ref(B(b)); *out = (dbsp_batch*)b; return DBSP_OK; }
+  *out = H(batch_slice(ctx, B(b), pos, B(b)->n));
+  return DBSP_OK;
+}
+
+int32_t dbsp_merger_new(dbsp_ctx* ctx, const dbsp_batch* a, const dbsp_batch* b, const uint64_t* vb, dbsp_merger** out) {
+  CHECK_ARG(memcmp(&B(a)->s, &B(b)->s, sizeof(dbsp_schema)) == 0, "merger_new: schema mismatch");
+  Merger* m = new Merger();
+  m->ctx = ctx;
+  m->a = B(a);
+  m->b = B(b);
+  batch_ref(m->a);
+  batch_ref(m->b);
+  if (vb && B(a)->s.n_val_lanes) {
+    m->has_vb = true;
+    for (int l = 0; l < B(a)->s.n_val_lanes; l++) m->vb[l] = vb[l];
+  }
+  *out = (dbsp_merger*)m;
+  return DBSP_OK;
+}
+
+int32_t dbsp_merger_work(dbsp_ctx* ctx, dbsp_merger* mm, int64_t* fuel) {
+  Merger* m = (Merger*)mm;
+  if (!m->complete() && *fuel > 0) {
+    u64 na, nb;
+    TRY(merge_path_split(ctx, m->a, m->b, m->ai + m->bi + (u64)*fuel, &na, &nb));
+    Batch* xa = batch_slice(ctx, m->a, m->ai, na);
+    Batch* xb = batch_slice(ctx, m->b, m->bi, nb);
+    Batch* chunk = nullptr;
+    int32_t rc = merge_bounded(ctx, xa, xb, m->has_vb ? m->vb : nullptr, &chunk);
+    batch_unref(xa);
+    batch_unref(xb);
+    if (rc) return rc;
+    m->chunks.push_back(chunk);
+    *fuel -= (int64_t)((na - m->ai) + (nb - m->bi));
+    m->ai = na;
+    m->bi = nb;
+  }
+  // fuel > 0 after the call <=> the merge is complete (trace/mod.rs:388-395)
+  if (m->complete()) { if (*fuel < 1) *fuel = 1; } else if (*fuel > 0) *fuel = 0;
+  return DBSP_OK;
+}
+
+int32_t dbsp_merger_free(dbsp_merger* mm) {
+  Merger* m = (Merger*)mm;
+  if (!m) return DBSP_OK;
+  for (Batch* c : m->chunks) batch_unref(c);
+  batch_unref(m->a);
+  batch_unref(m->b);
+  delete m;
+  return DBSP_OK;
+}
+
+int32_t dbsp_merger_done(dbsp_ctx* ctx, dbsp_merger* mm, dbsp_batch** out) {
+  Merger* m = (Merger*)mm;
+  CHECK_ARG(m->complete(), "merger_done: merge not complete");
+  Batch* o = nullptr;
+  TRY(batch_concat(ctx, m->a->s, m->chunks, &o));   // on failure the merger stays owned by the caller
+  dbsp_merger_free(mm);
+  *out = H(o);
+  return DBSP_OK;
+}
+
 int32_t dbsp_batch_neg(dbsp_ctx* ctx, const dbsp_batch* a, dbsp_batch** out) {
   Batch* o = nullptr;
   TRY(op_neg(ctx, B(a), &o));
@@ -433,9 +535,10 @@ int32_t dbsp_spine_insert(dbsp_ctx* ctx, dbsp_spine* s, const dbsp_batch* b) {
 }
 int32_t dbsp_spine_consolidate(dbsp_ctx* ctx, dbsp_spine* s, dbsp_batch** out) {
   Batch* acc = batch_new_empty(ctx, s->s);
+  const u64* vb = s->has_vbound ? s->vbound : nullptr;
   for (Batch* b : s->batches) {
     Batch* m = nullptr;
-    int32_t rc = merge_batches(ctx, acc, b, &m);
+    int32_t rc = merge_bounded(ctx, acc, b, vb, &m);
     batch_unref(acc);
     if (rc) return rc;
     acc = m;
@@ -444,6 +547,15 @@ int32_t dbsp_spine_consolidate(dbsp_ctx* ctx, dbsp_spine* s, dbsp_batch** out) {
   return DBSP_OK;
 }
 int32_t dbsp_spine_truncate_keys_below(dbsp_ctx* ctx, dbsp_spine* s, const uint64_t* key) {
+  bool raise = !s->has_bound;
+  if (!raise) {   // the bound only grows (spine_fueled.rs:223-233)
+    for (int l = 0; l < s->s.n_key_lanes; l++) {
+      u64 flip = s->s.lane_types[l] == DBSP_I64 ? 0x8000000000000000ull : 0ull;
+      u64 x = key[l] ^ flip, y = s->bound[l] ^ flip;
+      if (x != y) { raise = x > y; break; }
+    }
+  }
+  if (!raise) return DBSP_OK;
   s->has_bound = true;
   for (int l = 0; l < s->s.n_key_lanes; l++) s->bound[l] = key[l];
   std::vector<Batch*> keep;
@@ -454,6 +566,30 @@ int32_t dbsp_spine_truncate_keys_below(dbsp_ctx* ctx, dbsp_spine* s, const uint6
     if (v->n) keep.push_back(v); else batch_unref(v);
   }
   s->batches.swap(keep);
+  return DBSP_OK;
+}
+int32_t dbsp_spine_truncate_values_below(dbsp_ctx*, dbsp_spine* s, const uint64_t* val) {
+  int nk = s->s.n_key_lanes, nv = s->s.n_val_lanes;
+  bool raise = !s->has_vbound;
+  if (!raise) {   // the bound only grows (spine_fueled.rs:644-652)
+    for (int l = 0; l < nv; l++) {
+      u64 flip = s->s.lane_types[nk + l] == DBSP_I64 ? 0x8000000000000000ull : 0ull;
+      u64 x = val[l] ^ flip, y = s->vbound[l] ^ flip;
+      if (x != y) { raise = x > y; break; }
+    }
+  }
+  if (raise) for (int l = 0; l < nv; l++) s->vbound[l] = val[l];
+  s->has_vbound = true;
+  return DBSP_OK;
+}
+int32_t dbsp_spine_exert(dbsp_ctx* ctx, dbsp_spine* s, int64_t* effort) {
+  while (s->batches.size() >= 2) {
+    size_t m = s->batches.size();
+    int64_t cost = (int64_t)(s->batches[m - 2]->n + s->batches[m - 1]->n);
+    if (cost > *effort) break;
+    TRY(spine_merge_newest(ctx, s));
+    *effort -= cost;
+  }
   return DBSP_OK;
 }
 int32_t dbsp_spine_len(const dbsp_spine* s, uint64_t* n, uint32_t* nb) {

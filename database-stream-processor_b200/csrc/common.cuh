@@ -88,6 +88,8 @@ struct Spine {
   std::vector<Batch*> batches;   // oldest (largest) first; each holds one ref
   bool has_bound = false;
   u64 bound[MAXL];
+  bool has_vbound = false;   // lower_val_bound (spine_fueled.rs:118)
+  u64 vbound[MAXL];
   Ctx* ctx = nullptr;
 };
 
@@ -174,6 +176,7 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
 
 // ---- merge.cu --------------------------------------------------------------
 int32_t merge_batches(Ctx* ctx, const Batch* a, const Batch* b, Batch** out);
+int32_t merge_path_split(Ctx* ctx, const Batch* a, const Batch* b, u64 d, u64* na, u64* nb);
 
 // ---- device helpers ----------------------------------------------------------
 #ifdef __CUDACC__

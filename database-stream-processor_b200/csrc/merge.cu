@@ -128,6 +128,24 @@ __global__ void k_merge_partition(Cols A, u64 nA, Cols B, u64 nB, Flips f, u32 t
   part[t] = diag_search_g<L>(A, nA, B, nB, f, d);
 }
 
+// One merge-path split for the fuelled Merger: out[0] = a-count at diagonal d,
+// out[1] = 1 when the cut would separate an equal pair (A[a-1] == B[d-a]): the
+// caller then takes one more B row so that the pair's weights meet in one chunk.
+template <int L>
+__global__ void k_merge_split(Cols A, u64 nA, Cols B, u64 nB, Flips f, u64 d, u64* out) {
+  u64 a = diag_search_g<L>(A, nA, B, nB, f, d);
+  u64 j = d - a;
+  u64 pair = 0;
+  if (a > 0 && j < nB) {
+    pair = 1;
+#pragma unroll
+    for (int l = 0; l < L; l++)
+      if (A.c[l][a - 1] != B.c[l][j]) { pair = 0; break; }
+  }
+  out[0] = a;
+  out[1] = pair;
+}
+
 // Scratch shared by the phases of one tile (static shared memory of the kernel).
 struct TileScratch {
   u64* s_base;
@@ -505,7 +523,39 @@ int32_t merge_launch(Ctx* ctx, const Batch* a, const Batch* b, Batch** out) {
   return DBSP_OK;
 }
 
+template <int L>
+int32_t split_launch(Ctx* ctx, const Batch* a, const Batch* b, u64 d, u64* na, u64* nb) {
+  u64* dout = ctx->d_scratch + 124;
+  k_merge_split<L><<<1, 1, 0, ctx->stream>>>(a->cols(), a->n, b->cols(), b->n, a->flips(), d, dout);
+  ctx->kernel_launches++;
+  u64 h[2];
+  TRY(read_back(ctx, dout, 2, h));
+  *na = h[0];
+  *nb = d - h[0] + h[1];
+  return DBSP_OK;
+}
+
 }  // namespace
+
+// Rows of a and b among the first d rows of merge(a, b) (never separating an
+// equal pair): the chunk boundary of a fuelled merge.
+int32_t merge_path_split(Ctx* ctx, const Batch* a, const Batch* b, u64 d, u64* na, u64* nb) {
+  if (d >= a->n + b->n) { *na = a->n; *nb = b->n; return DBSP_OK; }
+  if (a->n == 0) { *na = 0; *nb = d; return DBSP_OK; }
+  if (b->n == 0) { *na = d; *nb = 0; return DBSP_OK; }
+  switch (a->nl()) {
+    case 1: return split_launch<1>(ctx, a, b, d, na, nb);
+    case 2: return split_launch<2>(ctx, a, b, d, na, nb);
+    case 3: return split_launch<3>(ctx, a, b, d, na, nb);
+    case 4: return split_launch<4>(ctx, a, b, d, na, nb);
+    case 5: return split_launch<5>(ctx, a, b, d, na, nb);
+    case 6: return split_launch<6>(ctx, a, b, d, na, nb);
+    case 7: return split_launch<7>(ctx, a, b, d, na, nb);
+    case 8: return split_launch<8>(ctx, a, b, d, na, nb);
+  }
+  set_error("merge: unsupported lane count");
+  return DBSP_ERR_UNSUPPORTED;
+}
 
 int32_t merge_batches(Ctx* ctx, const Batch* a, const Batch* b, Batch** out) {
   if (a->nl() != b->nl() || memcmp(&a->s, &b->s, sizeof(dbsp_schema)) != 0) {

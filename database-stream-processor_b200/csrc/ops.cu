@@ -244,6 +244,21 @@ __global__ void k_semijoin(Cols P, const i64* wP, u64 np, Cols K, const i64* wK,
   neww[i] = w;
 }
 
+// cursor.seek(val_bound) of the truncating merge (ordered/mod.rs:652-664,
+// 729-734) on flat rows: keep the rows whose value lanes are >= the bound.
+struct RowBound { u64 v[MAXL]; };   // value lanes, order-flipped
+__global__ void k_vals_ge(Cols C, u64 n, int nk, int nv, RowBound b, Flips f, u32* keep) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  if (i == n) { keep[n] = 0; return; }
+  bool ge = true;
+  for (int l = 0; l < nv; l++) {
+    u64 x = C.c[nk + l][i] ^ f.f[nk + l];
+    if (x != b.v[l]) { ge = x > b.v[l]; break; }
+  }
+  keep[i] = ge ? 1u : 0u;
+}
+
 // head flag over the first nk lanes (key boundaries of the flat rows).
 __global__ void k_key_heads(Cols C, u64 n, int nk, u32* flags) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -502,6 +517,87 @@ int32_t compact_ordered(Ctx* ctx, const dbsp_schema& s, const Cols& in, const i6
   k_scatter<<<blocks(n), TB, 0, ctx->stream>>>(in, L, w, keep, pos, n, oc, ow);
   LAUNCH_COUNT(ctx);
   *out = b;
+  return DBSP_OK;
+}
+
+// Drop the rows whose value is below `val_bound` (n_val_lanes u64).  Keys left
+// without values vanish with their rows.  Shares the batch when nothing is cut.
+int32_t op_truncate_values(Ctx* ctx, const Batch* b, const u64* val_bound, Batch** out) {
+  int nk = b->s.n_key_lanes, nv = b->s.n_val_lanes;
+  if (b->n == 0 || nv == 0) { batch_ref((Batch*)b); *out = (Batch*)b; return DBSP_OK; }
+  Flips f = b->flips();
+  RowBound rb;
+  for (int l = 0; l < nv; l++) rb.v[l] = val_bound[l] ^ f.f[nk + l];
+  u64 n = b->n;
+  BufP kb;
+  TRY(dev_alloc(ctx, (size_t)(n + 1) * 4 * 2, &kb));
+  u32* keep = (u32*)kb->p;
+  u32* pos = keep + (n + 1);
+  {
+    ProfScope ps(ctx, KID_COMPACT, n * (u64)nv * 8);
+    k_vals_ge<<<blocks(n + 1), TB, 0, ctx->stream>>>(b->cols(), n, nk, nv, rb, f, keep);
+  }
+  LAUNCH_COUNT(ctx);
+  TRY(exclusive_scan_u32(ctx, keep, pos, n));
+  u32 nout;
+  TRY(read_back32(ctx, pos + n, &nout));
+  if (nout == n) { batch_ref((Batch*)b); *out = (Batch*)b; return DBSP_OK; }
+  if (nout == 0) { *out = batch_new_empty(ctx, b->s); return DBSP_OK; }
+  Batch* o;
+  MCols oc;
+  i64* ow;
+  TRY(batch_alloc(ctx, b->s, nout, &o, &oc, &ow));
+  {
+    ProfScope ps(ctx, KID_COMPACT, (n + nout) * (u64)(b->nl() + 1) * 8);
+    k_scatter<<<blocks(n), TB, 0, ctx->stream>>>(b->cols(), b->nl(), b->w, keep, pos, n, oc, ow);
+  }
+  LAUNCH_COUNT(ctx);
+  *out = o;
+  return DBSP_OK;
+}
+
+// Zero-copy view of rows [lo, hi) of a batch (shares its storage).
+Batch* batch_slice(Ctx* ctx, const Batch* b, u64 lo, u64 hi) {
+  Batch* v = new Batch();
+  v->s = b->s;
+  v->ctx = ctx;
+  v->n = hi - lo;
+  for (int l = 0; l < b->nl(); l++) v->col[l] = b->col[l] + lo;
+  v->w = b->w + lo;
+  v->bufs = b->bufs;
+  if (v->n == 0) v->nkeys = 0;
+  return v;
+}
+
+// Concatenation of consolidated batches whose row ranges are already ordered
+// and disjoint (the chunks of a fuelled merge): device-to-device copies only.
+// Consumes one reference of each part.
+int32_t batch_concat(Ctx* ctx, const dbsp_schema& s, std::vector<Batch*>& parts, Batch** out) {
+  std::vector<Batch*> live;
+  u64 total = 0;
+  for (Batch* p : parts) {
+    if (p->n) { live.push_back(p); total += p->n; } else batch_unref(p);
+  }
+  parts.clear();
+  if (live.empty()) { *out = batch_new_empty(ctx, s); return DBSP_OK; }
+  if (live.size() == 1) { *out = live[0]; return DBSP_OK; }
+  Batch* o;
+  MCols oc;
+  i64* ow;
+  int32_t rc = batch_alloc(ctx, s, total, &o, &oc, &ow);
+  if (rc) { for (Batch* p : live) batch_unref(p); return rc; }
+  int L = s.n_key_lanes + s.n_val_lanes;
+  u64 off = 0;
+  for (Batch* p : live) {
+    for (int l = 0; l < L; l++)
+      cudaMemcpyAsync(oc.c[l] + off, p->col[l], p->n * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaMemcpyAsync(ow + off, p->w, p->n * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+    off += p->n;
+    batch_unref(p);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { batch_unref(o); set_error(cudaGetErrorString(e)); return DBSP_ERR_CUDA; }
+  *out = o;
   return DBSP_OK;
 }
 

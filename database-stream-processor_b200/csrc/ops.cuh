@@ -24,3 +24,6 @@ int32_t op_map_index(Ctx* ctx, const Batch* b, const dbsp_proj* proj, Batch** ou
 int32_t op_shard_partition(Ctx* ctx, const Batch* b, u32 P, Batch** outs);
 int32_t batch_build_csr(Ctx* ctx, Batch* b);
 int32_t batch_lower_bound(Ctx* ctx, const Batch* b, const u64* key, u64* pos);
+int32_t op_truncate_values(Ctx* ctx, const Batch* b, const u64* val_bound, Batch** out);
+Batch* batch_slice(Ctx* ctx, const Batch* b, u64 lo, u64 hi);
+int32_t batch_concat(Ctx* ctx, const dbsp_schema& s, std::vector<Batch*>& parts, Batch** out);

@@ -330,10 +330,62 @@ class Spine:
         k = (C.c_uint64 * capi.MAX_LANES)(*[int(x) & ((1 << 64) - 1) for x in key])
         self.be.api.call("spine_truncate_keys_below", self.be.ctx, self.h, k)
 
+    def truncate_values_below(self, val: Sequence[int]):
+        """Trace::truncate_values_below (spine_fueled.rs:644-656)."""
+        v = (C.c_uint64 * capi.MAX_LANES)(*[int(x) & ((1 << 64) - 1) for x in val])
+        self.be.api.call("spine_truncate_values_below", self.be.ctx, self.h, v)
+
+    def exert(self, effort: int) -> int:
+        """Trace::exert (spine_fueled.rs:627-634); returns the effort left."""
+        e = C.c_int64(int(effort))
+        self.be.api.call("spine_exert", self.be.ctx, self.h, C.byref(e))
+        return e.value
+
     def stats(self):
         n, nb = C.c_uint64(), C.c_uint32()
         self.be.api.call("spine_len", self.h, C.byref(n), C.byref(nb))
         return n.value, nb.value
+
+
+class Merger:
+    """The fuelled Merger (trace/mod.rs:371-396): new_merger / work / done."""
+
+    def __init__(self, be: "Backend", a: Batch, b: Batch, val_lower_bound: Sequence[int] | None = None):
+        self.be, self.schema = be, a.schema
+        self._keep = (a, b)
+        h = C.c_void_p()
+        be.api.call("merger_new", be.ctx, a.h, b.h, _lanes(val_lower_bound), C.byref(h))
+        self.h = h.value
+
+    def work(self, fuel: int) -> int:
+        """Spend up to `fuel`; the returned fuel is > 0 iff the merge is complete."""
+        f = C.c_int64(int(fuel))
+        self.be.api.call("merger_work", self.be.ctx, self.h, C.byref(f))
+        return f.value
+
+    def done(self) -> Batch:
+        out = C.c_void_p()
+        h, self.h = self.h, None   # freed by the library on success
+        try:
+            self.be.api.call("merger_done", self.be.ctx, h, C.byref(out))
+        except Exception:
+            self.h = h
+            raise
+        return Batch(self.be, out.value, self.schema)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.be.api._merger_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def _lanes(vals: Sequence[int] | None):
+    if vals is None:
+        return None
+    return (C.c_uint64 * capi.MAX_LANES)(*[int(x) & ((1 << 64) - 1) for x in vals])
 
 
 class Backend:
@@ -457,10 +509,21 @@ class Backend:
         return Batch(self, out.value, schema)
 
     # -- batch algebra -----------------------------------------------------
-    def merge(self, a: Batch, b: Batch) -> Batch:
+    def merge(self, a: Batch, b: Batch, val_lower_bound: Sequence[int] | None = None) -> Batch:
         out = self._out()
-        self.api.call("batch_merge", self.ctx, a.h, b.h, C.byref(out))
+        if val_lower_bound is None:
+            self.api.call("batch_merge", self.ctx, a.h, b.h, C.byref(out))
+        else:
+            self.api.call("batch_merge_bounded", self.ctx, a.h, b.h, _lanes(val_lower_bound), C.byref(out))
         return Batch(self, out.value, a.schema)
+
+    def merger(self, a: Batch, b: Batch, val_lower_bound: Sequence[int] | None = None) -> "Merger":
+        return Merger(self, a, b, val_lower_bound)
+
+    def truncate_keys_below(self, b: Batch, key: Sequence[int]) -> Batch:
+        out = self._out()
+        self.api.call("batch_truncate_keys_below", self.ctx, b.h, _lanes(key), C.byref(out))
+        return Batch(self, out.value, b.schema)
 
     def neg(self, a: Batch) -> Batch:
         out = self._out()

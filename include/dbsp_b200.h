@@ -190,6 +190,30 @@ int32_t dbsp_batch_empty(dbsp_ctx* ctx, const dbsp_schema* schema,
  * column_layer/builders.rs:98-169; ordered/mod.rs:344-396,806-834). */
 int32_t dbsp_batch_merge(dbsp_ctx* ctx, const dbsp_batch* a,
                          const dbsp_batch* b, dbsp_batch** out);
+/* Merger::work with a lower value bound, run to completion
+ * (trace/ord/indexed_zset_batch.rs:359-382 -> ordered/mod.rs:587-746
+ * push_merge_truncate_values_fueled): values below `val_lower_bound`
+ * (n_val_lanes u64; NULL = no bound) are dropped, keys left without values
+ * vanish.  OrdZSet batches (n_val_lanes == 0) ignore the bound
+ * (zset_batch.rs:307-318). */
+int32_t dbsp_batch_merge_bounded(dbsp_ctx* ctx, const dbsp_batch* a,
+                                 const dbsp_batch* b,
+                                 const uint64_t* val_lower_bound,
+                                 dbsp_batch** out);
+/* The fuelled Merger (trace/mod.rs:371-396: new_merger / work / done).
+ * work() spends at most *fuel units (here: input rows) and subtracts what it
+ * used; *fuel > 0 after the call <=> the merge is complete (:388-395).
+ * done() requires a complete merge, returns the batch and frees the merger. */
+typedef struct dbsp_merger dbsp_merger;
+int32_t dbsp_merger_new(dbsp_ctx* ctx, const dbsp_batch* a, const dbsp_batch* b,
+                        const uint64_t* val_lower_bound, dbsp_merger** out);
+int32_t dbsp_merger_work(dbsp_ctx* ctx, dbsp_merger* m, int64_t* fuel);
+int32_t dbsp_merger_done(dbsp_ctx* ctx, dbsp_merger* m, dbsp_batch** out);
+int32_t dbsp_merger_free(dbsp_merger* m);
+/* BatchReader::truncate_keys_below (trace/mod.rs:227-233;
+ * column_layer/mod.rs:316-319): zero-copy suffix view, key = n_key_lanes u64. */
+int32_t dbsp_batch_truncate_keys_below(dbsp_ctx* ctx, const dbsp_batch* b,
+                                       const uint64_t* key, dbsp_batch** out);
 /* neg (column_layer/mod.rs:452-480). */
 int32_t dbsp_batch_neg(dbsp_ctx* ctx, const dbsp_batch* a, dbsp_batch** out);
 /* Same rows, different key/value split: `index()` (operator/index.rs:128-157)
@@ -229,6 +253,16 @@ int32_t dbsp_spine_consolidate(dbsp_ctx* ctx, dbsp_spine* s, dbsp_batch** out);
 /* truncate_keys_below (spine_fueled.rs:223-233); `key` = n_key_lanes u64. */
 int32_t dbsp_spine_truncate_keys_below(dbsp_ctx* ctx, dbsp_spine* s,
                                        const uint64_t* key);
+/* Trace::truncate_values_below (trace/mod.rs:150-169; spine_fueled.rs:644-656):
+ * the bound only grows and is applied by later merges and by consolidate;
+ * values below it are undefined until then (as in the reference). */
+int32_t dbsp_spine_truncate_values_below(dbsp_ctx* ctx, dbsp_spine* s,
+                                         const uint64_t* val);
+/* Trace::exert (trace/mod.rs:104-113; spine_fueled.rs:627-634).  This spine
+ * merges eagerly on insert, so no merge is ever in progress; effort buys extra
+ * compaction instead: the two newest batches are merged while their combined
+ * length fits *effort (decremented by the rows merged). */
+int32_t dbsp_spine_exert(dbsp_ctx* ctx, dbsp_spine* s, int64_t* effort);
 int32_t dbsp_spine_len(const dbsp_spine* s, uint64_t* n_tuples,
                        uint32_t* n_batches);
 int32_t dbsp_spine_free(dbsp_spine* s);

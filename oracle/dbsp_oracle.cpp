@@ -236,50 +236,100 @@ void leaf_push_merge(Layer& outK, std::vector<i64>& outW, const Layer& A, const 
   if (lo2 < hi2) copy_range(B, wb, lo2, hi2);
 }
 
-// Batch::merge.  OrdZSet: one leaf push_merge (zset_batch.rs:307-318).
-// OrdIndexedZSet: OrderedBuilder::merge_step / push_merge / copy_range
-// (trace/layers/ordered/mod.rs:344-396, 787-834): on equal keys merge the two
-// value ranges and keep the key iff something survived; offsets rebased.
-BatchP merge(const Batch& a, const Batch& b) {
-  auto out = std::make_shared<Batch>(a.s);
-  Batch& O = *out;
-  if (!a.indexed()) {
-    leaf_push_merge(O.K, O.w, a.K, a.w, 0, a.K.n, b.K, b.w, 0, b.K.n);
-    return out;
+// Merger (trace/mod.rs:371-396).  OrdZSet: one leaf push_merge, not fuelled
+// (zset_batch.rs:307-318).  OrdIndexedZSet: OrderedBuilder::merge_step /
+// push_merge_fueled / copy_range (trace/layers/ordered/mod.rs:344-396,
+// 493-574, 787-834) and, with a lower value bound, the *_truncate_values_fueled
+// variants (:587-746): on equal keys merge the two value ranges (seeked to the
+// bound) and keep the key iff something survived; offsets rebased.  Fuel is
+// counted in values produced; a merge whose call returns with fuel > 0 is
+// complete (trace/mod.rs:378-395).
+struct Merger {
+  BatchP a, b, out;
+  size_t lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0;
+  Merger(BatchP a_, BatchP b_) : a(a_), b(b_), out(std::make_shared<Batch>(a_->s)) {
+    hi1 = a->K.n;
+    hi2 = b->K.n;
   }
-  auto copy_range = [&](const Batch& S, size_t lo, size_t hi) {
+  bool complete() const { return lo1 == hi1 && lo2 == hi2; }
+  // first value index of key k of S that is >= the bound (cursor.seek(val_bound))
+  static size_t vstart(const Batch& S, size_t k, const u64* vb) {
+    size_t vlo = S.offs[k], vhi = S.offs[k + 1];
+    if (!vb) return vlo;
+    return vlo + advance(vlo, vhi, [&](size_t i) { return cmp_row_tuple(S.V, i, vb) < 0; });
+  }
+  // copy_range[_truncate_values]_fueled (ordered/mod.rs:541-574, 711-746)
+  size_t copy_range(const Batch& S, size_t lo, size_t hi, const u64* vb, size_t fuel) {
+    Batch& O = *out;
+    size_t start = S.offs[lo];
     for (size_t k = lo; k < hi; k++) {
-      O.K.push_from(S.K, k);
-      size_t vlo = S.offs[k], vhi = S.offs[k + 1];
-      for (int l = 0; l < S.V.nl; l++) O.V.c[l].insert(O.V.c[l].end(), S.V.c[l].begin() + vlo, S.V.c[l].begin() + vhi);
-      O.V.n += vhi - vlo;
-      O.w.insert(O.w.end(), S.w.begin() + vlo, S.w.begin() + vhi);
-      O.offs.push_back(O.w.size());
+      size_t vlo = vstart(S, k, vb), vhi = S.offs[k + 1];
+      if (vhi > vlo) {
+        O.K.push_from(S.K, k);
+        for (int l = 0; l < S.V.nl; l++) O.V.c[l].insert(O.V.c[l].end(), S.V.c[l].begin() + vlo, S.V.c[l].begin() + vhi);
+        O.V.n += vhi - vlo;
+        O.w.insert(O.w.end(), S.w.begin() + vlo, S.w.begin() + vhi);
+        O.offs.push_back(O.w.size());
+      }
+      if (vhi - start >= fuel) return k + 1;
     }
-  };
-  size_t lo1 = 0, hi1 = a.K.n, lo2 = 0, hi2 = b.K.n;
-  while (lo1 < hi1 && lo2 < hi2) {
-    int c = cmp_rows(a.K, lo1, b.K, lo2);
+    return hi;
+  }
+  void merge_step(const u64* vb) {
+    const Batch &A = *a, &B = *b;
+    Batch& O = *out;
+    int c = cmp_rows(A.K, lo1, B.K, lo2);
     if (c < 0) {
-      size_t step = 1 + advance(lo1 + 1, hi1, [&](size_t i) { return cmp_rows(a.K, i, b.K, lo2) < 0; });
+      size_t step = 1 + advance(lo1 + 1, hi1, [&](size_t i) { return cmp_rows(A.K, i, B.K, lo2) < 0; });
       step = std::min<size_t>(step, 1000);
-      copy_range(a, lo1, lo1 + step);
-      lo1 += step;
+      lo1 = copy_range(A, lo1, lo1 + step, vb, SIZE_MAX);
     } else if (c == 0) {
       size_t before = O.w.size();
-      leaf_push_merge(O.V, O.w, a.V, a.w, a.offs[lo1], a.offs[lo1 + 1], b.V, b.w, b.offs[lo2], b.offs[lo2 + 1]);
-      if (O.w.size() > before) { O.K.push_from(a.K, lo1); O.offs.push_back(O.w.size()); }
+      leaf_push_merge(O.V, O.w, A.V, A.w, vstart(A, lo1, vb), A.offs[lo1 + 1], B.V, B.w, vstart(B, lo2, vb), B.offs[lo2 + 1]);
+      if (O.w.size() > before) { O.K.push_from(A.K, lo1); O.offs.push_back(O.w.size()); }
       lo1++; lo2++;
     } else {
-      size_t step = 1 + advance(lo2 + 1, hi2, [&](size_t i) { return cmp_rows(b.K, i, a.K, lo1) < 0; });
+      size_t step = 1 + advance(lo2 + 1, hi2, [&](size_t i) { return cmp_rows(B.K, i, A.K, lo1) < 0; });
       step = std::min<size_t>(step, 1000);
-      copy_range(b, lo2, lo2 + step);
-      lo2 += step;
+      lo2 = copy_range(B, lo2, lo2 + step, vb, SIZE_MAX);
     }
   }
-  if (lo1 < hi1) copy_range(a, lo1, hi1);
-  if (lo2 < hi2) copy_range(b, lo2, hi2);
-  return out;
+  void work(const u64* vb, i64* fuel) {
+    Batch& O = *out;
+    if (!a->indexed()) {   // zset_batch.rs:307-318: whole merge, fuel clamped to >= 1
+      size_t before = O.w.size();
+      leaf_push_merge(O.K, O.w, a->K, a->w, lo1, hi1, b->K, b->w, lo2, hi2);
+      lo1 = hi1; lo2 = hi2;
+      *fuel -= (i64)(O.w.size() - before);
+      *fuel = std::max<i64>(*fuel, 1);
+      return;
+    }
+    size_t starting = O.w.size();
+    i64 effort = 0;
+    while (lo1 < hi1 && lo2 < hi2 && effort < *fuel) {
+      merge_step(vb);
+      effort = (i64)(O.w.size() - starting);
+    }
+    if (lo1 == hi1 || lo2 == hi2) {
+      i64 remaining = *fuel - effort;
+      if (remaining > 0) {
+        if (lo1 < hi1) { if (remaining < 1000) remaining = 1000; lo1 = copy_range(*a, lo1, hi1, vb, (size_t)remaining); }
+        if (lo2 < hi2) { if (remaining < 1000) remaining = 1000; lo2 = copy_range(*b, lo2, hi2, vb, (size_t)remaining); }
+      }
+    }
+    effort = (i64)(O.w.size() - starting);
+    *fuel -= effort;
+  }
+};
+
+// Batch::merge = Merger run to completion (trace/mod.rs:280-291).
+BatchP merge(const BatchP& a, const BatchP& b, const u64* vb = nullptr) {
+  Merger m(a, b);
+  while (!m.complete()) {
+    i64 fuel = INT64_MAX;
+    m.work(vb, &fuel);
+  }
+  return m.out;
 }
 
 // Cursor::seek_key: first key index >= `key` (exponential search from `from`,
@@ -322,7 +372,10 @@ struct Spine {
   std::vector<BatchP> batches;   // oldest (largest) first
   bool has_bound = false;
   u64 bound[MAXL];
+  bool has_vbound = false;   // lower_val_bound (spine_fueled.rs:118, 644-656)
+  u64 vbound[MAXL];
   explicit Spine(const dbsp_schema& sc) : s(sc) {}
+  const u64* vb() const { return has_vbound ? vbound : nullptr; }
   void insert(BatchP b) {
     if (b->len() == 0) return;   // spine_fueled.rs:606-608
     if (has_bound) { BatchP t = truncate_keys_below(*b, bound); if (t) b = t; if (b->len() == 0) return; }
@@ -330,26 +383,49 @@ struct Spine {
     while (batches.size() >= 2) {
       size_t m = batches.size();
       if (batches[m - 2]->len() >= 2 * batches[m - 1]->len()) break;
-      BatchP merged = merge(*batches[m - 2], *batches[m - 1]);
+      BatchP merged = merge(batches[m - 2], batches[m - 1], vb());
       batches.pop_back(); batches.pop_back();
       if (merged->len()) batches.push_back(merged);
     }
   }
   BatchP consolidate() {   // spine_fueled.rs:583-600
     BatchP acc = std::make_shared<Batch>(s);
-    for (auto& b : batches) acc = merge(*acc, *b);
+    for (auto& b : batches) acc = merge(acc, b, vb());
     return acc;
   }
   void truncate(const u64* key) {   // spine_fueled.rs:223-233
+    if (has_bound && cmp_tuples(s.lane_types, s.n_key_lanes, key, bound) <= 0) return;   // bound = max(old, new)
     has_bound = true;
     for (int l = 0; l < s.n_key_lanes; l++) bound[l] = key[l];
     std::vector<BatchP> keep;
     for (auto& b : batches) {
-      BatchP t = truncate_keys_below(*b, key);
+      BatchP t = truncate_keys_below(*b, bound);
       if (!t) t = b;
       if (t->len()) keep.push_back(t);
     }
     batches.swap(keep);
+  }
+  // truncate_values_below (spine_fueled.rs:644-652): the bound only grows; it is
+  // applied by later merges (:866, :911, :981), contents below it are undefined.
+  void truncate_values(const u64* val) {
+    const uint8_t* ty = s.lane_types + s.n_key_lanes;
+    if (!has_vbound || cmp_tuples(ty, s.n_val_lanes, val, vbound) > 0)
+      for (int l = 0; l < s.n_val_lanes; l++) vbound[l] = val[l];
+    has_vbound = true;
+  }
+  // exert (spine_fueled.rs:627-634 -> apply_fuel): this spine merges eagerly, so
+  // there is never an in-progress merge; effort buys extra compaction instead —
+  // the two newest batches are merged while their size fits the effort.
+  void exert(i64* effort) {
+    while (batches.size() >= 2) {
+      size_t m = batches.size();
+      i64 cost = (i64)(batches[m - 2]->len() + batches[m - 1]->len());
+      if (cost > *effort) break;
+      BatchP merged = merge(batches[m - 2], batches[m - 1], vb());
+      batches.pop_back(); batches.pop_back();
+      if (merged->len()) batches.push_back(merged);
+      *effort -= cost;
+    }
   }
   size_t len() const { size_t n = 0; for (auto& b : batches) n += b->len(); return n; }
 };
@@ -522,7 +598,44 @@ int32_t orc_batch_empty(orc_ctx*, const dbsp_schema* s, orc_batch** out) {
 }
 
 int32_t orc_batch_merge(orc_ctx*, const orc_batch* a, const orc_batch* b, orc_batch** out) {
-  *out = wrap(merge(*a->p, *b->p));
+  *out = wrap(merge(a->p, b->p));
+  return DBSP_OK;
+}
+
+// Merger::work with a lower value bound run to completion
+// (indexed_zset_batch.rs:359-382; ordered/mod.rs:587-746).  OrdZSet ignores the
+// bound (zset_batch.rs:307-318).
+int32_t orc_batch_merge_bounded(orc_ctx*, const orc_batch* a, const orc_batch* b, const u64* vb, orc_batch** out) {
+  if (memcmp(&a->p->s, &b->p->s, sizeof(dbsp_schema))) { g_err = "merge: schema mismatch"; return DBSP_ERR_INVALID; }
+  *out = wrap(merge(a->p, b->p, a->p->indexed() ? vb : nullptr));
+  return DBSP_OK;
+}
+struct orc_merger { Merger m; bool has_vb; u64 vb[MAXL]; };
+int32_t orc_merger_new(orc_ctx*, const orc_batch* a, const orc_batch* b, const u64* vb, orc_merger** out) {
+  if (memcmp(&a->p->s, &b->p->s, sizeof(dbsp_schema))) { g_err = "merger: schema mismatch"; return DBSP_ERR_INVALID; }
+  orc_merger* m = new orc_merger{Merger(a->p, b->p), vb != nullptr && a->p->indexed(), {0}};
+  if (m->has_vb) for (int l = 0; l < a->p->s.n_val_lanes; l++) m->vb[l] = vb[l];
+  *out = m;
+  return DBSP_OK;
+}
+int32_t orc_merger_work(orc_ctx*, orc_merger* m, i64* fuel) {
+  if (m->m.complete()) { *fuel = std::max<i64>(*fuel, 1); return DBSP_OK; }
+  if (*fuel > 0) m->m.work(m->has_vb ? m->vb : nullptr, fuel);
+  if (m->m.complete()) *fuel = std::max<i64>(*fuel, 1);   // ABI: fuel > 0 after the call <=> merge complete
+  else *fuel = std::min<i64>(*fuel, 0);
+  return DBSP_OK;
+}
+int32_t orc_merger_done(orc_ctx*, orc_merger* m, orc_batch** out) {
+  if (!m->m.complete()) { g_err = "merger_done: merge not complete"; return DBSP_ERR_INVALID; }
+  *out = wrap(m->m.out);
+  delete m;
+  return DBSP_OK;
+}
+int32_t orc_merger_free(orc_merger* m) { delete m; return DBSP_OK; }
+// BatchReader::truncate_keys_below (trace/mod.rs:227-233).
+int32_t orc_batch_truncate_keys_below(orc_ctx*, const orc_batch* b, const u64* key, orc_batch** out) {
+  BatchP t = truncate_keys_below(*b->p, key);
+  *out = wrap(t ? t : b->p);
   return DBSP_OK;
 }
 
@@ -597,6 +710,8 @@ int32_t orc_spine_new(orc_ctx*, const dbsp_schema* s, orc_spine** out) { *out = 
 int32_t orc_spine_insert(orc_ctx*, orc_spine* s, const orc_batch* b) { s->s.insert(b->p); return DBSP_OK; }
 int32_t orc_spine_consolidate(orc_ctx*, orc_spine* s, orc_batch** out) { *out = wrap(s->s.consolidate()); return DBSP_OK; }
 int32_t orc_spine_truncate_keys_below(orc_ctx*, orc_spine* s, const u64* key) { s->s.truncate(key); return DBSP_OK; }
+int32_t orc_spine_truncate_values_below(orc_ctx*, orc_spine* s, const u64* val) { s->s.truncate_values(val); return DBSP_OK; }
+int32_t orc_spine_exert(orc_ctx*, orc_spine* s, i64* effort) { s->s.exert(effort); return DBSP_OK; }
 int32_t orc_spine_len(const orc_spine* s, u64* n, uint32_t* nb) {
   if (n) *n = s->s.len();
   if (nb) *nb = (uint32_t)s->s.batches.size();

@@ -93,6 +93,28 @@ def run_join_test(be):
     assert got["join"] == inc_outputs
 
 
+# ---- antijoin (dbsp/src/operator/join.rs:1335-1385) --------------------------
+def run_antijoin(be):
+    input1 = [[(1, 0, 1), (1, 1, 2), (2, 0, 1), (2, 1, 1)], [(3, 1, 1)], [], [(2, 2, 1), (4, 1, 1)]]
+    input2 = [[], [], [(1, 1, 3)], [(2, 5, 1)]]
+    outputs = [
+        [(1, 0, 1), (1, 1, 2), (2, 0, 1), (2, 1, 1)],
+        [(3, 1, 1)],
+        [(1, 0, -1), (1, 1, -2)],
+        [(2, 0, -1), (2, 1, -1), (4, 1, 1)],
+    ]
+    c = RootCircuit(be)
+    pair = Schema("uu")
+    it1, it2 = iter(input1), iter(input2)
+    in1 = c.add_source(lambda: zset(be, pair, next(it1)), pair).index(1)
+    in2 = c.add_source(lambda: zset(be, pair, next(it2)), pair).index(1)
+    got = []
+    in1.antijoin(in2).gather(0).inspect(lambda b: got.append(rows_of(b)))
+    for _ in range(4):
+        c.step()
+    assert got == outputs
+
+
 # ---- aggregate (dbsp/src/operator/aggregate/mod.rs:878-998) -----------------
 def run_count_test(be):
     c = RootCircuit(be)
@@ -392,6 +414,7 @@ ALL_CASES = {
     "distinct_indexed": run_distinct_indexed,
     "window_sliding": run_window_sliding,
     "window_tumbling": run_window_tumbling,
+    "antijoin": run_antijoin,
     "window_shrinking": run_window_shrinking,
     "watermark": run_watermark,
     "q3": run_q3,
