@@ -18,8 +18,8 @@
 // always (a, b) adjacent in merged order: the A row absorbs its partner's
 // weight, the B row is skipped — also across thread and tile boundaries (one
 // halo row on each side).  The tile's global output offset comes from a
-// decoupled look-back over per-tile status words (tiles take their index from
-// an atomic ticket, so predecessors are always resident or done).
+// decoupled look-back over per-tile status words (tile index = block index:
+// CTAs are dispatched in order, so predecessors are always resident or done).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -32,6 +32,9 @@ namespace {
 #define MERGE_THREADS_CFG 256
 #endif
 constexpr int MERGE_THREADS = MERGE_THREADS_CFG;
+#ifndef MERGE_LB_THREADS
+#define MERGE_LB_THREADS 32   // look-back window: predecessor tiles inspected per round trip (measured: 32 > 64 > 128 > 256)
+#endif
 constexpr u64 ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62, ST_MASK = (1ull << 62) - 1;
 
 // status words carry flag and value in one 64-bit word: relaxed device-scope
@@ -85,12 +88,16 @@ __device__ __forceinline__ void mbar_wait(u64* mbar, unsigned parity) {
 
 template <int L>
 struct MergeCfg {
+  // rows of one or two lanes (OrdZSet<u64>, OrdIndexedZSet<u64,u64>): the
+  // configuration swept on the B200 (profiles/README.md) — 256 threads x 9 rows,
+  // 5 CTAs/SM, selects instead of branches in search and serial merge
+  static constexpr bool NARROW = L <= 2;
   // odd rows/thread: the per-thread serial merge walks shared memory with a
   // stride of IPT 64-bit words between lanes of a warp -> bank-conflict free
 #ifdef MERGE_IPT_CFG
-  static constexpr int IPT = (L <= 2) ? MERGE_IPT_CFG : (L <= 4 ? 5 : 3);
+  static constexpr int IPT = NARROW ? MERGE_IPT_CFG : (L <= 4 ? 5 : 3);
 #else
-  static constexpr int IPT = (L <= 2) ? 7 : (L <= 4 ? 5 : 3);
+  static constexpr int IPT = NARROW ? 9 : (L <= 4 ? 5 : 3);
 #endif
   static constexpr int TILE = MERGE_THREADS * IPT;
   static constexpr int S = TILE + 8;   // staged slots per array (even; room for alignment slack + halos)
@@ -176,12 +183,25 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, const i64* __restric
   u64* s_lb_all = sc.s_lb_all;
   u64* s_lb_upto = sc.s_lb_upto;
   auto le = [&](int ia, int ib) {   // staged row ia <= staged row ib
+    if constexpr (MergeCfg<L>::NARROW) {   // all lanes loaded at once, no branches
+      u64 a[L], b[L];
 #pragma unroll
-    for (int l = 0; l < L; l++) {
-      u64 a = sl[l * S + ia], b = sl[l * S + ib];
-      if (a != b) return a < b;
+      for (int l = 0; l < L; l++) { a[l] = sl[l * S + ia]; b[l] = sl[l * S + ib]; }
+      bool r = true;
+#pragma unroll
+      for (int l = L - 1; l >= 0; l--) r = (a[l] < b[l]) | ((a[l] == b[l]) & r);
+      return r;
+    } else {
+      bool r = true, open = true;   // first differing lane decides
+#pragma unroll
+      for (int l = 0; l < L; l++) {
+        if (open) {
+          u64 a = sl[l * S + ia], b = sl[l * S + ib];
+          if (a != b) { r = a < b; open = false; }
+        }
+      }
+      return r;
     }
-    return true;
   };
 
   // ---- per-thread merge path ------------------------------------------------
@@ -198,17 +218,16 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, const i64* __restric
   // Serial merge with both run heads held in registers: one 3-way compare per
   // row, only the advanced side is re-read from shared memory.  `prev_eq`
   // says the previous merged row was an A row equal to the current B head.
+  // The loop touches shared memory only; weights are fetched afterwards in one
+  // batch of independent loads.
   u64 ka[L], kb[L];
-  i64 wa = 0, wb = 0;
   auto load_a = [&](int i) {
 #pragma unroll
     for (int l = 0; l < L; l++) ka[l] = sl[l * S + oa + i];
-    wa = wAg[i];
   };
   auto load_b = [&](int j) {
 #pragma unroll
     for (int l = 0; l < L; l++) kb[l] = sl[l * S + ob + j];
-    wb = wBg[j];
   };
   bool b_readable = (bi < nb) || (bi == nb && has_next);
   if (ai < na) load_a(ai);
@@ -221,12 +240,47 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, const i64* __restric
   }
 
   u32 src[IPT];
-  i64 wv[IPT];
-  u32 keep = 0;
+  u32 keep = 0, pmask = 0;   // pmask bit k: row k is an A row whose equal B partner follows it
+  if constexpr (MergeCfg<L>::NARROW) {
+    // Narrow rows: branch-free formulation — every lane of the warp executes the
+    // same instruction stream whichever side it consumes (selects instead of
+    // divergent take-A / take-B paths).
 #pragma unroll
-  for (int k = 0; k < IPT; k++) {
+    for (int k = 0; k < IPT; k++) {
+    const bool valid = ai + bi < n;
+    const bool a_ok = ai < na, b_in = bi < nb;
+    bool lt = false, eq = true;   // A head < / == B head (meaningful when both are readable)
+#pragma unroll
+    for (int l = L - 1; l >= 0; l--) {
+      lt = (ka[l] < kb[l]) | ((ka[l] == kb[l]) & lt);
+      eq = eq & (ka[l] == kb[l]);
+    }
+    const bool both = a_ok & b_readable;
+    const bool take_a = !b_in | (a_ok & (!both | lt | eq));
+    const bool partner = take_a & b_readable & eq;
+    src[k] = take_a ? (u32)(oa + ai) : (u32)(ob + bi);
+    keep |= (u32)(valid & (take_a | !prev_eq)) << k;
+    pmask |= (u32)(valid & partner) << k;
+    prev_eq = valid ? partner : prev_eq;
+    ai += (valid & take_a) ? 1 : 0;
+    bi += (valid & !take_a) ? 1 : 0;
+    b_readable = (bi < nb) | ((bi == nb) & has_next);
+    const bool ld_ok = valid & (take_a ? (ai < na) : b_readable);
+    const int slot = take_a ? (oa + ai) : (ob + bi);
+    if (ld_ok) {
+#pragma unroll
+      for (int l = 0; l < L; l++) {
+        const u64 nv = sl[l * S + slot];
+        ka[l] = take_a ? nv : ka[l];
+        kb[l] = take_a ? kb[l] : nv;
+      }
+    }
+    }
+  } else {
+    // Wide rows: the selects would cost 2 * L moves per row; branch instead.
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
     src[k] = 0;
-    wv[k] = 0;
     if (ai + bi < n) {
       const bool a_ok = ai < na, b_in = bi < nb;
       int c = 0;   // cmp3(A head, B head) when both are readable
@@ -240,25 +294,46 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, const i64* __restric
       if (take_a) {
         const bool partner = b_readable && c == 0;
         src[k] = oa + ai;
-        if (partner) {   // rare: the only place a weight value steers control flow
-          const i64 w = (i64)((u64)wa + (u64)wb);
-          wv[k] = w;
-          if (w != 0) keep |= 1u << k;
-        } else {
-          wv[k] = wa;
-          keep |= 1u << k;
-        }
+        keep |= 1u << k;
+        if (partner) pmask |= 1u << k;
         prev_eq = partner;
         ai++;
         if (ai < na) load_a(ai);
       } else {
         src[k] = ob + bi;
-        wv[k] = wb;
         if (!prev_eq) keep |= 1u << k;
         prev_eq = false;
         bi++;
         b_readable = (bi < nb) || (bi == nb && has_next);
         if (b_readable) load_b(bi);
+      }
+    }
+    }
+  }
+
+  // ---- weights: one batch of independent global loads --------------------------
+  // Row k's weight sits at wA[a0 + slot - oa] or wB[b0 + slot - ob].  The partner
+  // of an A row is the next merged row: row k+1 of this thread, or — for the
+  // thread's last row — the B head left over after the loop (possibly the first
+  // row of the next thread / tile).  Input weights are never zero (batch
+  // invariant), so only a partner sum can cancel.
+  i64 wv[IPT];
+#pragma unroll
+  for (int k = 0; k < IPT; k++) {
+    wv[k] = 0;
+    if (dt + k < n) {
+      const int s = (int)src[k];
+      wv[k] = (s >= ob) ? wBg[s - ob] : wAg[s - oa];
+    }
+  }
+  if (pmask) {   // rare
+    const i64 wlast = prev_eq ? wBg[bi] : 0;
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+      if (pmask & (1u << k)) {
+        const i64 pw = (k + 1 < IPT && dt + k + 1 < n) ? wv[k + 1 < IPT ? k + 1 : k] : wlast;
+        wv[k] = (i64)((u64)wv[k] + (u64)pw);
+        if (wv[k] == 0) keep &= ~(1u << k);
       }
     }
   }
@@ -292,39 +367,43 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, const i64* __restric
   }
 
   // ---- decoupled look-back for the tile's global output offset -------------------
-  // The whole CTA inspects MERGE_THREADS predecessor status words per round trip
-  // (tile t-1-tid per thread); aggregates of tiles that have not resolved their
-  // own prefix yet are summed on the way.
+  // The first LBT threads of the CTA inspect LBT predecessor status words per
+  // round trip (tile p - tid per thread); aggregates of tiles that have not
+  // resolved their own prefix yet are summed on the way.
   if (t == 0) {
     if (tid == 0) { st_relaxed(&status[0], ST_PREFIX | (u64)tile_total); s_base = 0; }
   } else {
     if (tid == 0) st_relaxed(&status[t], ST_AGG | (u64)tile_total);
+    constexpr int LBT = MERGE_LB_THREADS < MERGE_THREADS ? MERGE_LB_THREADS : MERGE_THREADS;
+    constexpr int NW = LBT / 32;
     u64 base_acc = 0;
-    long long p = (long long)t - 1;   // window = tiles p, p-1, ..., p-(MERGE_THREADS-1)
+    long long p = (long long)t - 1;   // window = tiles p, p-1, ..., p-(LBT-1)
     while (true) {
-      const long long q = p - tid;
-      u64 v = ST_PREFIX;               // tiles before 0 contribute an empty prefix
-      if (q >= 0) {
-        do { v = ld_relaxed(&status[q]); } while ((v >> 62) == 0);
-      }
-      const unsigned is_prefix = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-      const int wfirst = is_prefix ? (__ffs(is_prefix) - 1) : 32;
-      u64 all = v & ST_MASK, upto = ((tid & 31) <= wfirst) ? (v & ST_MASK) : 0;
+      if (tid < LBT) {
+        const long long q = p - tid;
+        u64 v = ST_PREFIX;               // tiles before 0 contribute an empty prefix
+        if (q >= 0) {
+          do { v = ld_relaxed(&status[q]); } while ((v >> 62) == 0);
+        }
+        const unsigned is_prefix = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+        const int wfirst = is_prefix ? (__ffs(is_prefix) - 1) : 32;
+        u64 all = v & ST_MASK, upto = ((tid & 31) <= wfirst) ? (v & ST_MASK) : 0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        all += __shfl_xor_sync(0xffffffffu, all, o);
-        upto += __shfl_xor_sync(0xffffffffu, upto, o);
-      }
-      if ((tid & 31) == 0) {
-        s_lb_first[tid >> 5] = wfirst;
-        s_lb_all[tid >> 5] = all;
-        s_lb_upto[tid >> 5] = upto;
+        for (int o = 16; o > 0; o >>= 1) {
+          all += __shfl_xor_sync(0xffffffffu, all, o);
+          upto += __shfl_xor_sync(0xffffffffu, upto, o);
+        }
+        if ((tid & 31) == 0) {
+          s_lb_first[tid >> 5] = wfirst;
+          s_lb_all[tid >> 5] = all;
+          s_lb_upto[tid >> 5] = upto;
+        }
       }
       __syncthreads();
       bool found = false;
       u64 add = 0;
 #pragma unroll
-      for (int wi = 0; wi < MERGE_THREADS / 32; wi++) {
+      for (int wi = 0; wi < NW; wi++) {
         if (!found) {
           if (s_lb_first[wi] < 32) { add += s_lb_upto[wi]; found = true; }
           else add += s_lb_all[wi];
@@ -333,7 +412,7 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, const i64* __restric
       base_acc += add;
       __syncthreads();   // s_lb_* are rewritten by the next window
       if (found) break;
-      p -= MERGE_THREADS;
+      p -= LBT;
     }
     if (tid == 0) {
       st_relaxed(&status[t], ST_PREFIX | (base_acc + tile_total));
@@ -357,17 +436,17 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, const i64* __restric
   }
 }
 
-// min CTAs/SM: caps registers at 42 for the narrow rows (6 CTAs fit their 32 KB tiles);
-// measured: without the cap ptxas' 48-register schedule runs 2.5x slower
+// min CTAs/SM: narrow rows stage 41 KB per CTA -> 5 CTAs/SM, which caps the
+// kernel at 48 registers (an uncapped schedule measured 2.5x slower)
 #ifdef MERGE_MIN_CTAS
 #define MERGE_MIN_CTAS_FOR(L) MERGE_MIN_CTAS
 #else
-#define MERGE_MIN_CTAS_FOR(L) ((L) <= 2 ? 6 : 3)
+#define MERGE_MIN_CTAS_FOR(L) ((L) <= 2 ? 5 : 3)
 #endif
 template <int L>
 __global__ void __launch_bounds__(MERGE_THREADS, MERGE_MIN_CTAS_FOR(L))
 k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __restrict__ wB, u64 nB, Flips f,
-              const u64* __restrict__ part, u32 ntiles, u32* ticket, u64* status, MCols O, i64* wO, u64* n_out,
+              const u64* __restrict__ part, u32 ntiles, u64* status, MCols O, i64* wO, u64* n_out,
               int use_tma) {
   constexpr int IPT = MergeCfg<L>::IPT;
   constexpr int TILE = MergeCfg<L>::TILE;
@@ -376,19 +455,16 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
   u64* sl = (u64*)smem_raw;                                   // L lanes of S staged slots
   unsigned short* perm = (unsigned short*)(sl + (size_t)L * S);   // TILE staged-slot ids of kept rows
   __shared__ __align__(8) u64 s_mbar;
-  __shared__ u32 s_tile;
   __shared__ u64 s_base;
   __shared__ u32 s_warp[MERGE_THREADS / 32];
   __shared__ int s_lb_first[MERGE_THREADS / 32];
   __shared__ u64 s_lb_all[MERGE_THREADS / 32], s_lb_upto[MERGE_THREADS / 32];
 
   const int tid = threadIdx.x;
-  if (tid == 0) {
-    s_tile = atomicAdd(ticket, 1u);
-    mbar_init(&s_mbar, 1);
-  }
-  __syncthreads();
-  const u32 t = s_tile;
+  // Tile index = block index: CTAs are dispatched in increasing blockIdx order,
+  // so every predecessor a look-back waits on is resident or finished.
+  const u32 t = blockIdx.x;
+  if (tid == 0) mbar_init(&s_mbar, 1);
   const u64 total = nA + nB;
   const u64 d0 = (u64)t * TILE;
   const u64 d1 = (d0 + TILE < total) ? d0 + TILE : total;
@@ -396,6 +472,7 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
   const u64 b0 = d0 - a0, b1 = d1 - a1;
   const int na = (int)(a1 - a0), nb = (int)(b1 - b0);
   const bool has_prev = a0 > 0, has_next = b1 < nB;
+  __syncthreads();   // s_mbar initialised
   bool any_flip = false;
 #pragma unroll
   for (int l = 0; l < L; l++) any_flip = any_flip || (f.f[l] != 0);
@@ -482,14 +559,13 @@ int32_t merge_launch(Ctx* ctx, const Batch* a, const Batch* b, Batch** out) {
   u64 total = a->n + b->n;
   u32 ntiles = (u32)((total + Cfg::TILE - 1) / Cfg::TILE);
   BufP aux;
-  // part[ntiles+1] u64 | status[ntiles] u64 | n_out u64 | ticket u32
-  size_t aux_u64 = (size_t)(ntiles + 1) + ntiles + 2;
+  // part[ntiles+1] u64 | status[ntiles] u64 | n_out u64
+  size_t aux_u64 = (size_t)(ntiles + 1) + ntiles + 1;
   TRY(dev_alloc(ctx, aux_u64 * 8, &aux));
   u64* part = (u64*)aux->p;
   u64* status = part + (ntiles + 1);
   u64* n_out = status + ntiles;
-  u32* ticket = (u32*)(n_out + 1);
-  CUDA_TRY(cudaMemsetAsync(status, 0, (size_t)(ntiles + 2) * 8, st));
+  CUDA_TRY(cudaMemsetAsync(status, 0, (size_t)(ntiles + 1) * 8, st));
   Batch* o;
   MCols oc;
   i64* ow;
@@ -508,7 +584,7 @@ int32_t merge_launch(Ctx* ctx, const Batch* a, const Batch* b, Batch** out) {
   }
   ProfScope* ps = new ProfScope(ctx, KID_MERGE, 0);
   k_merge_tiles<L><<<ntiles, MERGE_THREADS, Cfg::SMEM, st>>>(a->cols(), a->w, a->n, b->cols(), b->w, b->n, f, part, ntiles,
-                                                           ticket, status, oc, ow, n_out, use_tma);
+                                                           status, oc, ow, n_out, use_tma);
   long ps_idx = ps->idx;
   delete ps;   // records the end event
   ctx->kernel_launches += 2;
