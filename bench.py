@@ -336,8 +336,10 @@ def merge_sweep(device_index, rows=50_000_000):
     traffic = None
     try:   # dram__bytes_read+write of one launch from the committed ncu --set full capture (2 x 20 M rows), scaled by rows
         prof_j = json.load(open(os.path.join(ROOT, "profiles", "r1_merge_tiles_ncu_full.json")))
-        mb = float(prof_j["dram__bytes_read.sum"].split()[0]) + float(prof_j["dram__bytes_write.sum"].split()[0])
-        traffic = mb * 1e6 * (len(a) + len(b)) / 40_000_000
+        def nbytes(x):   # "960.49 Mbyte" -> bytes
+            v, u = x.split()[:2]
+            return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+        traffic = (nbytes(prof_j["dram__bytes_read.sum"]) + nbytes(prof_j["dram__bytes_write.sum"])) * (len(a) + len(b)) / 40_000_000
     except Exception:
         pass
     return {"workload": f"merge 2 x OrdIndexedZSet<u64,u64,i64>, {len(a)}+{len(b)} rows -> {len(m)}", "rows_per_s": (len(a) + len(b)) / (p["ms"] / 5 / 1e3),
