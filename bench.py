@@ -296,7 +296,7 @@ def roofline_from_profile(prof, query=None):
             "peak_source": how, **({"note": ROOFLINE_NOTES[query]} if query in ROOFLINE_NOTES else {})}
 
 
-def merge_sweep(device_index, rows=50_000_000):
+def merge_sweep(device_index, rows=50_000_000, n_val_lanes=1):
     """BASELINE.json configs[4]: merge of two consolidated OrdIndexedZSet<u64,u64,i64>
     batches (Zipf-ish keys), algorithmic GB/s of the merge kernel vs the HBM peak."""
     import torch
@@ -308,18 +308,18 @@ def merge_sweep(device_index, rows=50_000_000):
     dev = torch.device("cuda", device_index)
     g = torch.Generator(device=dev)
     g.manual_seed(0x7FC359184519C0AA & 0x7FFFFFFF)
-    s = Schema("u", "u")
+    s = Schema("u", "u" * n_val_lanes)
     batches = []
     for _ in range(2):
         # Zipf(s=1) keys over a domain of rows/4: inverse-CDF of a log-uniform draw
         u = torch.rand(rows, generator=g, device=dev, dtype=torch.float64)
         dom = rows // 4
         keys = torch.exp(u * np.log(dom)).to(torch.int64).clamp_(1, dom)
-        vals = torch.randint(0, 1 << 40, (rows,), generator=g, device=dev, dtype=torch.int64)
+        vals = [torch.randint(0, 1 << 40, (rows,), generator=g, device=dev, dtype=torch.int64) for _ in range(n_val_lanes)]
         w = torch.randint(0, 4, (rows,), generator=g, device=dev, dtype=torch.int64)
         w = torch.where(w >= 2, w - 1, w - 2)   # {-2,-1,1,2}
         torch.cuda.synchronize(dev)
-        batches.append(be.batch_from_columns(s, [int(keys.data_ptr()), int(vals.data_ptr())], int(w.data_ptr()), n=rows, on_device=True))
+        batches.append(be.batch_from_columns(s, [int(keys.data_ptr())] + [int(v.data_ptr()) for v in vals], int(w.data_ptr()), n=rows, on_device=True))
         be.sync()
         del u, keys, vals, w
     a, b = batches
@@ -335,6 +335,8 @@ def merge_sweep(device_index, rows=50_000_000):
     ach = p["alg_bytes"] / (p["ms"] / 1e3) / 1e9
     traffic = None
     try:   # dram__bytes_read+write of one launch from the committed ncu --set full capture (2 x 20 M rows), scaled by rows
+        if n_val_lanes != 1:
+            raise KeyError("capture is for 2-lane rows")
         prof_j = json.load(open(os.path.join(ROOT, "profiles", "r1_merge_tiles_ncu_full.json")))
         def nbytes(x):   # "960.49 Mbyte" -> bytes
             v, u = x.split()[:2]
@@ -342,7 +344,7 @@ def merge_sweep(device_index, rows=50_000_000):
         traffic = (nbytes(prof_j["dram__bytes_read.sum"]) + nbytes(prof_j["dram__bytes_write.sum"])) * (len(a) + len(b)) / 40_000_000
     except Exception:
         pass
-    return {"workload": f"merge 2 x OrdIndexedZSet<u64,u64,i64>, {len(a)}+{len(b)} rows -> {len(m)}", "rows_per_s": (len(a) + len(b)) / (p["ms"] / 5 / 1e3),
+    return {"workload": f"merge 2 x OrdIndexedZSet<u64,{'(' + ','.join(['u64'] * n_val_lanes) + ')' if n_val_lanes > 1 else 'u64'},i64>, {len(a)}+{len(b)} rows -> {len(m)}", "rows_per_s": (len(a) + len(b)) / (p["ms"] / 5 / 1e3),
             "roofline": {"bound": "hbm", "kernel": "merge_tiles", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic, "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum, profiles/r1_merge_tiles_ncu_full.json (2x20M-row launch) scaled by rows",
                          "alg_bytes_per_launch": p["alg_bytes"] / p["launches"], "avg_launch_us": 1e3 * p["ms"] / p["launches"], "peak_source": how},

@@ -32,6 +32,21 @@ namespace {
 #define MERGE_THREADS_CFG 256
 #endif
 constexpr int MERGE_THREADS = MERGE_THREADS_CFG;
+#ifndef MERGE_NARROW_MAX
+#define MERGE_NARROW_MAX 2   // rows up to this many lanes use the branch-free (select) search and serial merge
+#endif
+#ifndef MERGE_IPT_CFG
+#define MERGE_IPT_CFG 9      // rows per thread, 1-2 lanes
+#endif
+#ifndef MERGE_IPT_MID
+#define MERGE_IPT_MID 5      // rows per thread, 3-6 lanes
+#endif
+#ifndef MERGE_IPT_WIDE
+#define MERGE_IPT_WIDE 3     // rows per thread, 7-8 lanes
+#endif
+#ifndef MERGE_L2_PREFETCH
+#define MERGE_L2_PREFETCH 148   // tiles ahead whose inputs are prefetched into L2 (0 = off; swept: 148 > 444 > 740 > off)
+#endif
 #ifndef MERGE_LB_THREADS
 #define MERGE_LB_THREADS 32   // look-back window: predecessor tiles inspected per round trip (measured: 32 > 64 > 128 > 256)
 #endif
@@ -62,6 +77,12 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
                "l"(gsrc), "r"(bytes), "r"(m)
                : "memory");
 }
+// L2 prefetch of the 16-byte granules inside [p, p + bytes) (never past either end)
+__device__ __forceinline__ void l2_prefetch(const void* p, u64 bytes) {
+  const u64 a = ((u64)(size_t)p + 15ull) & ~15ull;
+  const u64 e = ((u64)(size_t)p + bytes) & ~15ull;
+  if (e > a) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((unsigned)(e - a)) : "memory");
+}
 __device__ __forceinline__ void mbar_init(u64* mbar, unsigned count) {
   unsigned m = (unsigned)__cvta_generic_to_shared(mbar);
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(m), "r"(count) : "memory");
@@ -91,14 +112,10 @@ struct MergeCfg {
   // rows of one or two lanes (OrdZSet<u64>, OrdIndexedZSet<u64,u64>): the
   // configuration swept on the B200 (profiles/README.md) — 256 threads x 9 rows,
   // 5 CTAs/SM, selects instead of branches in search and serial merge
-  static constexpr bool NARROW = L <= 2;
+  static constexpr bool NARROW = L <= MERGE_NARROW_MAX;
   // odd rows/thread: the per-thread serial merge walks shared memory with a
   // stride of IPT 64-bit words between lanes of a warp -> bank-conflict free
-#ifdef MERGE_IPT_CFG
-  static constexpr int IPT = NARROW ? MERGE_IPT_CFG : (L <= 4 ? 5 : 3);
-#else
-  static constexpr int IPT = NARROW ? 9 : (L <= 4 ? 5 : 3);
-#endif
+  static constexpr int IPT = (L <= 2) ? MERGE_IPT_CFG : (L <= 6 ? MERGE_IPT_MID : MERGE_IPT_WIDE);
   static constexpr int TILE = MERGE_THREADS * IPT;
   static constexpr int S = TILE + 8;   // staged slots per array (even; room for alignment slack + halos)
   // shared memory holds the staged lanes and 16-bit slot ids only; the weights
@@ -438,11 +455,16 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, const i64* __restric
 
 // min CTAs/SM: narrow rows stage 41 KB per CTA -> 5 CTAs/SM, which caps the
 // kernel at 48 registers (an uncapped schedule measured 2.5x slower)
-#ifdef MERGE_MIN_CTAS
-#define MERGE_MIN_CTAS_FOR(L) MERGE_MIN_CTAS
-#else
-#define MERGE_MIN_CTAS_FOR(L) ((L) <= 2 ? 5 : 3)
+#ifndef MERGE_MIN_CTAS
+#define MERGE_MIN_CTAS 5
 #endif
+#ifndef MERGE_CTAS_MID
+#define MERGE_CTAS_MID 6   // 3-4 lanes, swept: 3 -> 41 %, 6 -> 60 % of the HBM peak on 3-lane rows (register cap 40)
+#endif
+#ifndef MERGE_CTAS_WIDE
+#define MERGE_CTAS_WIDE 4   // 5-8 lanes (5 lanes x 5 rows: 46 -> 61 %; 8 lanes x 3 rows: 57 %)
+#endif
+#define MERGE_MIN_CTAS_FOR(L) ((L) <= 2 ? MERGE_MIN_CTAS : ((L) <= 4 ? MERGE_CTAS_MID : MERGE_CTAS_WIDE))
 template <int L>
 __global__ void __launch_bounds__(MERGE_THREADS, MERGE_MIN_CTAS_FOR(L))
 k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __restrict__ wB, u64 nB, Flips f,
@@ -472,6 +494,23 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
   const u64 b0 = d0 - a0, b1 = d1 - a1;
   const int na = (int)(a1 - a0), nb = (int)(b1 - b0);
   const bool has_prev = a0 > 0, has_next = b1 < nB;
+#if MERGE_L2_PREFETCH
+  // Pull the inputs of the tile that will follow in this CTA slot (about one CTA
+  // lifetime from now) into L2, so that its TMA staging does not wait on HBM.
+  if (tid == 32 && t + MERGE_L2_PREFETCH < ntiles) {
+    const u64 pa0 = part[t + MERGE_L2_PREFETCH], pa1 = part[t + MERGE_L2_PREFETCH + 1];
+    const u64 pd0 = (u64)(t + MERGE_L2_PREFETCH) * TILE;
+    const u64 pd1 = (pd0 + TILE < total) ? pd0 + TILE : total;
+    const u64 pb0 = pd0 - pa0, pb1 = pd1 - pa1;
+#pragma unroll
+    for (int l = 0; l < L; l++) {
+      l2_prefetch(A.c[l] + pa0, (pa1 - pa0) * 8);
+      l2_prefetch(B.c[l] + pb0, (pb1 - pb0) * 8);
+    }
+    l2_prefetch(wA + pa0, (pa1 - pa0) * 8);
+    l2_prefetch(wB + pb0, (pb1 - pb0) * 8);
+  }
+#endif
   __syncthreads();   // s_mbar initialised
   bool any_flip = false;
 #pragma unroll

@@ -11,4 +11,5 @@ import bench  # noqa: E402
 
 if __name__ == "__main__":
     rows = int(sys.argv[1]) if len(sys.argv) > 1 else 20_000_000
-    print(bench.merge_sweep(0, rows=rows))
+    n_val_lanes = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    print(bench.merge_sweep(0, rows=rows, n_val_lanes=n_val_lanes))
