@@ -6,9 +6,9 @@ include/dbsp_b200.h (CUDA library `libdbsp_b200.so`, sm_100a).  Importable as
 """
 from . import _capi as capi
 from .circuit import FoldCount, FoldSum, Max, Min, RootCircuit, Stream
-from .zset import Backend, Batch, Proj, Schema, Spine, col, const, key, lval, rval, val
+from .zset import Backend, Batch, Batcher, Merger, Proj, Schema, Spine, col, const, key, lval, rval, val
 
 __all__ = [
     "capi", "RootCircuit", "Stream", "Max", "Min", "FoldCount", "FoldSum", "Backend", "Batch", "Proj",
-    "Schema", "Spine", "key", "lval", "rval", "val", "col", "const",
+    "Schema", "Spine", "Batcher", "Merger", "key", "lval", "rval", "val", "col", "const",
 ]

@@ -75,6 +75,12 @@ _SIGS = {
     "upload_free": [_P],
     "batch_empty": [_P, C.POINTER(CSchema), _PP],
     "batch_merge": [_P, _P, _P, _PP],
+    "batcher_new": [_P, C.POINTER(CSchema), _PP],
+    "batcher_push": [_P, _P, _PP, _P, C.c_uint64, C.c_int32],
+    "batcher_push_consolidated": [_P, _P, _PP, _P, C.c_uint64, C.c_int32],
+    "batcher_tuples": [_P, _U64P],
+    "batcher_seal": [_P, _P, _PP],
+    "batcher_free": [_P],
     "batch_merge_bounded": [_P, _P, _P, _U64P, _PP],
     "merger_new": [_P, _P, _P, _U64P, _PP],
     "merger_work": [_P, _P, _I64P],

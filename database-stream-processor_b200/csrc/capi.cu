@@ -14,6 +14,7 @@ struct dbsp_batch : Batch {};
 struct dbsp_spine : Spine {};
 struct Merger;
 struct dbsp_merger;
+struct dbsp_batcher;
 
 static inline Batch* B(const dbsp_batch* b) { return (Batch*)b; }
 static inline dbsp_batch* H(Batch* b) { return (dbsp_batch*)b; }
@@ -344,6 +345,86 @@ int32_t dbsp_batch_from_sorted(dbsp_ctx* ctx, const dbsp_schema* s, const uint64
   CUDA_TRY(cudaMemcpyAsync(ow, w, n * 8, kind, ctx->stream));
   if (!on_device) { ctx->h2d_bytes += n * 8 * (L + 1); CUDA_TRY(cudaStreamSynchronize(ctx->stream)); }
   *out = H(b);
+  return DBSP_OK;
+}
+
+// MergeBatcher (trace/ord/merge_batcher/mod.rs:155-260): queue of consolidated
+// batches, newest last; the two newest are merged while the newer holds at least
+// half the rows of the older (the reference compares chunk counts of 8 KiB
+// buffers — the same geometric rule; the schedule is not observable in seal()).
+struct Batcher {
+  dbsp_schema s;
+  std::vector<Batch*> queue;
+};
+static int32_t batcher_enqueue(Ctx* ctx, Batcher* q, Batch* b) {
+  if (b->n == 0) { batch_unref(b); return DBSP_OK; }
+  q->queue.push_back(b);
+  while (q->queue.size() > 1 && q->queue[q->queue.size() - 1]->n >= q->queue[q->queue.size() - 2]->n / 2) {
+    Batch* y = q->queue.back(); q->queue.pop_back();
+    Batch* x = q->queue.back(); q->queue.pop_back();
+    Batch* m = nullptr;
+    int32_t rc = merge_batches(ctx, x, y, &m);
+    batch_unref(x);
+    batch_unref(y);
+    if (rc) return rc;
+    if (m->n) q->queue.push_back(m); else batch_unref(m);
+  }
+  return DBSP_OK;
+}
+int32_t dbsp_batcher_new(dbsp_ctx*, const dbsp_schema* s, dbsp_batcher** out) {
+  int L = s->n_key_lanes + s->n_val_lanes;
+  CHECK_ARG(L >= 1 && L <= MAXL, "schema must have 1..8 lanes");
+  Batcher* q = new Batcher();
+  q->s = *s;
+  *out = (dbsp_batcher*)q;
+  return DBSP_OK;
+}
+int32_t dbsp_batcher_push(dbsp_ctx* ctx, dbsp_batcher* bq, const uint64_t* const* cols, const int64_t* w, uint64_t n,
+                          int32_t on_device) {
+  Batcher* q = (Batcher*)bq;
+  if (n == 0) return DBSP_OK;
+  dbsp_batch* b = nullptr;
+  TRY(dbsp_batch_from_tuples(ctx, &q->s, cols, w, n, on_device, &b));
+  return batcher_enqueue(ctx, q, B(b));
+}
+int32_t dbsp_batcher_push_consolidated(dbsp_ctx* ctx, dbsp_batcher* bq, const uint64_t* const* cols, const int64_t* w,
+                                       uint64_t n, int32_t on_device) {
+  Batcher* q = (Batcher*)bq;
+  if (n == 0) return DBSP_OK;
+  CHECK_ARG(w != nullptr, "push_consolidated: weights required");
+  dbsp_batch* b = nullptr;
+  TRY(dbsp_batch_from_sorted(ctx, &q->s, cols, w, n, on_device, &b));
+  return batcher_enqueue(ctx, q, B(b));
+}
+int32_t dbsp_batcher_tuples(const dbsp_batcher* bq, uint64_t* n) {
+  u64 t = 0;
+  for (Batch* b : ((const Batcher*)bq)->queue) t += b->n;
+  *n = t;
+  return DBSP_OK;
+}
+int32_t dbsp_batcher_free(dbsp_batcher* bq) {
+  Batcher* q = (Batcher*)bq;
+  if (!q) return DBSP_OK;
+  for (Batch* b : q->queue) batch_unref(b);
+  delete q;
+  return DBSP_OK;
+}
+int32_t dbsp_batcher_seal(dbsp_ctx* ctx, dbsp_batcher* bq, dbsp_batch** out) {   // finish_into (:251-265) + Builder
+  Batcher* q = (Batcher*)bq;
+  while (q->queue.size() >= 2) {
+    Batch* y = q->queue.back(); q->queue.pop_back();
+    Batch* x = q->queue.back(); q->queue.pop_back();
+    Batch* m = nullptr;
+    int32_t rc = merge_batches(ctx, x, y, &m);
+    batch_unref(x);
+    batch_unref(y);
+    if (rc) return rc;
+    if (m->n) q->queue.push_back(m); else batch_unref(m);
+  }
+  Batch* r = q->queue.empty() ? batch_new_empty(ctx, q->s) : q->queue.back();
+  q->queue.clear();
+  delete q;
+  *out = H(r);
   return DBSP_OK;
 }
 

@@ -382,6 +382,60 @@ class Merger:
             pass
 
 
+class Batcher:
+    """Batcher (trace/mod.rs:316-335) = MergeBatcher (merge_batcher/mod.rs:22-81)."""
+
+    def __init__(self, be: "Backend", schema: Schema):
+        self.be, self.schema = be, schema
+        h = C.c_void_p()
+        be.api.call("batcher_new", be.ctx, C.byref(schema.c()), C.byref(h))
+        self.h = h.value
+
+    def _push(self, fn, cols, weights):
+        cols = [as_u64(c) for c in cols]
+        n = len(cols[0]) if cols else 0
+        w = np.ascontiguousarray(np.asarray(weights, dtype=np.int64)) if weights is not None else None
+        self.be.api.call(fn, self.be.ctx, self.h, col_ptrs(cols), w.ctypes.data if w is not None else None, n, 0)
+
+    def push_batch(self, cols: Sequence, weights=None):
+        """Unsorted tuples, column-major host arrays (weights None = all +1)."""
+        self._push("batcher_push", cols, weights)
+
+    def push_rows(self, rows: Iterable[Sequence[int]]):
+        rows = list(rows)
+        if not rows:
+            return
+        arr = [[_wrap(r[l]) for r in rows] for l in range(self.schema.nl)]
+        self.push_batch([np.array(a, dtype=np.uint64) for a in arr], [r[-1] for r in rows])
+
+    def push_consolidated_batch(self, cols: Sequence, weights):
+        """Rows already sorted, unique and non-zero."""
+        self._push("batcher_push_consolidated", cols, weights)
+
+    def tuples(self) -> int:
+        n = C.c_uint64()
+        self.be.api.call("batcher_tuples", self.h, C.byref(n))
+        return n.value
+
+    def seal(self) -> Batch:
+        out = C.c_void_p()
+        h, self.h = self.h, None   # consumed by the library
+        self.be.api.call("batcher_seal", self.be.ctx, h, C.byref(out))
+        return Batch(self.be, out.value, self.schema)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.be.api._batcher_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def _wrap(x):
+    return int(x) & ((1 << 64) - 1)
+
+
 def _lanes(vals: Sequence[int] | None):
     if vals is None:
         return None
@@ -516,6 +570,9 @@ class Backend:
         else:
             self.api.call("batch_merge_bounded", self.ctx, a.h, b.h, _lanes(val_lower_bound), C.byref(out))
         return Batch(self, out.value, a.schema)
+
+    def batcher(self, schema: Schema) -> "Batcher":
+        return Batcher(self, schema)
 
     def merger(self, a: Batch, b: Batch, val_lower_bound: Sequence[int] | None = None) -> "Merger":
         return Merger(self, a, b, val_lower_bound)

@@ -190,6 +190,24 @@ int32_t dbsp_batch_empty(dbsp_ctx* ctx, const dbsp_schema* schema,
  * column_layer/builders.rs:98-169; ordered/mod.rs:344-396,806-834). */
 int32_t dbsp_batch_merge(dbsp_ctx* ctx, const dbsp_batch* a,
                          const dbsp_batch* b, dbsp_batch** out);
+/* Batcher (trace/mod.rs:316-335) = MergeBatcher (trace/ord/merge_batcher/mod.rs:22-81,
+ * 155-260): push_batch consolidates the pushed tuples and queues them, merging
+ * the two newest queue entries while the newer is at least half the older;
+ * push_consolidated skips the consolidation (rows already sorted, unique, non-zero);
+ * seal merges what is left into one batch and frees the batcher. */
+typedef struct dbsp_batcher dbsp_batcher;
+int32_t dbsp_batcher_new(dbsp_ctx* ctx, const dbsp_schema* schema,
+                         dbsp_batcher** out);
+int32_t dbsp_batcher_push(dbsp_ctx* ctx, dbsp_batcher* b,
+                          const uint64_t* const* cols, const int64_t* weights,
+                          uint64_t n, int32_t on_device);
+int32_t dbsp_batcher_push_consolidated(dbsp_ctx* ctx, dbsp_batcher* b,
+                                       const uint64_t* const* cols,
+                                       const int64_t* weights, uint64_t n,
+                                       int32_t on_device);
+int32_t dbsp_batcher_tuples(const dbsp_batcher* b, uint64_t* n_tuples);
+int32_t dbsp_batcher_seal(dbsp_ctx* ctx, dbsp_batcher* b, dbsp_batch** out);
+int32_t dbsp_batcher_free(dbsp_batcher* b);
 /* Merger::work with a lower value bound, run to completion
  * (trace/ord/indexed_zset_batch.rs:359-382 -> ordered/mod.rs:587-746
  * push_merge_truncate_values_fueled): values below `val_lower_bound`

@@ -602,6 +602,51 @@ int32_t orc_batch_merge(orc_ctx*, const orc_batch* a, const orc_batch* b, orc_ba
   return DBSP_OK;
 }
 
+// MergeBatcher (trace/ord/merge_batcher/mod.rs:22-81, 155-260): push consolidates
+// and queues; the two newest entries merge while the newer is at least half the
+// older (the reference counts 8 KiB chunks, this port counts rows); seal =
+// finish_into + Builder.
+struct orc_batcher { dbsp_schema s; std::vector<BatchP> queue; };
+static void batcher_enqueue(orc_batcher* q, BatchP b) {
+  if (b->len() == 0) return;
+  q->queue.push_back(b);
+  while (q->queue.size() > 1 && q->queue[q->queue.size() - 1]->len() >= q->queue[q->queue.size() - 2]->len() / 2) {
+    BatchP y = q->queue.back(); q->queue.pop_back();
+    BatchP x = q->queue.back(); q->queue.pop_back();
+    BatchP m = merge(x, y);
+    if (m->len()) q->queue.push_back(m);
+  }
+}
+int32_t orc_batcher_new(orc_ctx*, const dbsp_schema* s, orc_batcher** out) { *out = new orc_batcher{*s, {}}; return DBSP_OK; }
+int32_t orc_batcher_push(orc_ctx*, orc_batcher* q, const u64* const* cols, const i64* w, u64 n, int32_t) {
+  if (n) batcher_enqueue(q, from_tuples(q->s, cols, w, n));
+  return DBSP_OK;
+}
+int32_t orc_batch_from_sorted(orc_ctx* c, const dbsp_schema* s, const u64* const* cols, const i64* w, u64 n, int32_t od,
+                              orc_batch** out);
+int32_t orc_batcher_push_consolidated(orc_ctx* c, orc_batcher* q, const u64* const* cols, const i64* w, u64 n, int32_t od) {
+  if (!n) return DBSP_OK;
+  orc_batch* b = nullptr;
+  int32_t rc = orc_batch_from_sorted(c, &q->s, cols, w, n, od, &b);
+  if (rc) return rc;
+  batcher_enqueue(q, b->p);
+  delete b;
+  return DBSP_OK;
+}
+int32_t orc_batcher_tuples(const orc_batcher* q, u64* n) { u64 t = 0; for (auto& b : q->queue) t += b->len(); *n = t; return DBSP_OK; }
+int32_t orc_batcher_free(orc_batcher* q) { delete q; return DBSP_OK; }
+int32_t orc_batcher_seal(orc_ctx*, orc_batcher* q, orc_batch** out) {
+  while (q->queue.size() >= 2) {
+    BatchP y = q->queue.back(); q->queue.pop_back();
+    BatchP x = q->queue.back(); q->queue.pop_back();
+    BatchP m = merge(x, y);
+    if (m->len()) q->queue.push_back(m);
+  }
+  *out = wrap(q->queue.empty() ? std::make_shared<Batch>(q->s) : q->queue.back());
+  delete q;
+  return DBSP_OK;
+}
+
 // Merger::work with a lower value bound run to completion
 // (indexed_zset_batch.rs:359-382; ordered/mod.rs:587-746).  OrdZSet ignores the
 // bound (zset_batch.rs:307-318).

@@ -93,6 +93,46 @@ def run_join_test(be):
     assert got["join"] == inc_outputs
 
 
+# ---- merge batcher (dbsp/src/trace/ord/merge_batcher/tests.rs:26-125) ---------
+def run_merge_batcher(be):
+    """The literal MergeSorter tests, observed through push / seal (the chunk
+    structure of the reference's expected values is flattened)."""
+    def cols(rows, nl):
+        return [np.array([r[l] for r in rows], dtype=np.uint64) for l in range(nl)], np.array([r[-1] for r in rows], dtype=np.int64)
+
+    one, two = Schema("u"), Schema("uu")
+    # merge_empty_inputs
+    b = be.batcher(one)
+    assert b.tuples() == 0 and b.seal().rows() == []
+    # small_push: queue [[(0,0):1], [(45,0):-1]] then push [(45,1):1]
+    b = be.batcher(two)
+    b.push_consolidated_batch(*cols([(0, 0, 1), (45, 0, -1)], 2))
+    b.push_batch(*cols([(45, 1, 1)], 2))
+    assert b.seal().rows() == [(0, 0, 1), (45, 0, -1), (45, 1, 1)]
+    # merge_by
+    b = be.batcher(one)
+    b.push_consolidated_batch(*cols([(0, 1), (1, 6), (24, 5), (54, -23)], 1))
+    b.push_consolidated_batch(*cols([(0, 7), (1, 6), (24, -5), (25, 12), (89, 1)], 1))
+    assert b.seal().rows() == [(0, 8), (1, 12), (25, 12), (54, -23), (89, 1)]
+    # push_with_excess_stashes
+    b = be.batcher(one)
+    b.push_batch(*cols([(0, 1), (1, 6), (24, 5), (54, -23)], 1))
+    assert b.tuples() == 4
+    assert b.seal().rows() == [(0, 1), (1, 6), (24, 5), (54, -23)]
+    # force_finish_merge / force_merge_on_push
+    expected = [(0, 9), (1, 18), (23, 54), (24, 5), (25, 12), (54, -46), (89, 1), (97, -102)]
+    for last_is_push in (False, True):
+        b = be.batcher(one)
+        b.push_consolidated_batch(*cols([(0, 1), (1, 6), (24, 5), (54, -23)], 1))
+        b.push_consolidated_batch(*cols([(89, 1)], 1))
+        b.push_consolidated_batch(*cols([(0, 8), (1, 12), (25, 12), (54, -23)], 1))
+        if last_is_push:
+            b.push_batch(*cols([(97, -102), (23, 54)], 1))
+        else:
+            b.push_consolidated_batch(*cols([(23, 54), (97, -102)], 1))
+        assert b.seal().rows() == expected
+
+
 # ---- antijoin (dbsp/src/operator/join.rs:1335-1385) --------------------------
 def run_antijoin(be):
     input1 = [[(1, 0, 1), (1, 1, 2), (2, 0, 1), (2, 1, 1)], [(3, 1, 1)], [], [(2, 2, 1), (4, 1, 1)]]
@@ -415,6 +455,7 @@ ALL_CASES = {
     "window_sliding": run_window_sliding,
     "window_tumbling": run_window_tumbling,
     "antijoin": run_antijoin,
+    "merge_batcher": run_merge_batcher,
     "window_shrinking": run_window_shrinking,
     "watermark": run_watermark,
     "q3": run_q3,
