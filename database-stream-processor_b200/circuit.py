@@ -224,7 +224,7 @@ class Stream:
     def stream_join(self, other: "Stream", proj: Proj) -> "Stream":
         """stream_join (operator/join.rs:52-84): stateless Join::eval."""
         be = self.circuit.be
-        l, r = self.shard(), other.shard()
+        l, r = self.shard_with(other)
         return l._binary(r, lambda a, b: be.join_batches(a, b, proj), "stream_join", proj.schema)
 
     def semijoin_stream(self, keys: "Stream") -> "Stream":
@@ -261,7 +261,7 @@ class Stream:
         """join / join_index / join_generic (operator/join.rs:180-292):
         delta_L |x| trace(R) + delta_R |x| z^-1 trace(L), both sides sharded."""
         be = self.circuit.be
-        left, right = self.shard(), other.shard()
+        left, right = self.shard_with(other)
         lt, rt = Spine(be, left.schema), Spine(be, right.schema)
 
         def fn(dl: Batch, dr: Batch):
@@ -443,6 +443,18 @@ class Stream:
             return Stream(self.circuit, self.node, self.schema, True)
         be = self.circuit.be
         return self._unary(lambda b: comm.shard(be, b), "shard", self.schema, True)
+
+    def shard_with(self, other: "Stream") -> tuple["Stream", "Stream"]:
+        """shard() of both inputs of a binary operator (join.rs:265-266) in ONE
+        exchange round: same result as (self.shard(), other.shard())."""
+        comm = self.circuit.comm
+        if comm is None or comm.world_size == 1 or self.sharded or other.sharded:
+            return self.shard(), other.shard()
+        be = self.circuit.be
+        pair = Node(self.circuit, [self.node, other.node], lambda a, b: comm.shard_many(be, [a, b]), "shard2")
+        left = Stream(self.circuit, Node(self.circuit, [pair], lambda t: t[0], "shard2.0"), self.schema, True)
+        right = Stream(self.circuit, Node(self.circuit, [pair], lambda t: t[1], "shard2.1"), other.schema, True)
+        return left, right
 
     def gather(self, root: int = 0) -> "Stream":
         """gather (operator/communication/gather.rs:41-103)."""

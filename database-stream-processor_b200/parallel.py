@@ -48,53 +48,69 @@ class Comm:
     # -- batches -----------------------------------------------------------
     def _exchange(self, be: Backend, parts: list[Batch]) -> list[Batch]:
         """All-to-all of one batch per peer; returns the batches received."""
-        P = self.world_size
-        schema = parts[0].schema
-        L1 = schema.nl + 1
-        counts = [len(p) for p in parts]
-        send_counts = torch.tensor(counts, dtype=torch.int64, device=self.device)
-        recv_counts = torch.empty(P, dtype=torch.int64, device=self.device)
+        return self._exchange_many(be, [parts])[0]
+
+    def _exchange_many(self, be: Backend, streams: list[list[Batch]]) -> list[list[Batch]]:
+        """One exchange round for several streams at once: streams[i][p] is the
+        batch of stream i destined to peer p.  One count all-to-all (one count
+        per stream and peer) and ONE payload all-to-all whose per-peer segment
+        is the concatenation of the streams' [lane.. | weights] blocks — the
+        fixed latency of an exchange is paid once per operator, not once per
+        input (a join shards both of its inputs in the same step)."""
+        P, nS = self.world_size, len(streams)
+        schemas = [parts[0].schema for parts in streams]
+        L1 = [s.nl + 1 for s in schemas]
+        counts = [[len(streams[i][p]) for i in range(nS)] for p in range(P)]      # [peer][stream]
+        send_counts = torch.tensor(counts, dtype=torch.int64, device=self.device).reshape(-1)
+        recv_counts = torch.empty(P * nS, dtype=torch.int64, device=self.device)
         dist.all_to_all_single(recv_counts, send_counts, group=self.group)
-        rc = recv_counts.tolist()
+        rc = recv_counts.reshape(P, nS).tolist()                                  # [peer][stream]
         segs = []
         be.sync()   # the partition kernels ran on the library's stream; torch reads the columns on its own
-        for p in parts:
-            cols, w = be.batch_flat_tensors(p, synced=True)
-            segs.extend(cols)
-            segs.append(w)
-        send = torch.cat(segs) if sum(counts) else torch.empty(0, dtype=torch.int64, device=self.device)
-        recv = torch.empty(sum(rc) * L1, dtype=torch.int64, device=self.device)
-        dist.all_to_all_single(recv, send, output_split_sizes=[c * L1 for c in rc],
-                               input_split_sizes=[c * L1 for c in counts], group=self.group)
-        self.bytes_sent += (sum(counts) - counts[self.rank]) * L1 * 8
+        for p in range(P):
+            for i in range(nS):
+                if counts[p][i]:
+                    cols, w = be.batch_flat_tensors(streams[i][p], synced=True)
+                    segs.extend(cols)
+                    segs.append(w)
+        send = torch.cat(segs) if segs else torch.empty(0, dtype=torch.int64, device=self.device)
+        in_split = [sum(counts[p][i] * L1[i] for i in range(nS)) for p in range(P)]
+        out_split = [sum(rc[q][i] * L1[i] for i in range(nS)) for q in range(P)]
+        recv = torch.empty(sum(out_split), dtype=torch.int64, device=self.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=out_split, input_split_sizes=in_split, group=self.group)
+        self.bytes_sent += sum(in_split[p] for p in range(P) if p != self.rank) * 8
         if recv.is_cuda:
             torch.cuda.current_stream(recv.device).synchronize()   # once, before the library adopts the segments
-        total = sum(rc)
-        if 0 < total <= self.SORT_THRESHOLD and P > 2:
-            # Small deltas: P-1 merges cost more in launches and read-backs than one
-            # consolidation of the concatenated segments (Batch::from_tuples).
-            cols = []
-            for l in range(schema.nl):
-                cols.append(torch.cat([recv[off + l * n: off + (l + 1) * n] for off, n in self._segments(rc, L1)]))
-            w = torch.cat([recv[off + schema.nl * n: off + L1 * n] for off, n in self._segments(rc, L1)])
-            return [be.batch_from_device_tensors(schema, cols, w)]
-        out, off = [], 0
+        # offsets of stream i's block inside peer q's segment
+        base, off = [], 0
         for q in range(P):
-            n = rc[q]
-            seg = recv[off: off + n * L1]
-            off += n * L1
-            cols = [seg[l * n: (l + 1) * n] for l in range(schema.nl)]
-            out.append(be.batch_from_flat_tensors(schema, cols, seg[schema.nl * n: L1 * n], synced=True))
+            row = []
+            for i in range(nS):
+                row.append(off)
+                off += rc[q][i] * L1[i]
+            base.append(row)
+        out = []
+        for i in range(nS):
+            schema, l1 = schemas[i], L1[i]
+            ns = [rc[q][i] for q in range(P)]
+            total = sum(ns)
+            if 0 < total <= self.SORT_THRESHOLD and P > 2:
+                # Small deltas: P-1 merges cost more in launches and read-backs than one
+                # consolidation of the concatenated segments (Batch::from_tuples).
+                cols = [torch.cat([recv[base[q][i] + l * ns[q]: base[q][i] + (l + 1) * ns[q]] for q in range(P)])
+                        for l in range(schema.nl)]
+                w = torch.cat([recv[base[q][i] + schema.nl * ns[q]: base[q][i] + l1 * ns[q]] for q in range(P)])
+                out.append([be.batch_from_device_tensors(schema, cols, w)])
+                continue
+            got = []
+            for q in range(P):
+                n, o = ns[q], base[q][i]
+                cols = [recv[o + l * n: o + (l + 1) * n] for l in range(schema.nl)]
+                got.append(be.batch_from_flat_tensors(schema, cols, recv[o + schema.nl * n: o + l1 * n], synced=True))
+            out.append(got)
         return out
 
     SORT_THRESHOLD = 1 << 20
-
-    @staticmethod
-    def _segments(rc, L1):
-        off = 0
-        for n in rc:
-            yield off, n
-            off += n * L1
 
     @staticmethod
     def _merge_all(be: Backend, batches: list[Batch]) -> Batch:
@@ -111,6 +127,11 @@ class Comm:
         """shard (communication/shard.rs:106-162)."""
         parts = be.shard_partition(b, self.world_size)
         return self._merge_all(be, self._exchange(be, parts))
+
+    def shard_many(self, be: Backend, batches: list[Batch]) -> list[Batch]:
+        """shard() of several streams in one exchange round (the two inputs of a join)."""
+        streams = [be.shard_partition(b, self.world_size) for b in batches]
+        return [self._merge_all(be, got) for got in self._exchange_many(be, streams)]
 
     def gather(self, be: Backend, b: Batch, root: int = 0) -> Batch:
         """gather (communication/gather.rs:41-103): everything to `root`,

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-WORLD = 3   # > 2 so that the small-delta consolidation path of the receiver is exercised too
+WORLDS = [2, 3]   # 2: receiver merges the peers' sorted segments; > 2: small deltas are consolidated in one go
 
 
 def _free_port():
@@ -65,14 +65,15 @@ def _worker(rank, world, port, query, n_events, step, outdir):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("world", WORLDS)
 @pytest.mark.parametrize("query", ["q3", "q4", "q7"])
-def test_sharded_equals_single(tmp_path, oracle, query):
+def test_sharded_equals_single(tmp_path, oracle, query, world):
     from parity_util import build_query, feed
     from dbsp_b200.nexmark import NexmarkGenerator
 
     n_events, step = (120_000, 40_000) if query != "q7" else (400_000, 100_000)
     port = _free_port()
-    mp.spawn(_worker, args=(WORLD, port, query, n_events, step, str(tmp_path)), nprocs=WORLD, join=True)
+    mp.spawn(_worker, args=(world, port, query, n_events, step, str(tmp_path)), nprocs=world, join=True)
     sharded = np.load(os.path.join(tmp_path, "sharded.npy"), allow_pickle=True)
     c, handles, out = build_query(oracle, query)
     gen = NexmarkGenerator()
