@@ -56,6 +56,10 @@ class ThreadComm:
     def shard(self, be, b):
         return self._merge_all(be, self._exchange(be.shard_partition(b, self.world_size)))
 
+    def shard_many(self, be, batches):
+        # in-process mailboxes have no per-round latency worth fusing: one round per stream (exchange.rs:128-200)
+        return [self.shard(be, b) for b in batches]
+
     def gather(self, be, b, root=0):
         empty = be.batch_empty(b.schema)
         return self._merge_all(be, self._exchange([b if p == root else empty for p in range(self.world_size)]))
