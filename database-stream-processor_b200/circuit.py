@@ -329,6 +329,25 @@ class Stream:
 
         return s._unary(fn, "aggregate", out_schema, not local)
 
+    def stream_aggregate(self, aggregator) -> "Stream":
+        """stream_aggregate (operator/aggregate/mod.rs:172-196): Aggregate::eval
+        (:362-376) — the aggregate of every key of *this step's* batch with
+        weight +1; no state.  Runs the same kernels as `aggregate` on a trace
+        holding only the batch and an empty output trace."""
+        be = self.circuit.be
+        s = self.shard()
+        kind = aggregator.kind
+        out_schema = s.schema if kind in (capi.AGG_MAX, capi.AGG_MIN) else Schema(s.schema.key, "u")
+
+        def fn(d: Batch):
+            if len(d) == 0:
+                return be.batch_empty(out_schema)
+            tin, tout = Spine(be, s.schema), Spine(be, out_schema)
+            tin.insert(d)
+            return be.aggregate_delta(d, tin, tout, kind)
+
+        return s._unary(fn, "stream_aggregate", out_schema, True)
+
     def weigh(self, f, mode=capi.WEIGH_LINEAR) -> "Stream":
         """weigh (operator/aggregate/mod.rs:285-323)."""
         be = self.circuit.be
