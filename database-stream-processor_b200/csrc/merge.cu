@@ -9,17 +9,22 @@
 // summed and zero sums are dropped.
 //
 // One pass over HBM.  A merge-path partition kernel cuts the merged sequence
-// into tiles.  Each CTA stages its A and B segments in shared memory with TMA
-// bulk copies (cp.async.bulk + mbarrier: one thread issues 2*(L+1) copies, no
-// registers, no per-thread address arithmetic); every thread
+// into tiles.  Each CTA first asks L2 to prefetch the inputs of a tile 148
+// tiles ahead (cp.async.bulk.prefetch.L2), then stages the *lanes* of its A and
+// B segments in shared memory with TMA bulk copies (cp.async.bulk + mbarrier:
+// one thread issues 2*L copies, no registers, no per-thread address
+// arithmetic); the weights never enter shared memory.  Every thread
 // merge-path-searches its own diagonal and serially merges IPT rows with both
-// run heads in registers; kept rows are compacted in shared memory and written
-// back coalesced.  Because both inputs are consolidated, an equal pair is
-// always (a, b) adjacent in merged order: the A row absorbs its partner's
+// run heads in registers, then fetches its rows' weights in one batch of
+// independent loads; kept rows are compacted as 16-bit slot ids, gathered and
+// written back coalesced.  Because both inputs are consolidated, an equal pair
+// is always (a, b) adjacent in merged order: the A row absorbs its partner's
 // weight, the B row is skipped — also across thread and tile boundaries (one
 // halo row on each side).  The tile's global output offset comes from a
 // decoupled look-back over per-tile status words (tile index = block index:
 // CTAs are dispatched in order, so predecessors are always resident or done).
+// Tile shapes, register caps, look-back width and prefetch distance were swept
+// on the B200 (profiles/README.md).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
