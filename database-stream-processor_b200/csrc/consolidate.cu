@@ -23,6 +23,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
+#include "segsort.cuh"
 
 namespace {
 
@@ -405,6 +406,25 @@ inline int bits_for(u64 range) { return range == 0 ? 0 : 64 - __builtin_clzll(ra
 
 }  // namespace
 
+// ---- experimental prefix-sorted path (segsort.cuh; DBSP_PREFIX_SORT=1) ----------
+// out[0] += inversions on lane 0, out[1] = longest equal-lane-0 run (capped at SEG_RUN_CAP + 1)
+__global__ void k_lane0_props(Cols cols, Flips f, u64 n, u64* out) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned inv = 0, run = 0;
+  if (i < n) inv = seg_lane0_props(cols.c[0], f.f[0], n, i, &run);
+  const unsigned m = __ballot_sync(0xffffffffu, inv != 0);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) run = max(run, __shfl_xor_sync(0xffffffffu, run, o));
+  if ((threadIdx.x & 31) == 0) {
+    if (m) atomicAdd((unsigned long long*)&out[0], (unsigned long long)__popc(m));
+    if (run) atomicMax((unsigned long long*)&out[1], (unsigned long long)run);
+  }
+}
+__global__ void k_segment_rank(Cols cols, Flips f, int L, u64 n, u32* idx) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) seg_rank_row(cols.c, f.f, L, n, i, idx);
+}
+
 int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const i64* w, u64 n, const BufP* adopt,
                          Batch** out, const u32* d_n) {
   const int L = s.n_key_lanes + s.n_val_lanes;
@@ -459,6 +479,32 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
     p.W = 1;
     p.use_key = 0;   // compare / copy the lanes themselves, identity order
   } else {
+    // ---- (2b) experimental: lane 0 already ordered, short equal-lane-0 runs ------
+    // (time-ordered event tables): rank every row inside its run instead of sorting
+    // the whole batch.  Off unless DBSP_PREFIX_SORT is set (not yet measured).
+    static const bool prefix_sort = getenv("DBSP_PREFIX_SORT") != nullptr;
+    bool ranked = false;
+    if (prefix_sort && L >= 2 && n > 1) {
+      u64* d = ctx->d_scratch + 44;
+      CUDA_TRY(cudaMemsetAsync(d, 0, 16, st));
+      k_lane0_props<<<nblk, TB, 0, st>>>(cols, f, n, d);
+      LAUNCH_COUNT(ctx);
+      u64 h[2];
+      TRY(read_back(ctx, d, 2, h));
+      if (h[0] == 0 && h[1] <= SEG_RUN_CAP) {
+        TRY(dev_alloc(ctx, (size_t)n * 4, &ibuf));
+        {
+          ProfScope ps(ctx, KID_MISC, n * (u64)L * 8 + n * 4);
+          k_segment_rank<<<nblk, TB, 0, st>>>(cols, f, L, n, (u32*)ibuf->p);
+        }
+        LAUNCH_COUNT(ctx);
+        idx_cur = (u32*)ibuf->p;
+        p.W = 1;
+        p.use_key = 0;   // compare / copy the lanes themselves through the row ids
+        ranked = true;
+      }
+    }
+    if (!ranked) {
     // ---- (3) bit-packing plan: lanes from last (least significant) to first ----
     int word = 0, used = 0;
     for (int l = L - 1; l >= 0; l--) {
@@ -519,6 +565,7 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
         key_sorted = dk.Current();
       }
     }
+    }   // !ranked
   }
 
   // ---- (4) epilogue -------------------------------------------------------------
