@@ -231,7 +231,7 @@ class Stream:
         """semijoin_stream (operator/semijoin.rs:38-62)."""
         be = self.circuit.be
         l, r = self.shard(), keys.shard()
-        return l._binary(r, lambda a, b: be.semijoin(a, b), "semijoin", self.schema, True)
+        return l._binary(r, lambda a, b: be.semijoin(a, b), "semijoin", Schema(self.schema.lanes), True)
 
     # -- stateful ------------------------------------------------------------
     def integrate(self) -> "Stream":

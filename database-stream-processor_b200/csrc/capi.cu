@@ -19,6 +19,9 @@ struct dbsp_batcher;
 static inline Batch* B(const dbsp_batch* b) { return (Batch*)b; }
 static inline dbsp_batch* H(Batch* b) { return (dbsp_batch*)b; }
 
+// every entry point makes the context's device current: a host may drive several contexts (GPUs) from one
+// process, one per worker thread
+#define ENTER(c) CUDA_TRY(cudaSetDevice((c)->device))
 #define CHECK_ARG(c, msg)                 \
   do {                                    \
     if (!(c)) { set_error(msg); return DBSP_ERR_INVALID; } \
@@ -198,11 +201,11 @@ int32_t dbsp_ctx_destroy(dbsp_ctx* c) {
   if (c->live_bufs.load() == 0) delete c;   // else the last DevBuf deletes it
   return DBSP_OK;
 }
-int32_t dbsp_ctx_sync(dbsp_ctx* c) {
+int32_t dbsp_ctx_sync(dbsp_ctx* c) { ENTER(c);
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return DBSP_OK;
 }
-int32_t dbsp_ctx_stats(dbsp_ctx* c, uint64_t* k, uint64_t* h2d, uint64_t* d2h, int32_t reset) {
+int32_t dbsp_ctx_stats(dbsp_ctx* c, uint64_t* k, uint64_t* h2d, uint64_t* d2h, int32_t reset) { ENTER(c);
   if (k) *k = c->kernel_launches;
   if (h2d) *h2d = c->h2d_bytes;
   if (d2h) *d2h = c->d2h_bytes;
@@ -211,14 +214,14 @@ int32_t dbsp_ctx_stats(dbsp_ctx* c, uint64_t* k, uint64_t* h2d, uint64_t* d2h, i
 }
 void* dbsp_ctx_stream(dbsp_ctx* c) { return (void*)c->stream; }
 
-int32_t dbsp_ctx_profile(dbsp_ctx* c, int32_t enable) {
+int32_t dbsp_ctx_profile(dbsp_ctx* c, int32_t enable) { ENTER(c);
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   for (auto& r : c->prof) { c->ev_pool.push_back(r.a); c->ev_pool.push_back(r.b); }
   c->prof.clear();
   c->prof_on = enable != 0;
   return DBSP_OK;
 }
-int32_t dbsp_ctx_profile_read(dbsp_ctx* c, int32_t id, char* name32, uint64_t* launches, double* ms, uint64_t* bytes) {
+int32_t dbsp_ctx_profile_read(dbsp_ctx* c, int32_t id, char* name32, uint64_t* launches, double* ms, uint64_t* bytes) { ENTER(c);
   if (id < 0 || id >= KID_COUNT) return DBSP_ERR_INVALID;
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   u64 n = 0, b = 0;
@@ -238,7 +241,7 @@ int32_t dbsp_ctx_profile_read(dbsp_ctx* c, int32_t id, char* name32, uint64_t* l
 }
 
 int32_t dbsp_batch_from_tuples(dbsp_ctx* ctx, const dbsp_schema* s, const uint64_t* const* cols, const int64_t* w,
-                               uint64_t n, int32_t on_device, dbsp_batch** out) {
+                               uint64_t n, int32_t on_device, dbsp_batch** out) { ENTER(ctx);
   int L = s->n_key_lanes + s->n_val_lanes;
   CHECK_ARG(L >= 1 && L <= MAXL, "schema must have 1..8 lanes");
   BufP hold;
@@ -252,7 +255,7 @@ int32_t dbsp_batch_from_tuples(dbsp_ctx* ctx, const dbsp_schema* s, const uint64
 }
 
 int32_t dbsp_batch_from_table(dbsp_ctx* ctx, const uint64_t* const* cols, uint32_t n_cols, const int64_t* w, uint64_t n,
-                              int32_t on_device, const dbsp_proj* proj, dbsp_batch** out) {
+                              int32_t on_device, const dbsp_proj* proj, dbsp_batch** out) { ENTER(ctx);
   CHECK_ARG(n_cols >= 1 && n_cols <= MAXL, "table must have 1..8 columns");
   BufP hold;
   Cols dc;
@@ -277,7 +280,7 @@ struct dbsp_upload {
 uint32_t dbsp_proj_table_mask(const dbsp_proj* proj) { return proj_used_mask(*proj, 0); }
 
 int32_t dbsp_upload_begin(dbsp_ctx* ctx, const uint64_t* const* cols, uint32_t n_cols, uint32_t col_mask,
-                          const int64_t* w, uint64_t n, dbsp_upload** out) {
+                          const int64_t* w, uint64_t n, dbsp_upload** out) { ENTER(ctx);
   CHECK_ARG(n_cols >= 1 && n_cols <= MAXL, "table must have 1..8 columns");
   dbsp_upload* u = new dbsp_upload();
   u->ctx = ctx;
@@ -314,7 +317,7 @@ int32_t dbsp_upload_begin(dbsp_ctx* ctx, const uint64_t* const* cols, uint32_t n
   return DBSP_OK;
 }
 
-int32_t dbsp_batch_from_upload(dbsp_ctx* ctx, dbsp_upload* u, const dbsp_proj* proj, dbsp_batch** out) {
+int32_t dbsp_batch_from_upload(dbsp_ctx* ctx, dbsp_upload* u, const dbsp_proj* proj, dbsp_batch** out) { ENTER(ctx);
   CUDA_TRY(cudaStreamWaitEvent(ctx->stream, u->done, 0));   // compute stream waits for the copy
   Batch* b = nullptr;
   TRY(project_and_consolidate(ctx, u->dc, 0, u->n_cols, u->dw, u->n, *proj, &b));
@@ -333,7 +336,7 @@ int32_t dbsp_upload_free(dbsp_upload* u) {
 }
 
 int32_t dbsp_batch_from_sorted(dbsp_ctx* ctx, const dbsp_schema* s, const uint64_t* const* cols, const int64_t* w,
-                               uint64_t n, int32_t on_device, dbsp_batch** out) {
+                               uint64_t n, int32_t on_device, dbsp_batch** out) { ENTER(ctx);
   int L = s->n_key_lanes + s->n_val_lanes;
   if (n == 0) { *out = H(batch_new_empty(ctx, *s)); return DBSP_OK; }
   Batch* b;
@@ -380,7 +383,7 @@ int32_t dbsp_batcher_new(dbsp_ctx*, const dbsp_schema* s, dbsp_batcher** out) {
   return DBSP_OK;
 }
 int32_t dbsp_batcher_push(dbsp_ctx* ctx, dbsp_batcher* bq, const uint64_t* const* cols, const int64_t* w, uint64_t n,
-                          int32_t on_device) {
+                          int32_t on_device) { ENTER(ctx);
   Batcher* q = (Batcher*)bq;
   if (n == 0) return DBSP_OK;
   dbsp_batch* b = nullptr;
@@ -388,7 +391,7 @@ int32_t dbsp_batcher_push(dbsp_ctx* ctx, dbsp_batcher* bq, const uint64_t* const
   return batcher_enqueue(ctx, q, B(b));
 }
 int32_t dbsp_batcher_push_consolidated(dbsp_ctx* ctx, dbsp_batcher* bq, const uint64_t* const* cols, const int64_t* w,
-                                       uint64_t n, int32_t on_device) {
+                                       uint64_t n, int32_t on_device) { ENTER(ctx);
   Batcher* q = (Batcher*)bq;
   if (n == 0) return DBSP_OK;
   CHECK_ARG(w != nullptr, "push_consolidated: weights required");
@@ -409,7 +412,7 @@ int32_t dbsp_batcher_free(dbsp_batcher* bq) {
   delete q;
   return DBSP_OK;
 }
-int32_t dbsp_batcher_seal(dbsp_ctx* ctx, dbsp_batcher* bq, dbsp_batch** out) {   // finish_into (:251-265) + Builder
+int32_t dbsp_batcher_seal(dbsp_ctx* ctx, dbsp_batcher* bq, dbsp_batch** out) { ENTER(ctx);   // finish_into (:251-265) + Builder
   Batcher* q = (Batcher*)bq;
   while (q->queue.size() >= 2) {
     Batch* y = q->queue.back(); q->queue.pop_back();
@@ -428,12 +431,12 @@ int32_t dbsp_batcher_seal(dbsp_ctx* ctx, dbsp_batcher* bq, dbsp_batch** out) {  
   return DBSP_OK;
 }
 
-int32_t dbsp_batch_empty(dbsp_ctx* ctx, const dbsp_schema* s, dbsp_batch** out) {
+int32_t dbsp_batch_empty(dbsp_ctx* ctx, const dbsp_schema* s, dbsp_batch** out) { ENTER(ctx);
   *out = H(batch_new_empty(ctx, *s));
   return DBSP_OK;
 }
 
-int32_t dbsp_batch_merge(dbsp_ctx* ctx, const dbsp_batch* a, const dbsp_batch* b, dbsp_batch** out) {
+int32_t dbsp_batch_merge(dbsp_ctx* ctx, const dbsp_batch* a, const dbsp_batch* b, dbsp_batch** out) { ENTER(ctx);
   Batch* o = nullptr;
   TRY(merge_batches(ctx, B(a), B(b), &o));
   *out = H(o);
@@ -441,14 +444,14 @@ int32_t dbsp_batch_merge(dbsp_ctx* ctx, const dbsp_batch* a, const dbsp_batch* b
 }
 
 int32_t dbsp_batch_merge_bounded(dbsp_ctx* ctx, const dbsp_batch* a, const dbsp_batch* b, const uint64_t* vb,
-                                 dbsp_batch** out) {
+                                 dbsp_batch** out) { ENTER(ctx);
   Batch* o = nullptr;
   TRY(merge_bounded(ctx, B(a), B(b), vb, &o));
   *out = H(o);
   return DBSP_OK;
 }
 
-int32_t dbsp_batch_truncate_keys_below(dbsp_ctx* ctx, const dbsp_batch* b, const uint64_t* key, dbsp_batch** out) {
+int32_t dbsp_batch_truncate_keys_below(dbsp_ctx* ctx, const dbsp_batch* b, const uint64_t* key, dbsp_batch** out) { ENTER(ctx);
   u64 pos;
   TRY(batch_lower_bound(ctx, B(b), key, &pos));
   if (pos == 0) { batch_ref(B(b)); *out = (dbsp_batch*)b; return DBSP_OK; }
@@ -456,7 +459,7 @@ int32_t dbsp_batch_truncate_keys_below(dbsp_ctx* ctx, const dbsp_batch* b, const
   return DBSP_OK;
 }
 
-int32_t dbsp_merger_new(dbsp_ctx* ctx, const dbsp_batch* a, const dbsp_batch* b, const uint64_t* vb, dbsp_merger** out) {
+int32_t dbsp_merger_new(dbsp_ctx* ctx, const dbsp_batch* a, const dbsp_batch* b, const uint64_t* vb, dbsp_merger** out) { ENTER(ctx);
   CHECK_ARG(memcmp(&B(a)->s, &B(b)->s, sizeof(dbsp_schema)) == 0, "merger_new: schema mismatch");
   Merger* m = new Merger();
   m->ctx = ctx;
@@ -472,7 +475,7 @@ int32_t dbsp_merger_new(dbsp_ctx* ctx, const dbsp_batch* a, const dbsp_batch* b,
   return DBSP_OK;
 }
 
-int32_t dbsp_merger_work(dbsp_ctx* ctx, dbsp_merger* mm, int64_t* fuel) {
+int32_t dbsp_merger_work(dbsp_ctx* ctx, dbsp_merger* mm, int64_t* fuel) { ENTER(ctx);
   Merger* m = (Merger*)mm;
   if (!m->complete() && *fuel > 0) {
     u64 na, nb;
@@ -504,7 +507,7 @@ int32_t dbsp_merger_free(dbsp_merger* mm) {
   return DBSP_OK;
 }
 
-int32_t dbsp_merger_done(dbsp_ctx* ctx, dbsp_merger* mm, dbsp_batch** out) {
+int32_t dbsp_merger_done(dbsp_ctx* ctx, dbsp_merger* mm, dbsp_batch** out) { ENTER(ctx);
   Merger* m = (Merger*)mm;
   CHECK_ARG(m->complete(), "merger_done: merge not complete");
   Batch* o = nullptr;
@@ -514,14 +517,14 @@ int32_t dbsp_merger_done(dbsp_ctx* ctx, dbsp_merger* mm, dbsp_batch** out) {
   return DBSP_OK;
 }
 
-int32_t dbsp_batch_neg(dbsp_ctx* ctx, const dbsp_batch* a, dbsp_batch** out) {
+int32_t dbsp_batch_neg(dbsp_ctx* ctx, const dbsp_batch* a, dbsp_batch** out) { ENTER(ctx);
   Batch* o = nullptr;
   TRY(op_neg(ctx, B(a), &o));
   *out = H(o);
   return DBSP_OK;
 }
 
-int32_t dbsp_batch_reindex(dbsp_ctx* ctx, const dbsp_batch* a, uint32_t nk, dbsp_batch** out) {
+int32_t dbsp_batch_reindex(dbsp_ctx* ctx, const dbsp_batch* a, uint32_t nk, dbsp_batch** out) { ENTER(ctx);
   const Batch* x = B(a);
   CHECK_ARG((int)nk <= x->nl(), "reindex: too many key lanes");
   Batch* v = new Batch();
@@ -539,7 +542,7 @@ int32_t dbsp_batch_reindex(dbsp_ctx* ctx, const dbsp_batch* a, uint32_t nk, dbsp
 }
 
 int32_t dbsp_batch_len(const dbsp_batch* b, uint64_t* n) { *n = B(b)->n; return DBSP_OK; }
-int32_t dbsp_batch_key_count(dbsp_ctx* ctx, const dbsp_batch* b, uint64_t* n) {
+int32_t dbsp_batch_key_count(dbsp_ctx* ctx, const dbsp_batch* b, uint64_t* n) { ENTER(ctx);
   Batch* x = B(b);
   if (x->s.n_val_lanes == 0) { *n = x->n; return DBSP_OK; }
   TRY(batch_build_csr(ctx, x));
@@ -549,7 +552,7 @@ int32_t dbsp_batch_key_count(dbsp_ctx* ctx, const dbsp_batch* b, uint64_t* n) {
 int32_t dbsp_batch_schema(const dbsp_batch* b, dbsp_schema* out) { *out = B(b)->s; return DBSP_OK; }
 
 int32_t dbsp_batch_download_csr(dbsp_ctx* ctx, const dbsp_batch* bb, uint64_t* const* keys, uint64_t* offs,
-                                uint64_t* const* vals, int64_t* diffs) {
+                                uint64_t* const* vals, int64_t* diffs) { ENTER(ctx);
   Batch* b = B(bb);
   cudaStream_t st = ctx->stream;
   int nk = b->s.n_key_lanes, nv = b->s.n_val_lanes;
@@ -587,7 +590,7 @@ int32_t dbsp_batch_device_columns(const dbsp_batch* b, const uint64_t** cols, co
   return DBSP_OK;
 }
 
-int32_t dbsp_batch_last_key(dbsp_ctx* ctx, const dbsp_batch* b, uint64_t* key, int32_t* valid) {
+int32_t dbsp_batch_last_key(dbsp_ctx* ctx, const dbsp_batch* b, uint64_t* key, int32_t* valid) { ENTER(ctx);
   const Batch* x = B(b);
   *valid = x->n > 0;
   if (!x->n) return DBSP_OK;
@@ -603,18 +606,18 @@ int32_t dbsp_batch_last_key(dbsp_ctx* ctx, const dbsp_batch* b, uint64_t* key, i
 int32_t dbsp_batch_clone(const dbsp_batch* b, dbsp_batch** out) { batch_ref(B(b)); *out = (dbsp_batch*)b; return DBSP_OK; }
 int32_t dbsp_batch_free(dbsp_batch* b) { batch_unref(B(b)); return DBSP_OK; }
 
-int32_t dbsp_spine_new(dbsp_ctx* ctx, const dbsp_schema* s, dbsp_spine** out) {
+int32_t dbsp_spine_new(dbsp_ctx* ctx, const dbsp_schema* s, dbsp_spine** out) { ENTER(ctx);
   dbsp_spine* sp = new dbsp_spine();
   sp->s = *s;
   sp->ctx = ctx;
   *out = sp;
   return DBSP_OK;
 }
-int32_t dbsp_spine_insert(dbsp_ctx* ctx, dbsp_spine* s, const dbsp_batch* b) {
+int32_t dbsp_spine_insert(dbsp_ctx* ctx, dbsp_spine* s, const dbsp_batch* b) { ENTER(ctx);
   CHECK_ARG(memcmp(&s->s, &B(b)->s, sizeof(dbsp_schema)) == 0, "spine_insert: schema mismatch");
   return spine_insert(ctx, s, B(b));
 }
-int32_t dbsp_spine_consolidate(dbsp_ctx* ctx, dbsp_spine* s, dbsp_batch** out) {
+int32_t dbsp_spine_consolidate(dbsp_ctx* ctx, dbsp_spine* s, dbsp_batch** out) { ENTER(ctx);
   Batch* acc = batch_new_empty(ctx, s->s);
   const u64* vb = s->has_vbound ? s->vbound : nullptr;
   for (Batch* b : s->batches) {
@@ -627,7 +630,7 @@ int32_t dbsp_spine_consolidate(dbsp_ctx* ctx, dbsp_spine* s, dbsp_batch** out) {
   *out = H(acc);
   return DBSP_OK;
 }
-int32_t dbsp_spine_truncate_keys_below(dbsp_ctx* ctx, dbsp_spine* s, const uint64_t* key) {
+int32_t dbsp_spine_truncate_keys_below(dbsp_ctx* ctx, dbsp_spine* s, const uint64_t* key) { ENTER(ctx);
   bool raise = !s->has_bound;
   if (!raise) {   // the bound only grows (spine_fueled.rs:223-233)
     for (int l = 0; l < s->s.n_key_lanes; l++) {
@@ -663,7 +666,7 @@ int32_t dbsp_spine_truncate_values_below(dbsp_ctx*, dbsp_spine* s, const uint64_
   s->has_vbound = true;
   return DBSP_OK;
 }
-int32_t dbsp_spine_exert(dbsp_ctx* ctx, dbsp_spine* s, int64_t* effort) {
+int32_t dbsp_spine_exert(dbsp_ctx* ctx, dbsp_spine* s, int64_t* effort) { ENTER(ctx);
   while (s->batches.size() >= 2) {
     size_t m = s->batches.size();
     int64_t cost = (int64_t)(s->batches[m - 2]->n + s->batches[m - 1]->n);
@@ -694,24 +697,24 @@ int32_t dbsp_spine_free(dbsp_spine* s) {
   return DBSP_OK;
 
 int32_t dbsp_join_delta_trace(dbsp_ctx* ctx, const dbsp_batch* d, const dbsp_spine* t, const dbsp_proj* p, int32_t dl,
-                              dbsp_batch** out) { OUT1(op_join_delta_trace(ctx, B(d), t, p, dl, &o__)) }
-int32_t dbsp_join_batches(dbsp_ctx* ctx, const dbsp_batch* l, const dbsp_batch* r, const dbsp_proj* p, dbsp_batch** out) {
+                              dbsp_batch** out) { ENTER(ctx); OUT1(op_join_delta_trace(ctx, B(d), t, p, dl, &o__)) }
+int32_t dbsp_join_batches(dbsp_ctx* ctx, const dbsp_batch* l, const dbsp_batch* r, const dbsp_proj* p, dbsp_batch** out) { ENTER(ctx);
   OUT1(op_join_batches(ctx, B(l), B(r), p, &o__)) }
-int32_t dbsp_semijoin(dbsp_ctx* ctx, const dbsp_batch* pairs, const dbsp_batch* keys, dbsp_batch** out) {
+int32_t dbsp_semijoin(dbsp_ctx* ctx, const dbsp_batch* pairs, const dbsp_batch* keys, dbsp_batch** out) { ENTER(ctx);
   OUT1(op_semijoin(ctx, B(pairs), B(keys), &o__)) }
 int32_t dbsp_aggregate_delta(dbsp_ctx* ctx, const dbsp_batch* d, const dbsp_spine* in_tr, const dbsp_spine* out_tr,
-                             int32_t kind, dbsp_batch** out) { OUT1(op_aggregate_delta(ctx, B(d), in_tr, out_tr, kind, &o__)) }
-int32_t dbsp_weigh(dbsp_ctx* ctx, const dbsp_batch* b, const dbsp_expr* f, int32_t mode, dbsp_batch** out) {
+                             int32_t kind, dbsp_batch** out) { ENTER(ctx); OUT1(op_aggregate_delta(ctx, B(d), in_tr, out_tr, kind, &o__)) }
+int32_t dbsp_weigh(dbsp_ctx* ctx, const dbsp_batch* b, const dbsp_expr* f, int32_t mode, dbsp_batch** out) { ENTER(ctx);
   OUT1(op_weigh(ctx, B(b), f, mode, &o__)) }
-int32_t dbsp_distinct_delta(dbsp_ctx* ctx, const dbsp_batch* d, const dbsp_spine* i, dbsp_batch** out) {
+int32_t dbsp_distinct_delta(dbsp_ctx* ctx, const dbsp_batch* d, const dbsp_spine* i, dbsp_batch** out) { ENTER(ctx);
   OUT1(op_distinct_delta(ctx, B(d), i, &o__)) }
-int32_t dbsp_stream_distinct(dbsp_ctx* ctx, const dbsp_batch* b, dbsp_batch** out) { OUT1(op_stream_distinct(ctx, B(b), &o__)) }
+int32_t dbsp_stream_distinct(dbsp_ctx* ctx, const dbsp_batch* b, dbsp_batch** out) { ENTER(ctx); OUT1(op_stream_distinct(ctx, B(b), &o__)) }
 int32_t dbsp_window_delta(dbsp_ctx* ctx, const dbsp_spine* t, const dbsp_batch* d, int32_t has_prev, const uint64_t* s0,
-                          const uint64_t* e0, const uint64_t* s1, const uint64_t* e1, dbsp_batch** out) {
+                          const uint64_t* e0, const uint64_t* s1, const uint64_t* e1, dbsp_batch** out) { ENTER(ctx);
   OUT1(op_window_delta(ctx, t, B(d), has_prev, s0, e0, s1, e1, &o__)) }
-int32_t dbsp_map_index(dbsp_ctx* ctx, const dbsp_batch* b, const dbsp_proj* p, dbsp_batch** out) {
+int32_t dbsp_map_index(dbsp_ctx* ctx, const dbsp_batch* b, const dbsp_proj* p, dbsp_batch** out) { ENTER(ctx);
   OUT1(op_map_index(ctx, B(b), p, &o__)) }
-int32_t dbsp_shard_partition(dbsp_ctx* ctx, const dbsp_batch* b, uint32_t P, dbsp_batch** outs) {
+int32_t dbsp_shard_partition(dbsp_ctx* ctx, const dbsp_batch* b, uint32_t P, dbsp_batch** outs) { ENTER(ctx);
   std::vector<Batch*> o(P, nullptr);
   TRY(op_shard_partition(ctx, B(b), P, o.data()));
   for (uint32_t p = 0; p < P; p++) outs[p] = H(o[p]);

@@ -615,11 +615,8 @@ int32_t merge_launch(Ctx* ctx, const Batch* a, const Batch* b, Batch** out) {
   i64* ow;
   TRY(batch_alloc(ctx, a->s, total, &o, &oc, &ow));
   Flips f = a->flips();
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(k_merge_tiles<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    attr_set = true;
-  }
+  // per *device* attribute and cheap: set on every launch (a process may drive several GPUs)
+  CUDA_TRY(cudaFuncSetAttribute(k_merge_tiles<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
   static const bool tma_off = getenv("DBSP_MERGE_NO_TMA") != nullptr;
   const int use_tma = (!tma_off && uniform_phase(a) && uniform_phase(b)) ? 1 : 0;
   {

@@ -30,7 +30,7 @@ const u64 HOT_AUCTION_RATIO = 2, HOT_BIDDERS_RATIO = 4, HOT_SELLERS_RATIO = 4;  
 const u64 HOT_RATIO_DIV = 100;         // bids.rs:12-13, auctions.rs:21
 const u64 NUM_ACTIVE_PEOPLE = 1000, PERSON_ID_LEAD = 10, NUM_IN_FLIGHT_AUCTIONS = 100;  // config.rs:11,71,81
 const u64 BASE_TIME = 1436918400000ull;   // 2015-07-15T00:00:00Z, the Nexmark epoch
-const double INTER_EVENT_DELAY_US = 1000000.0 / 10000000.0;   // first_event_rate = 10M/s (config.rs:50)
+const u64 DEFAULT_FIRST_EVENT_RATE = 10000000;   // NexmarkConfig::first_event_rate (config.rs:51,134), a CLI option there
 
 inline u64 mix64(u64 x) {
   x += 0x9e3779b97f4a7c15ull;
@@ -47,7 +47,7 @@ struct Rng {   // counter-based: stream (seed, event, draw#)
 };
 
 // generator/config.rs:118-120
-inline u64 timestamp_for_event(u64 n) { return BASE_TIME + (u64)(INTER_EVENT_DELAY_US * (double)n) / 1000; }
+inline u64 timestamp_for_event(double delay_us, u64 n) { return BASE_TIME + (u64)(delay_us * (double)n) / 1000; }
 // people.rs:105-113
 inline u64 last_base0_person_id(u64 event_id) {
   u64 epoch = event_id / TOTAL_PROP, offset = event_id % TOTAL_PROP;
@@ -120,13 +120,13 @@ struct Cols {
   u64 *b_auction, *b_bidder, *b_price, *b_dt, *b_extra;
 };
 
-void gen_range(u64 seed, u64 first, u64 lo, u64 hi, const Cols& c) {
+void gen_range(u64 seed, double delay_us, u64 first, u64 lo, u64 hi, const Cols& c) {
   const Dict& d = dict();
   u64 p0 = persons_before(first), a0 = auctions_before(first), b0 = bids_before(first);
   for (u64 e = lo; e < hi; e++) {
     Rng r(seed, e);
     u64 rem = e % TOTAL_PROP;
-    u64 ts = timestamp_for_event(e);
+    u64 ts = timestamp_for_event(delay_us, e);
     if (rem < PERSON_PROP) {   // people.rs:50-86
       u64 i = persons_before(e) - p0;
       if (c.p_id) c.p_id[i] = last_base0_person_id(e) + FIRST_PERSON_ID;
@@ -146,7 +146,7 @@ void gen_range(u64 seed, u64 first, u64 lo, u64 hi, const Cols& c) {
       if (c.a_dt) c.a_dt[i] = ts;
       // auctions.rs:124-143 next_auction_length_ms
       u64 num_events_for_auctions = (NUM_IN_FLIGHT_AUCTIONS * TOTAL_PROP) / AUCTION_PROP;
-      u64 future = timestamp_for_event(e + num_events_for_auctions);
+      u64 future = timestamp_for_event(delay_us, e + num_events_for_auctions);
       u64 horizon = future > ts ? future - ts : 0;
       u64 len = 1 + r.range(std::max<u64>(horizon * 2, 1));
       if (c.a_expires) c.a_expires[i] = ts + len;
@@ -181,11 +181,13 @@ void nexmark_counts(u64 first, u64 n, u64* np, u64* na, u64* nb) {
   *nb = bids_before(first + n) - bids_before(first);
 }
 
-// Fill the requested columns (NULL = skip) for events [first, first+n).
-void nexmark_generate(u64 seed, u64 first, u64 n, int nthreads, u64* p_id, u64* p_name, u64* p_city, u64* p_state,
-                      u64* p_dt, u64* a_id, u64* a_seller, u64* a_category, u64* a_dt, u64* a_expires, u64* b_auction,
-                      u64* b_bidder, u64* b_price, u64* b_dt, u64* b_extra) {
+// Fill the requested columns (NULL = skip) for events [first, first+n).  `rate` = first_event_rate in
+// events/s (generator/config.rs:62: inter_event_delay_us = 1e6 / rate); 0 = the reference default.
+void nexmark_generate_rate(u64 seed, u64 rate, u64 first, u64 n, int nthreads, u64* p_id, u64* p_name, u64* p_city,
+                           u64* p_state, u64* p_dt, u64* a_id, u64* a_seller, u64* a_category, u64* a_dt, u64* a_expires,
+                           u64* b_auction, u64* b_bidder, u64* b_price, u64* b_dt, u64* b_extra) {
   Cols c{p_id, p_name, p_city, p_state, p_dt, a_id, a_seller, a_category, a_dt, a_expires, b_auction, b_bidder, b_price, b_dt, b_extra};
+  const double delay_us = 1000000.0 / (double)(rate ? rate : DEFAULT_FIRST_EVENT_RATE);
   if (nthreads < 1) nthreads = 1;
   if (n < 100000) nthreads = 1;
   std::vector<std::thread> th;
@@ -193,9 +195,15 @@ void nexmark_generate(u64 seed, u64 first, u64 n, int nthreads, u64* p_id, u64* 
   for (int t = 0; t < nthreads; t++) {
     u64 lo = first + std::min<u64>(n, t * chunk), hi = first + std::min<u64>(n, (t + 1) * chunk);
     if (lo >= hi) continue;
-    th.emplace_back([=] { gen_range(seed, first, lo, hi, c); });
+    th.emplace_back([=] { gen_range(seed, delay_us, first, lo, hi, c); });
   }
   for (auto& t : th) t.join();
+}
+void nexmark_generate(u64 seed, u64 first, u64 n, int nthreads, u64* p_id, u64* p_name, u64* p_city, u64* p_state,
+                      u64* p_dt, u64* a_id, u64* a_seller, u64* a_category, u64* a_dt, u64* a_expires, u64* b_auction,
+                      u64* b_bidder, u64* b_price, u64* b_dt, u64* b_extra) {
+  nexmark_generate_rate(seed, 0, first, n, nthreads, p_id, p_name, p_city, p_state, p_dt, a_id, a_seller, a_category, a_dt,
+                        a_expires, b_auction, b_bidder, b_price, b_dt, b_extra);
 }
 
 u64 nexmark_base_time(void) { return BASE_TIME; }

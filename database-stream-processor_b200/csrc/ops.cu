@@ -118,13 +118,14 @@ __global__ void k_project_rows(Cols in, int nk_in, int n_in_lanes, unsigned used
 // `seek_key` of cursor/mod.rs + advance.rs:25-72).  One search per key instead of
 // one per row; all spine batches in one launch.
 __global__ void k_probe_keys(Cols D, const u64* kstart, u64 nkeys, BatchRefs tr, int nk, Flips f, u32* lo_out,
-                             u32* cnt_out, u32* ktot) {
+                             u32* cnt_out, u32* ktot, unsigned long long* tot64) {
   u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0) *tot64 = 0;   // accumulated by k_row_counts (next kernel on the stream)
   if (k >= nkeys) return;
   const u64 row = kstart[k];
   u64 q[MAXL];
   for (int l = 0; l < nk; l++) q[l] = D.c[l][row] ^ f.f[l];
-  u32 tot = 0;
+  u64 tot = 0;
   for (int b = 0; b < tr.nb; b++) {
     const Cols& T = tr.b[b].c;
     const u64 nt = tr.b[b].n;
@@ -135,19 +136,27 @@ __global__ void k_probe_keys(Cols D, const u64* kstart, u64 nkeys, BatchRefs tr,
     hi = upper_bound_q(T, hi, top, q, nk, f);
     lo_out[k * tr.nb + b] = (u32)lo;
     cnt_out[k * tr.nb + b] = (u32)(hi - lo);
-    tot += (u32)(hi - lo);
+    tot += hi - lo;
   }
-  ktot[k] = tot;
+  ktot[k] = tot > 0xffffffffull ? 0xffffffffu : (u32)tot;   // saturate: the 64-bit total below then trips the guard
 }
 
 // matches of every delta row = matches of its key; also the row -> key index
-__global__ void k_row_counts(const u32* head_exscan, const u32* ktot, u64 nd, u32* rowcnt, u32* ki) {
+__global__ void k_row_counts(const u32* head_exscan, const u32* ktot, u64 nd, u32* rowcnt, u32* ki,
+                             unsigned long long* tot64) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > nd) return;
-  if (i == nd) { rowcnt[nd] = 0; return; }
-  u32 k = head_exscan[i + 1] - 1;   // inclusive head count - 1
-  ki[i] = k;
-  rowcnt[i] = ktot[k];
+  unsigned long long c = 0;
+  if (i == nd) rowcnt[nd] = 0;
+  if (i < nd) {
+    u32 k = head_exscan[i + 1] - 1;   // inclusive head count - 1
+    ki[i] = k;
+    c = ktot[k];
+    rowcnt[i] = (u32)c;
+  }
+  // 64-bit total of the matches: the 32-bit scan below wraps silently on a skewed join, this does not
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(tot64, c);
 }
 
 // Expand the matches: output slot o -> (delta row i, batch b, trace row).  Slots
@@ -470,6 +479,14 @@ __global__ void k_shard_scatter(Cols in, int L, const i64* w, const u32* flags, 
 }
 
 inline unsigned blocks(u64 n) { return (unsigned)((n + TB - 1) / TB); }
+// Row indices, offsets and scans of the operator kernels are 32-bit: reject (never wrap) anything larger.
+#define ROWS32(n, what)                                                                        \
+  do {                                                                                         \
+    if ((u64)(n) >= 0xffffffffull) {                                                           \
+      set_error(std::string(what) + ": 2^32-1 or more rows in one batch; split the batch");   \
+      return DBSP_ERR_UNSUPPORTED;                                                             \
+    }                                                                                          \
+  } while (0)
 #define CHECK_P(c, msg)                                   \
   do {                                                    \
     if (!(c)) { set_error(msg); return DBSP_ERR_INVALID; } \
@@ -502,6 +519,7 @@ static int32_t tmp_alloc(Ctx* ctx, int L, u64 cap, TmpRows* t) {
 
 int32_t compact_ordered(Ctx* ctx, const dbsp_schema& s, const Cols& in, const i64* w, const u32* keep, u64 n, Batch** out) {
   // keep has n+1 entries (keep[n] == 0)
+  ROWS32(n, "compact");
   int L = s.n_key_lanes + s.n_val_lanes;
   BufP pbuf;
   TRY(dev_alloc(ctx, (size_t)(n + 1) * 4, &pbuf));
@@ -529,6 +547,7 @@ int32_t op_truncate_values(Ctx* ctx, const Batch* b, const u64* val_bound, Batch
   RowBound rb;
   for (int l = 0; l < nv; l++) rb.v[l] = val_bound[l] ^ f.f[nk + l];
   u64 n = b->n;
+  ROWS32(n, "truncate_values");
   BufP kb;
   TRY(dev_alloc(ctx, (size_t)(n + 1) * 4 * 2, &kb));
   u32* keep = (u32*)kb->p;
@@ -624,6 +643,7 @@ int32_t project_and_consolidate(Ctx* ctx, const Cols& in, int nk_in, int n_in_la
   const dbsp_schema& os = proj.out_schema;
   int Lo = os.n_key_lanes + os.n_val_lanes;
   if (n == 0) { *out = batch_new_empty(ctx, os); return DBSP_OK; }
+  ROWS32(n, "map_index / flat_map_index");
   unsigned g = (unsigned)((n + PROJ_ROWS - 1) / PROJ_ROWS);
   const unsigned umask = proj_used_mask(proj, nk_in);
   BufP cb;
@@ -665,6 +685,7 @@ int32_t project_and_consolidate(Ctx* ctx, const Cols& in, int nk_in, int n_in_la
 // key segment starts of the first nk lanes: kstart[nkeys+1] (u64 row indices),
 // plus the exclusive scan of the head flags (u32[n+1]) used for row -> key.
 static int32_t key_segments(Ctx* ctx, const Batch* b, int nk, BufP* kstart, BufP* head_ex, u64* nkeys) {
+  ROWS32(b->n, "key_segments");
   BufP fb;
   TRY(dev_alloc(ctx, (size_t)(b->n + 1) * 4, &fb));
   TRY(dev_alloc(ctx, (size_t)(b->n + 1) * 4, head_ex));
@@ -693,6 +714,8 @@ static int32_t probe_chunk(Ctx* ctx, const Batch* delta, int nk, Batch* const* t
   BatchRefs refs;
   refs.nb = nb;
   u64 trace_rows = 0;
+  ROWS32(nd, "join/gather delta");
+  for (int b = 0; b < nb; b++) ROWS32(tb[b]->n, "join/gather trace batch");
   for (int b = 0; b < nb; b++) {
     refs.b[b].c = tb[b]->cols();
     refs.b[b].w = tb[b]->w;
@@ -708,19 +731,24 @@ static int32_t probe_chunk(Ctx* ctx, const Batch* delta, int nk, Batch* const* t
   u32* rowcnt = (u32*)rb->p;
   u32* ex = rowcnt + (nd + 1);
   u32* ki = ex + (nd + 1);
+  unsigned long long* tot64 = (unsigned long long*)(ctx->d_scratch + 24);
   {
     // delta keys read once, ranges written once; every bisection step touches one
     // trace key row (bounded by the trace's key bytes)
     u64 lg = 1; while ((1ull << lg) < trace_rows / std::max(nb, 1) + 1) lg++;
     u64 touched = std::min<u64>(nkeys * (u64)nb * 2 * lg, trace_rows) * (u64)std::max(nk, 1) * 8;
     ProfScope ps(ctx, KID_PROBE_RANGES, nkeys * ((u64)nk * 8 + (u64)nb * 8 + 4) + touched);
-    k_probe_keys<<<blocks(nkeys), TB, 0, st>>>(delta->cols(), kstart, nkeys, refs, nk, f, lo, cnt, ktot);
+    k_probe_keys<<<blocks(nkeys), TB, 0, st>>>(delta->cols(), kstart, nkeys, refs, nk, f, lo, cnt, ktot, tot64);
   }
-  k_row_counts<<<blocks(nd + 1), TB, 0, st>>>(head_ex, ktot, nd, rowcnt, ki);
+  k_row_counts<<<blocks(nd + 1), TB, 0, st>>>(head_ex, ktot, nd, rowcnt, ki, tot64);
   ctx->kernel_launches += 2;
   TRY(exclusive_scan_u32(ctx, rowcnt, ex, nd));
-  u32 total;
-  TRY(read_back32(ctx, ex + nd, &total));
+  u64 total;
+  TRY(read_back(ctx, tot64, 1, &total));
+  if (total >= 0xffffffffull) {
+    set_error("join/gather: 2^32-1 or more matches in one step (" + std::to_string(total) + "); feed the delta in smaller batches");
+    return DBSP_ERR_UNSUPPORTED;
+  }
   if (total == 0) { *out = batch_new_empty(ctx, out_schema); return DBSP_OK; }
   int Lo = out_schema.n_key_lanes + out_schema.n_val_lanes;
   dbsp_proj pj;
@@ -926,6 +954,7 @@ int32_t op_weigh(Ctx* ctx, const Batch* b, const dbsp_expr* f, int mode, Batch**
   for (int l = 0; l < nk; l++) os.lane_types[l] = b->s.lane_types[l];
   if (b->n == 0) { *out = batch_new_empty(ctx, os); return DBSP_OK; }
   u64 m = b->n * (mode == DBSP_WEIGH_AVG ? 2 : 1);
+  ROWS32(m, "weigh");
   TmpRows t;
   TRY(tmp_alloc(ctx, os.n_key_lanes, m, &t));
   k_weigh<<<blocks(b->n), TB, 0, ctx->stream>>>(b->cols(), b->w, b->n, nk, nv, *f, mode, t.c, t.w);
@@ -968,14 +997,18 @@ int32_t op_stream_distinct(Ctx* ctx, const Batch* b, Batch** out) {
 // SemiJoinStream::eval (operator/semijoin.rs:100-142)
 int32_t op_semijoin(Ctx* ctx, const Batch* pairs, const Batch* keys, Batch** out) {
   u64 n = pairs->n;
-  if (n == 0 || keys->n == 0) { *out = batch_new_empty(ctx, pairs->s); return DBSP_OK; }
+  // Out: ZSet<Key = (Pairs::Key, Pairs::Val)> (semijoin.rs:47): same flat rows, every lane a key lane
+  dbsp_schema os = pairs->s;
+  os.n_key_lanes = (uint8_t)pairs->nl();
+  os.n_val_lanes = 0;
+  if (n == 0 || keys->n == 0) { *out = batch_new_empty(ctx, os); return DBSP_OK; }
   BufP ab, kb;
   TRY(dev_alloc(ctx, (size_t)n * 8, &ab));
   TRY(dev_alloc(ctx, (size_t)(n + 1) * 4, &kb));
   k_semijoin<<<blocks(n + 1), TB, 0, ctx->stream>>>(pairs->cols(), pairs->w, n, keys->cols(), keys->w, keys->n,
                                                    pairs->s.n_key_lanes, pairs->flips(), (u32*)kb->p, (i64*)ab->p);
   LAUNCH_COUNT(ctx);
-  return compact_ordered(ctx, pairs->s, pairs->cols(), (i64*)ab->p, (u32*)kb->p, n, out);
+  return compact_ordered(ctx, os, pairs->cols(), (i64*)ab->p, (u32*)kb->p, n, out);
 }
 
 // Balanced merge of consolidated batches; consumes one reference of each part.
@@ -1090,6 +1123,7 @@ int32_t op_shard_partition(Ctx* ctx, const Batch* b, u32 P, Batch** outs) {
   const u64 n = b->n;
   const int L = b->nl();
   CHECK_P(P <= 64, "shard_partition: at most 64 shards");
+  ROWS32((n + 1) * (u64)P, "shard_partition");
   BufP fb;
   const u64 m = (u64)P * (n + 1);
   TRY(dev_alloc(ctx, (size_t)(m + 1) * 4 * 2, &fb));
@@ -1129,6 +1163,7 @@ int32_t op_shard_partition(Ctx* ctx, const Batch* b, u32 P, Batch** outs) {
 int32_t batch_build_csr(Ctx* ctx, Batch* b) {
   if (b->nkeys != ~0ull) return DBSP_OK;
   if (b->n == 0) { b->nkeys = 0; return DBSP_OK; }
+  ROWS32(b->n, "key_count / download_csr");
   int nk = b->s.n_key_lanes;
   BufP fb, pb;
   TRY(dev_alloc(ctx, (size_t)(b->n + 1) * 4 * 2, &fb));

@@ -48,6 +48,8 @@ def _load():
         _lib.nexmark_counts.restype = None
         _lib.nexmark_generate.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int] + [C.c_void_p] * 15
         _lib.nexmark_generate.restype = None
+        _lib.nexmark_generate_rate.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int] + [C.c_void_p] * 15
+        _lib.nexmark_generate_rate.restype = None
     return _lib
 
 
@@ -55,8 +57,11 @@ class NexmarkGenerator:
     """Seeded generator; `tables(first, n)` returns dict(person=[cols..],
     auction=[cols..], bid=[cols..]) as uint64 numpy columns."""
 
-    def __init__(self, seed: int = 0x7FC359184519C0AA, threads: int | None = None):
+    def __init__(self, seed: int = 0x7FC359184519C0AA, threads: int | None = None, first_event_rate: int = 0):
+        """first_event_rate: NexmarkConfig::first_event_rate in events/s (crates/nexmark/src/config.rs:51); 0 = the
+        reference default of 10 M/s, i.e. 10 000 events per millisecond of event time."""
         self.seed = seed
+        self.rate = int(first_event_rate)
         self.threads = threads or min(os.cpu_count() or 1, 32)
         self.lib = _load()
 
@@ -77,5 +82,5 @@ class NexmarkGenerator:
         for t, ncol in (("person", 5), ("auction", 5), ("bid", 5)):
             cols = out[t]
             ptrs += [c.ctypes.data for c in cols] if cols is not None else [None] * ncol
-        self.lib.nexmark_generate(self.seed, first, n, self.threads, *ptrs)
+        self.lib.nexmark_generate_rate(self.seed, self.rate, first, n, self.threads, *ptrs)
         return out

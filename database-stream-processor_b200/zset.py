@@ -606,7 +606,7 @@ class Backend:
     def semijoin(self, pairs: Batch, keys: Batch) -> Batch:
         out = self._out()
         self.api.call("semijoin", self.ctx, pairs.h, keys.h, C.byref(out))
-        return Batch(self, out.value, pairs.schema)
+        return Batch(self, out.value, Schema(pairs.schema.lanes))   # OrdZSet<(K, V)> (semijoin.rs:47)
 
     def aggregate_delta(self, delta: Batch, in_trace: Spine, out_trace: Spine, kind: int) -> Batch:
         out = self._out()

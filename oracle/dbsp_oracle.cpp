@@ -787,7 +787,12 @@ int32_t orc_join_batches(orc_ctx*, const orc_batch* l, const orc_batch* r, const
 int32_t orc_semijoin(orc_ctx*, const orc_batch* pairs, const orc_batch* keys, orc_batch** out) {
   const Batch& P = *pairs->p;
   const Batch& Kb = *keys->p;
-  Builder bld(P.s);
+  // Out: ZSet<Key = (Pairs::Key, Pairs::Val)> (semijoin.rs:47): an OrdZSet over all lanes
+  dbsp_schema os = P.s;
+  os.n_key_lanes = (uint8_t)(P.s.n_key_lanes + P.s.n_val_lanes);
+  os.n_val_lanes = 0;
+  const int pnk = P.s.n_key_lanes, pnv = P.s.n_val_lanes;
+  Builder bld(os);
   size_t i = 0, j = 0;
   u64 key[MAXL], val[MAXL];
   while (i < P.K.n && j < Kb.K.n) {
@@ -799,7 +804,7 @@ int32_t orc_semijoin(orc_ctx*, const orc_batch* pairs, const orc_batch* keys, or
       size_t lo, hi;
       P.vrange(i, lo, hi);
       for (size_t v = lo; v < hi; v++) {
-        if (P.indexed()) P.V.get(v, val);
+        if (P.indexed()) { P.V.get(v, val); for (int l = 0; l < pnv; l++) key[pnk + l] = val[l]; }
         i64 w = (i64)((u64)P.w[v] * (u64)Kb.w[j]);
         if (w != 0) bld.push(key, val, w);
       }

@@ -32,10 +32,12 @@ def feed(handles, tables):
         handles[k].set(tables[k])
 
 
-def run_nexmark_pair(be_a, be_b, query, n_events, step, seed=0x7FC359184519C0AA, first=0):
+def run_nexmark_pair(be_a, be_b, query, n_events, step, seed=0x7FC359184519C0AA, first=0, rate=0):
     """Run `query` on two backends over the same seeded events; every step's
-    output Z-set must be identical.  Returns the number of output tuples."""
-    gen = NexmarkGenerator(seed)
+    output Z-set must be identical.  Returns the number of output tuples.
+    `rate` = first_event_rate (0 = the reference default, 10 k events per ms of event time: q7's 10 s
+    windows then need > 100 M events to close; tests pass a lower rate so that windows open and close)."""
+    gen = NexmarkGenerator(seed, first_event_rate=rate)
     ca, ha, oa = build_query(be_a, query)
     cb, hb, ob = build_query(be_b, query)
     total = 0
