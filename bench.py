@@ -1,33 +1,33 @@
 #!/usr/bin/env python
 """bench.py — Nexmark events/s through the B200 Z-set hot path.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--query q3|q4|q7]
 
-A *step* is one `Circuit::step()` of the query over one batch of synthetic
-Nexmark events (E events per rank per step).  The primary workload at N=1 is
-BASELINE.json configs[1]: Nexmark q3 (person |x| auction incremental join),
-100 M events (E = 5 M, W+K = 20 steps).  q4 and q7 ride along in `queries`
-(same metric, same harness) unless --query pins one.
+Workload.  A *circuit step* is one `Circuit::step()` of the query over E = 5 M synthetic Nexmark events per
+GPU.  A *bench step* (what --steps / --warmup count) is S consecutive circuit steps (S per query below), so that
+the timed region of the driver's `--steps 20` is hundreds of circuit steps instead of 20 sub-millisecond ones.
+The primary line at N=1 is BASELINE.json configs[1]: Nexmark q3 (person |x| auction incremental join); q4, q7 and
+the config[4] merge sweep ride along under `queries` / `merge_sweep` unless --query pins one query.
 
-`value`   : events/s with the step's input columns already resident in HBM.
-`e2e`     : the same steps through the C ABI with HOST (pinned) columns — H2D
-            copies of every step's inputs and a D2H download of the step's
-            output Z-set are inside the timed region.
-`roofline`: the step's dominant kernel class, algorithmic bytes / device time
-            from CUDA events the library records on its own stream
-            (dbsp_ctx_profile), against MEASURED_PEAKS.json.
-`--impl reference`: the CPU oracle (C++ restatement of the reference's
-            algorithms; the Rust reference cannot be built here) on all host
-            threads, N worker replicas with the reference's hash-shard/exchange
-            scheme, on a bounded sample of the same workload.
+`value`    : events/s, the step's input columns already resident in HBM (device-timed, CUDA events on the library's
+             stream, max over ranks).  `rows_per_s` next to it counts only the table rows the query ingests (q3 reads
+             the 8 % of events that are persons/auctions).
+`e2e`      : the same steps through the C ABI with HOST (pinned) columns: the H2D copy of every step's inputs and
+             the D2H download of every step's output Z-set are inside the timed region.
+`roofline` : the dominant kernel class of the timed region: algorithmic bytes / device time from CUDA events the
+             library records on its own stream (dbsp_ctx_profile), against MEASURED_PEAKS.json; `traffic` from the
+             committed ncu --set full capture of that kernel (profiles/r2_ncu_traffic.json), scaled by bytes.
+`--impl reference` / `cpu_baseline`: the CPU arm = oracle/nexmark_workers.cpp — the C++ restatement of the
+             reference's algorithms run as N worker threads with hash-shard + in-process exchange and no interpreter
+             between steps (the Rust reference cannot be built here: no rustc), rebuilt with -march=native on the box
+             it is timed on.  `--impl reference` runs the SAME circuit steps as the GPU arm (same E, same S, same
+             K and W); the in-line `cpu_baseline` of a default run is a bounded sample (fewer steps, stated).
 """
 from __future__ import annotations
 
 import argparse
-import ctypes
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -39,13 +39,20 @@ sys.path.insert(0, ROOT)
 
 METRIC = "nexmark_events_per_sec"
 UNIT = "events/s"
-QUERY_COLS = {   # columns each query actually reads (the others are not generated / copied)
+QUERY_COLS = {   # tables each query reads (the others are not generated / copied)
     "q3": ("person", "auction"),
     "q4": ("auction", "bid"),
     "q7": ("bid",),
     "q0": ("bid",),
 }
-FULL_EVENTS = {"q3": 100_000_000, "q4": 100_000_000, "q7": 1_000_000_000, "q0": 1_000_000}
+FULL_EVENTS = {"q3": 100_000_000, "q4": 100_000_000, "q7": 1_000_000_000}
+# circuit steps per bench step
+CIRCUIT_STEPS = {"q3": 8, "q4": 2, "q7": 2}
+# NexmarkConfig::first_event_rate (crates/nexmark/src/config.rs:51,134).  q3/q4 never look at event time.  q7's 10 s
+# tumbling windows (q7.rs:43) hold 100 M events at the reference default of 10 M events/s: none would close before
+# event 140 M.  At 1 M events/s a window closes every second circuit step, so the run does the same work per event
+# as configs[3] (1 B events at the default rate: every bid enters one window and leaves it once), ten windows deep.
+EVENT_RATE = {"q3": 0, "q4": 0, "q7": 1_000_000}
 
 
 def peaks():
@@ -114,13 +121,13 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def gen_steps(query, rank, world, n_steps, events_per_step, pinned):
-    """Host column tables of n_steps steps for this rank.  Rank r's step s is
-    the contiguous event range [(s*world + r) * E, +E) (round-robin input
-    distribution at batch granularity, operator/input.rs:664-703)."""
+def gen_steps(query, rank, world, n_steps, events_per_step, pinned, rate=None):
+    """Host column tables of n_steps circuit steps for this rank.  Rank r's step s is the contiguous event range
+    [(s*world + r) * E, +E) (round-robin input distribution at batch granularity, operator/input.rs:664-703)."""
     from dbsp_b200.nexmark import NexmarkGenerator
 
-    gen = NexmarkGenerator(threads=max(1, (os.cpu_count() or 8) // max(world, 1)))
+    gen = NexmarkGenerator(threads=max(1, (os.cpu_count() or 8) // max(world, 1)),
+                           first_event_rate=EVENT_RATE[query] if rate is None else rate)
     want = QUERY_COLS[query]
     if pinned:
         import torch
@@ -129,21 +136,34 @@ def gen_steps(query, rank, world, n_steps, events_per_step, pinned):
             return torch.empty(k, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
     else:
         alloc = None
-    steps = []
-    for s in range(n_steps):
-        first = (s * world + rank) * events_per_step
-        t = gen.tables(first, events_per_step, want=want, alloc=alloc)
-        steps.append(t)
-    return steps
+    return [gen.tables((s * world + rank) * events_per_step, events_per_step, want=want, alloc=alloc) for s in range(n_steps)]
+
+
+def rows_in(steps, lo, hi):
+    return sum(len(t[k][0]) for t in steps[lo:hi] for k in t if t[k] is not None)
 
 
 def empty_cols():
     return [np.empty(0, np.uint64) for _ in range(5)]
 
 
-def feed_host(handles, t):
-    for k in ("person", "auction", "bid"):
-        handles[k].set(t[k] if t[k] is not None else empty_cols())
+def make_comm(device, be=None):
+    from dbsp_b200.parallel import Comm
+
+    return Comm(device)
+
+
+def workload_cfg(query, E, S, W, K, world):
+    total = world * E * S * (W + K)
+    cfg = {"workload": f"Nexmark {query}: {E} events per circuit step per GPU, {S} circuit steps per bench step, "
+                       f"{K} timed + {W} warm-up bench steps = {total} events over {world} GPU(s); "
+                       f"BASELINE configs full size {FULL_EVENTS.get(query)}",
+           "query": query, "events_per_circuit_step_per_gpu": E, "circuit_steps_per_bench_step": S,
+           "timed_circuit_steps": K * S, "total_events": total,
+           "first_event_rate": EVENT_RATE[query] or 10_000_000,
+           "l2": "inputs larger than L2 (every circuit step streams fresh event columns); traces grow past L2",
+           "parallelism": f"key-hash shard x{world}" if world > 1 else "single GPU"}
+    return cfg
 
 
 def run_b200(args, query, rank, world, comm, device, do_e2e=True):
@@ -154,9 +174,10 @@ def run_b200(args, query, rank, world, comm, device, do_e2e=True):
     from dbsp_b200.nexmark import queries as nq
     from dbsp_b200.runtime import Runtime
 
-    E, W, K = args.events_per_step, args.warmup, args.steps
+    E, S = args.events_per_step, args.circuit_steps or CIRCUIT_STEPS[query]
+    W, K = args.warmup * S, args.steps * S          # in circuit steps
     steps = gen_steps(query, rank, world, W + K, E, pinned=True)
-    res = {}
+    res = {"circuit_steps_per_bench_step": S}
 
     def build(be):
         c = dbsp_b200.RootCircuit(be, comm)
@@ -181,6 +202,8 @@ def run_b200(args, query, rank, world, comm, device, do_e2e=True):
     # ---- (1) device-resident inputs -------------------------------------------
     os.environ.setdefault("DBSP_POOL_RESERVE_GB", "24")   # pool growth (cudaMalloc of slabs) stays out of the timed region
     be = Runtime(device.index)
+    if comm is not None and hasattr(comm, "attach"):
+        comm.attach(be)
     ext = torch.cuda.ExternalStream(be.stream_ptr, device=device)
     dev_steps = []
     for t in steps:
@@ -204,37 +227,41 @@ def run_b200(args, query, rank, world, comm, device, do_e2e=True):
     sync_all(be)
     be.stats(reset=True)
     be.profile(True)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     with ClockSampler(device.index) as clk:
         t0 = time.perf_counter()
-        ev0.record(ext)
+        evs[0].record(ext)
         for s in range(W, W + K):
             feed_dev(dev_steps[s])
             c.step()
-        ev1.record(ext)
+            evs[s - W + 1].record(ext)
         sync_all(be)
         wall = time.perf_counter() - t0
-    dev_ms = ev0.elapsed_time(ev1)
+    dev_ms = evs[0].elapsed_time(evs[K])
+    per_step = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(K))
     ms = max_over_ranks(dev_ms)
     st = be.stats()
     prof = be.profile_read()
     be.profile(False)
     out_rows = len(out.value)
-    res.update(value=world * E * K / (ms / 1e3), ms_per_step=ms / K, wall_ms_per_step=wall * 1e3 / K,
+    in_rows = rows_in(steps, W, W + K)
+    res.update(value=world * E * K / (ms / 1e3), rows_per_s=world * in_rows / (ms / 1e3), ms_per_step=ms / args.steps,
+               ms_per_circuit_step=ms / K, wall_ms_per_circuit_step=wall * 1e3 / K,
+               circuit_step_ms_p50=per_step[K // 2], circuit_step_ms_p99=per_step[min(K - 1, int(K * 0.99))],
+               circuit_step_ms_max=per_step[-1], timed_region_ms=ms,
                gpu_launches=st["kernel_launches"], profile=prof, clocks=clk.summary(), last_step_out_rows=out_rows)
     del c, handles, out, dev_steps
     be.sync()
 
     # ---- (2) end to end: host columns in, output Z-set out -----------------------------
     if do_e2e:
-        be2, ext2 = be, ext   # same context / stream / memory pool, fresh circuit state
-        c, handles, out = build(be2)
+        c, handles, out = build(be)
         tabs = {"person": build.tables.person, "auction": build.tables.auction, "bid": build.tables.bid}
         masks = {k: tabs[k].table_mask() for k in tabs}
 
         def start_uploads(t):
             """H2D of one step's tables on the copy stream (only the columns the query reads)."""
-            return {k: (be2.upload_begin(t[k], masks[k]) if (t[k] is not None and masks[k]) else None) for k in tabs}
+            return {k: (be.upload_begin(t[k], masks[k]) if (t[k] is not None and masks[k]) else None) for k in tabs}
 
         def feed_uploads(ups):
             for k in tabs:
@@ -247,11 +274,11 @@ def run_b200(args, query, rank, world, comm, device, do_e2e=True):
             feed_uploads(start_uploads(steps[s]))
             c.step()
             out.value.download()
-        sync_all(be2)
-        be2.stats(reset=True)
+        sync_all(be)
+        be.stats(reset=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
-        e0.record(ext2)
+        e0.record(ext)
         nxt = start_uploads(steps[W])             # every step's H2D copy is inside the timed region ...
         for s in range(W, W + K):
             cur = nxt
@@ -259,27 +286,103 @@ def run_b200(args, query, rank, world, comm, device, do_e2e=True):
             feed_uploads(cur)
             c.step()
             out.value.download()                  # D2H of the step's result Z-set
-        e1.record(ext2)
-        sync_all(be2)
+        e1.record(ext)
+        sync_all(be)
         wall2 = time.perf_counter() - t0
         ms2 = max_over_ranks(max(e0.elapsed_time(e1), wall2 * 1e3))   # host copies are part of the path: take the larger clock
-        st2 = be2.stats()
-        res["e2e"] = {"value": world * E * K / (ms2 / 1e3), "unit": UNIT, "h2d_bytes_per_step": st2["h2d_bytes"] // K,
-                      "d2h_bytes_per_step": st2["d2h_bytes"] // K, "ms_per_step": ms2 / K}
+        st2 = be.stats()
+        res["e2e"] = {"value": world * E * K / (ms2 / 1e3), "unit": UNIT, "h2d_bytes_per_step": st2["h2d_bytes"] // args.steps,
+                      "d2h_bytes_per_step": st2["d2h_bytes"] // args.steps, "ms_per_step": ms2 / args.steps,
+                      "ms_per_circuit_step": ms2 / K}
         del c, handles, out
     be.sync()
     import gc
 
+    if comm is not None and hasattr(comm, "detach"):
+        comm.detach()
     gc.collect()
     be.close()
     return res
 
 
+def parity_check(rank, world, comm, device, queries=("q3", "q4", "q7"), events=100_000, n_steps=5):
+    """N > 1 only, outside every timed region: the sharded circuit's output, gathered to rank 0, must equal —
+    bit for bit, every step — the output of a single-GPU circuit fed the union of all ranks' inputs.  The driver's
+    1-GPU test box cannot run tests/test_multigpu.py, so the multi-GPU CUDA path is verified here."""
+    import torch
+
+    import dbsp_b200
+    from dbsp_b200.nexmark import queries as nq
+    from dbsp_b200.runtime import Runtime
+
+    be = Runtime(device.index)
+    if hasattr(comm, "attach"):
+        comm.attach(be)
+    report = {"steps": n_steps, "events_per_step_per_gpu": events, "queries": {}}
+    ok_all = True
+    try:
+        for q in queries:
+            rate = 100_000 if q == "q7" else 0            # q7: a 10 s window = 1 M events, closes every few steps
+            mine = gen_steps(q, rank, world, n_steps, events, pinned=False, rate=rate)
+            c = dbsp_b200.RootCircuit(be, comm)
+            inp, handles = nq.add_nexmark_input(c)
+            out = nq.QUERIES[q](inp).gather(0).output()
+            if rank == 0:
+                c1 = dbsp_b200.RootCircuit(be, None)
+                inp1, handles1 = nq.add_nexmark_input(c1)
+                out1 = nq.QUERIES[q](inp1).output()
+                union = gen_steps(q, 0, 1, n_steps, events * world, pinned=False, rate=rate)
+            ok, rows = True, 0
+            for s in range(n_steps):
+                for k in ("person", "auction", "bid"):
+                    handles[k].set(mine[s][k] if mine[s][k] is not None else empty_cols())
+                c.step()
+                if rank == 0:
+                    for k in ("person", "auction", "bid"):
+                        handles1[k].set(union[s][k] if union[s][k] is not None else empty_cols())
+                    c1.step()
+                    a, b = out.value.download(), out1.value.download()
+                    same = len(a["diffs"]) == len(b["diffs"]) and np.array_equal(a["diffs"], b["diffs"])
+                    same = same and all(np.array_equal(x, y) for x, y in zip(a["keys"], b["keys"]))
+                    same = same and all(np.array_equal(x, y) for x, y in zip(a["vals"], b["vals"]))
+                    if a["offs"] is not None:
+                        same = same and np.array_equal(a["offs"], b["offs"])
+                    ok = ok and bool(same)
+                    rows += len(b["diffs"])
+            t = torch.tensor([1 if ok else 0, rows], dtype=torch.int64, device=device)
+            torch.distributed.broadcast(t, 0)
+            ok, rows = bool(t[0].item()), int(t[1].item())
+            report["queries"][q] = {"equal_every_step": ok, "output_rows_compared": rows}
+            ok_all = ok_all and ok and (rows > 0)
+            del c, handles, out
+            if rank == 0:
+                del c1, handles1, out1
+    finally:
+        be.sync()
+        if hasattr(comm, "detach"):
+            comm.detach()
+        import gc
+
+        gc.collect()
+        be.close()
+    report["ok"] = ok_all
+    return report
+
+
 ROOFLINE_NOTES = {
-    "q3": "q3 reads only Person/Auction events (8% of the stream): a 5M-event step is ~60k-row batches, so every kernel "
-          "is launch-latency bound and the dominant class (radix passes on 60k rows) sits far below the HBM roofline; "
-          "see queries.q4.roofline and merge_sweep.roofline for the bandwidth-bound kernels",
+    "q3": "q3 reads only Person/Auction events (8% of the stream): a 5M-event circuit step is ~60k-row batches, so its "
+          "kernels are launch-latency bound and sit far below the HBM roofline; see queries.q4.roofline, "
+          "queries.q7.roofline and merge_sweep[*].roofline for the bandwidth-bound kernels",
 }
+
+
+def ncu_traffic(kernel, alg_bytes_per_launch):
+    """dram bytes per launch of `kernel` from the committed ncu --set full capture, scaled by algorithmic bytes."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))[kernel]
+        return t["dram_bytes"] * alg_bytes_per_launch / t["alg_bytes"], t["source"]
+    except Exception:
+        return None, None
 
 
 def roofline_from_profile(prof, query=None):
@@ -290,15 +393,24 @@ def roofline_from_profile(prof, query=None):
     p = prof[name]
     total_ms = sum(v["ms"] for v in prof.values())
     achieved = p["alg_bytes"] / (p["ms"] / 1e3) / 1e9 if p["ms"] > 0 else 0.0
+    traffic, src = ncu_traffic(name, p["alg_bytes"] / p["launches"])
     return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "launches": p["launches"], "avg_launch_us": 1e3 * p["ms"] / p["launches"],
+            "traffic": traffic, "traffic_source": src, "launches": p["launches"], "avg_launch_us": 1e3 * p["ms"] / p["launches"],
             "alg_bytes_per_launch": p["alg_bytes"] / p["launches"], "share_of_kernel_time": p["ms"] / total_ms if total_ms else None,
             "peak_source": how, **({"note": ROOFLINE_NOTES[query]} if query in ROOFLINE_NOTES else {})}
 
 
-def merge_sweep(device_index, rows=50_000_000, n_val_lanes=1):
-    """BASELINE.json configs[4]: merge of two consolidated OrdIndexedZSet<u64,u64,i64>
-    batches (Zipf-ish keys), algorithmic GB/s of the merge kernel vs the HBM peak."""
+def kernel_table(prof):
+    peak, _ = peaks()
+    return {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "alg_GB": round(v["alg_bytes"] / 1e9, 4),
+                "frac_of_hbm_peak": round(v["alg_bytes"] / (v["ms"] / 1e3) / 1e9 / peak, 4) if v["ms"] > 0 else None}
+            for k, v in prof.items()}
+
+
+def merge_sweep(device_index, rows=50_000_000, n_val_lanes=1, reps=5):
+    """BASELINE.json configs[4]: merge of two consolidated batches of `rows` rows each — OrdIndexedZSet<u64,u64,i64>
+    (n_val_lanes=1) or OrdZSet<u64,i64> (n_val_lanes=0) — Zipf(1) keys; algorithmic GB/s of the merge kernel
+    (every input row read once, every output row written once) vs the HBM peak."""
     import torch
 
     from dbsp_b200 import Schema
@@ -313,96 +425,78 @@ def merge_sweep(device_index, rows=50_000_000, n_val_lanes=1):
     for _ in range(2):
         # Zipf(s=1) keys over a domain of rows/4: inverse-CDF of a log-uniform draw
         u = torch.rand(rows, generator=g, device=dev, dtype=torch.float64)
-        dom = rows // 4
+        dom = max(rows // 4, 2)
         keys = torch.exp(u * np.log(dom)).to(torch.int64).clamp_(1, dom)
+        del u
+        if n_val_lanes == 0:   # OrdZSet<u64>: spread the Zipf keys so that consolidation keeps most rows
+            keys = keys * 1024 + torch.randint(0, 1024, (rows,), generator=g, device=dev, dtype=torch.int64)
         vals = [torch.randint(0, 1 << 40, (rows,), generator=g, device=dev, dtype=torch.int64) for _ in range(n_val_lanes)]
         w = torch.randint(0, 4, (rows,), generator=g, device=dev, dtype=torch.int64)
         w = torch.where(w >= 2, w - 1, w - 2)   # {-2,-1,1,2}
         torch.cuda.synchronize(dev)
         batches.append(be.batch_from_columns(s, [int(keys.data_ptr())] + [int(v.data_ptr()) for v in vals], int(w.data_ptr()), n=rows, on_device=True))
         be.sync()
-        del u, keys, vals, w
+        del keys, vals, w
+        torch.cuda.empty_cache()
     a, b = batches
-    for _ in range(3):
+    for _ in range(2):
         be.merge(a, b)
     be.profile(True)
-    for _ in range(5):
+    for _ in range(reps):
         m = be.merge(a, b)
     prof = be.profile_read()
     be.profile(False)
     peak, how = peaks()
     p = prof["merge_tiles"]
     ach = p["alg_bytes"] / (p["ms"] / 1e3) / 1e9
-    traffic = None
-    try:   # dram__bytes_read+write of one launch from the committed ncu --set full capture (2 x 20 M rows), scaled by rows
-        if n_val_lanes != 1:
-            raise KeyError("capture is for 2-lane rows")
-        prof_j = json.load(open(os.path.join(ROOT, "profiles", "r1_merge_tiles_ncu_full.json")))
-        def nbytes(x):   # "960.49 Mbyte" -> bytes
-            v, u = x.split()[:2]
-            return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
-        traffic = (nbytes(prof_j["dram__bytes_read.sum"]) + nbytes(prof_j["dram__bytes_write.sum"])) * (len(a) + len(b)) / 40_000_000
-    except Exception:
-        pass
-    return {"workload": f"merge 2 x OrdIndexedZSet<u64,{'(' + ','.join(['u64'] * n_val_lanes) + ')' if n_val_lanes > 1 else 'u64'},i64>, {len(a)}+{len(b)} rows -> {len(m)}", "rows_per_s": (len(a) + len(b)) / (p["ms"] / 5 / 1e3),
-            "roofline": {"bound": "hbm", "kernel": "merge_tiles", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": traffic, "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum, profiles/r1_merge_tiles_ncu_full.json (2x20M-row launch) scaled by rows",
-                         "alg_bytes_per_launch": p["alg_bytes"] / p["launches"], "avg_launch_us": 1e3 * p["ms"] / p["launches"], "peak_source": how},
-            "inputs_larger_than_l2": True}
+    traffic, src = ncu_traffic("merge_tiles", p["alg_bytes"] / p["launches"])
+    ty = "OrdZSet<u64,i64>" if n_val_lanes == 0 else f"OrdIndexedZSet<u64,{'(' + ','.join(['u64'] * n_val_lanes) + ')' if n_val_lanes > 1 else 'u64'},i64>"
+    res = {"workload": f"merge 2 x {ty}, {len(a)}+{len(b)} rows -> {len(m)}", "rows_per_s": (len(a) + len(b)) / (p["ms"] / reps / 1e3),
+           "roofline": {"bound": "hbm", "kernel": "merge_tiles", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "traffic": traffic, "traffic_source": src,
+                        "alg_bytes_per_launch": p["alg_bytes"] / p["launches"], "avg_launch_us": 1e3 * p["ms"] / p["launches"], "peak_source": how},
+           "inputs_larger_than_l2": (len(a) + len(b)) * 8 * (2 + n_val_lanes) > 126e6,
+           "consolidate_kernels": {k: v for k, v in kernel_table(prof).items() if k != "merge_tiles"}}
+    del a, b, m, batches
+    be.sync()
+    be.close()
+    return res
 
 
-def run_reference(args, query, n_workers=None, budget_s=25.0):
-    """The CPU arm: oracle circuit replicas on all host threads."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
+def run_reference(args, query, bench_steps=None, warmup=None, n_workers=None, gpus=1):
+    """The CPU arm: the oracle port as native C++ worker threads (oracle/nexmark_workers.cpp), rebuilt with
+    -march=native on this host.  Runs the same circuit steps (same E and S) as the GPU arm; `bench_steps` / `warmup`
+    bound the number of bench steps (the in-line cpu_baseline is a bounded sample)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import dbsp_b200
-    from dbsp_b200.nexmark import NexmarkGenerator
-    from dbsp_b200.nexmark import queries as nq
-    from oracle_backend import OracleBackend
-    from thread_workers import run_workers
+    import native_workers as nw
 
-    T = n_workers or min(os.cpu_count() or 1, 16)
-    E, W, K = args.events_per_step, args.warmup, args.steps
-    # bounded sample: CPU steps are sized so that W+K of them fit the budget
-    cpu_E = args.cpu_events_per_step
-    gen = NexmarkGenerator()
-    want = QUERY_COLS[query]
-    tables = [gen.tables(s * cpu_E, cpu_E, want=want) for s in range(W + K)]
-
-    def worker(rank, comm):
-        be = OracleBackend()
-        c = dbsp_b200.RootCircuit(be, comm if T > 1 else None)
-        inp, handles = nq.add_nexmark_input(c)
-        out = nq.QUERIES[query](inp).output()
-        times = []
-        for s, t in enumerate(tables):
-            mine = {k: (None if v is None else [col[rank::T] for col in v]) for k, v in t.items()}
-            comm.barrier()
-            t0 = time.perf_counter()
-            feed_host(handles, mine)
-            c.step()
-            comm.barrier()
-            times.append(time.perf_counter() - t0)
-        return times
-
-    all_times = run_workers(T, worker)
-    per_step = np.max(np.array(all_times), axis=0)
-    timed = per_step[W:]
-    secs = float(timed.sum())
-    return {"value": cpu_E * K / secs, "cores": T, "kind": "port", "ms_per_step": 1e3 * secs / K,
-            "sample": f"{query}: {W}+{K} steps of {cpu_E} events on {T} oracle worker threads (hash-shard + in-process exchange)"}
+    T = n_workers or min(os.cpu_count() or 1, args.cpu_threads)
+    E, S = args.events_per_step * gpus, args.circuit_steps or CIRCUIT_STEPS[query]
+    Kb = args.steps if bench_steps is None else bench_steps
+    Wb = args.warmup if warmup is None else warmup
+    W, K = Wb * S, Kb * S
+    steps = gen_steps(query, 0, 1, W + K, E, pinned=False)
+    secs, rows, fps, how = nw.run(query, T, steps, native=True)
+    timed = float(sum(secs[W:]))
+    in_rows = rows_in(steps, W, W + K)
+    return {"value": E * K / timed, "rows_per_s": in_rows / timed, "cores": T, "kind": "port", "ms_per_step": 1e3 * timed / Kb,
+            "bench_steps": Kb, "warmup": Wb, "build": how, "last_step_out_rows": rows[-1],
+            "sample": f"{query}: {Wb}+{Kb} bench steps x {S} circuit steps of {E} events on {T} native oracle worker threads "
+                      f"(C++ port of the reference's algorithms, hash-shard + in-process exchange, {how})"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=16)
-    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--query", default=None, help="q3 | q4 | q7 (default: q3 primary + q4, q7 riding along)")
-    ap.add_argument("--events-per-step", type=int, default=5_000_000)
-    ap.add_argument("--cpu-events-per-step", type=int, default=400_000)
-    ap.add_argument("--no-extras", action="store_true", help="skip q4/q7 and the merge sweep")
+    ap.add_argument("--events-per-step", type=int, default=5_000_000, help="events per circuit step per GPU")
+    ap.add_argument("--circuit-steps", type=int, default=0, help="circuit steps per bench step (0 = per-query default)")
+    ap.add_argument("--cpu-threads", type=int, default=16)
+    ap.add_argument("--no-extras", action="store_true", help="skip q4/q7, the merge sweep and the in-line cpu_baseline")
+    ap.add_argument("--sweep-rows", default="10000000,100000000,1000000000", help="config[4] total rows per merge")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -412,18 +506,19 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     primary = args.query or "q3"
     E, W, K = args.events_per_step, args.warmup, args.steps
-    cfg = {"workload": f"Nexmark {primary}, {E} events/step/GPU x {K} timed steps (+{W} warm-up) = {world * E * (W + K)} events; "
-                       f"BASELINE configs[1..3] full size {FULL_EVENTS[primary]}",
-           "events_per_step_per_gpu": E, "query": primary, "l2": "inputs larger than L2 (each step streams fresh event columns); traces grow past L2",
-           "parallelism": f"key-hash shard x{world}" if world > 1 else "single GPU"}
+    S = args.circuit_steps or CIRCUIT_STEPS[primary]
 
     if args.impl == "reference":
         if rank != 0:
             return
-        r = run_reference(args, primary)
-        line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+        # same workload as the GPU arm at --gpus N: N x E events per circuit step, all on this host's cores
+        r = run_reference(args, primary, gpus=max(args.gpus, 1))
+        cfg = workload_cfg(primary, E, S, W, K, max(args.gpus, 1))
+        line = {"impl_note": f"CPU arm: every circuit step's {max(args.gpus, 1) * E} events on one host, {r['cores']} worker threads; the Rust "
+                             "reference cannot be built here (no rustc): this is the C++ port under oracle/ (kind: port)",
+                "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
-                "data": "synthetic", "impl": "reference", "config": cfg,
+                "data": "synthetic", "impl": "reference", "config": cfg, "rows_per_s": r["rows_per_s"],
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -440,39 +535,68 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        from dbsp_b200.parallel import Comm
-
         dist.init_process_group("nccl", device_id=device)
-        comm = Comm(device)
+        comm = make_comm(device)
 
     res = run_b200(args, primary, rank, world, comm, device)
+    cfg = workload_cfg(primary, E, S, W, K, world)
     line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic", "config": cfg, "clocks": res["clocks"], "e2e": res.get("e2e"),
-            "gpu_launches": res["gpu_launches"], "roofline": roofline_from_profile(res["profile"], primary),
-            "kernel_profile": {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "alg_GB": round(v["alg_bytes"] / 1e9, 4)} for k, v in res["profile"].items()}}
+            "gpu_launches": res["gpu_launches"], "rows_per_s": res["rows_per_s"],
+            "ms_per_circuit_step": res["ms_per_circuit_step"], "timed_region_ms": res["timed_region_ms"],
+            "circuit_step_latency_ms": {"p50": res["circuit_step_ms_p50"], "p99": res["circuit_step_ms_p99"], "max": res["circuit_step_ms_max"]},
+            "roofline": roofline_from_profile(res["profile"], primary), "kernel_profile": kernel_table(res["profile"])}
     if comm is not None:
-        line["nvlink_bytes_sent_rank0"] = comm.bytes_sent
+        line["nvlink_bytes_sent_rank0"] = getattr(comm, "bytes_sent", None)
 
     if not args.no_extras and args.query is None:
         extras = {}
         for q in ("q4", "q7"):
             r = run_b200(args, q, rank, world, comm, device)
-            extras[q] = {"value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "e2e": r.get("e2e"),
-                         "gpu_launches": r["gpu_launches"], "roofline": roofline_from_profile(r["profile"]),
-                         "kernel_profile": {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "alg_GB": round(v["alg_bytes"] / 1e9, 4)} for k, v in r["profile"].items()},
-                         "events": world * E * (W + K)}
+            extras[q] = {"value": r["value"], "unit": UNIT, "rows_per_s": r["rows_per_s"], "ms_per_step": r["ms_per_step"],
+                         "ms_per_circuit_step": r["ms_per_circuit_step"], "timed_region_ms": r["timed_region_ms"],
+                         "circuit_step_latency_ms": {"p50": r["circuit_step_ms_p50"], "p99": r["circuit_step_ms_p99"], "max": r["circuit_step_ms_max"]},
+                         "e2e": r.get("e2e"), "gpu_launches": r["gpu_launches"], "roofline": roofline_from_profile(r["profile"]),
+                         "kernel_profile": kernel_table(r["profile"]), "config": workload_cfg(q, E, r["circuit_steps_per_bench_step"], W, K, world),
+                         "last_step_out_rows": r["last_step_out_rows"]}
         line["queries"] = extras
-        if world == 1:
-            line["merge_sweep"] = merge_sweep(local)
+        # configs[4]: every rank merges its own replica (no exchange); rank 0 reports its own and the aggregate
+        sweep = []
+        for total in [int(x) for x in args.sweep_rows.split(",") if x]:
+            for nv in (1, 0):
+                if nv == 0 and total != 100_000_000:
+                    continue
+                try:
+                    m = merge_sweep(local, rows=total // 2, n_val_lanes=nv)
+                except Exception as e:   # e.g. out of memory on a shared box: report, do not hide
+                    m = {"workload": f"merge sweep {total} rows nv={nv}", "error": str(e)[:200]}
+                if world > 1 and "roofline" in m:
+                    t = torch.tensor([m["roofline"]["achieved"]], dtype=torch.float64, device=device)
+                    torch.distributed.all_reduce(t)
+                    m["aggregate_GBps_all_gpus"] = float(t.item())
+                    m["replicas"] = world
+                sweep.append(m)
+        line["merge_sweep"] = sweep
 
-    if rank == 0 and world == 1:
-        cb = run_reference(args, primary)
+    if comm is not None:
+        try:
+            par = parity_check(rank, world, comm, device)
+        except Exception as e:
+            par = {"ok": False, "error": repr(e)[:300]}
+        line["parity_checked"] = bool(par.get("ok"))
+        line["parity"] = par
+
+    if rank == 0 and world == 1 and not args.no_extras:
+        cb = run_reference(args, primary, bench_steps=4, warmup=1)
         line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
         if "queries" in line:
             for q in ("q4", "q7"):
-                c2 = run_reference(args, q)
+                c2 = run_reference(args, q, bench_steps=3, warmup=1)
                 line["queries"][q]["cpu_baseline"] = {"value": c2["value"], "unit": UNIT, "cores": c2["cores"], "kind": c2["kind"], "sample": c2["sample"]}
+    elif rank == 0 and world == 1:
+        cb = run_reference(args, primary, bench_steps=2, warmup=1)
+        line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

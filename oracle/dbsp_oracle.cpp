@@ -150,39 +150,66 @@ struct Builder {
   }
 };
 
-// consolidate (trace/consolidation/mod.rs:32-52): sort by key, sum the
-// weights of equal keys, drop zeros; then Builder (merge_batcher/mod.rs:65-80).
-// The reference sorts with its own pdqsort (consolidation/quicksort.rs:12-33);
-// only the sorted order is observable, std::sort (introsort) stands in.
-BatchP from_tuples(const dbsp_schema& s, const u64* const* cols, const i64* w, size_t n) {
-  int nl = s.n_key_lanes + s.n_val_lanes;
-  std::vector<size_t> idx(n);
-  for (size_t i = 0; i < n; i++) idx[i] = i;
-  auto less = [&](size_t a, size_t b) {
-    for (int l = 0; l < nl; l++) {
-      int c = cmp1(s.lane_types[l], cols[l][a], cols[l][b]);
-      if (c) return c < 0;
-    }
+// consolidate (trace/consolidation/mod.rs:32-52,182-231): the tuples are gathered into an array of
+// ((K,V),R) structs like the reference's Vec<((K,V),R)>, sorted by key, the weights of equal keys
+// summed in place, zeros dropped; then Builder (merge_batcher/mod.rs:65-80).  The reference sorts with
+// its own pdqsort (consolidation/quicksort.rs:12-33); only the sorted order is observable, std::sort
+// (introsort) stands in.  i64 lanes are sorted through the order-preserving map x ^ 2^63.
+template <int NL>
+struct RowT {
+  u64 k[NL];
+  i64 w;
+};
+template <int NL>
+BatchP from_tuples_n(const dbsp_schema& s, const u64* const* cols, const i64* w, size_t n) {
+  typedef RowT<NL> Row;
+  u64 flip[NL];
+  for (int l = 0; l < NL; l++) flip[l] = s.lane_types[l] == DBSP_I64 ? 0x8000000000000000ull : 0ull;
+  std::vector<Row> v(n);
+  for (size_t i = 0; i < n; i++) {
+    for (int l = 0; l < NL; l++) v[i].k[l] = cols[l][i] ^ flip[l];
+    v[i].w = w ? w[i] : 1;
+  }
+  auto less = [](const Row& a, const Row& b) {
+    for (int l = 0; l < NL; l++)
+      if (a.k[l] != b.k[l]) return a.k[l] < b.k[l];
     return false;
   };
-  std::sort(idx.begin(), idx.end(), less);
+  auto same = [](const Row& a, const Row& b) {
+    for (int l = 0; l < NL; l++)
+      if (a.k[l] != b.k[l]) return false;
+    return true;
+  };
+  std::sort(v.begin(), v.end(), less);
   Builder bld(s);
   u64 row[MAXL];
   size_t i = 0;
   while (i < n) {
-    size_t j = i;
-    i64 sum = 0;
-    while (j < n && !less(idx[i], idx[j]) && !less(idx[j], idx[i])) {
-      sum = (i64)((u64)sum + (u64)(w ? w[idx[j]] : 1));  // isize add wraps in release
+    size_t j = i + 1;
+    i64 sum = v[i].w;
+    while (j < n && same(v[i], v[j])) {
+      sum = (i64)((u64)sum + (u64)v[j].w);  // isize add wraps in release
       j++;
     }
     if (sum != 0) {
-      for (int l = 0; l < nl; l++) row[l] = cols[l][idx[i]];
+      for (int l = 0; l < NL; l++) row[l] = v[i].k[l] ^ flip[l];
       bld.push(row, row + s.n_key_lanes, sum);
     }
     i = j;
   }
   return bld.done();
+}
+BatchP from_tuples(const dbsp_schema& s, const u64* const* cols, const i64* w, size_t n) {
+  switch (s.n_key_lanes + s.n_val_lanes) {
+    case 1: return from_tuples_n<1>(s, cols, w, n);
+    case 2: return from_tuples_n<2>(s, cols, w, n);
+    case 3: return from_tuples_n<3>(s, cols, w, n);
+    case 4: return from_tuples_n<4>(s, cols, w, n);
+    case 5: return from_tuples_n<5>(s, cols, w, n);
+    case 6: return from_tuples_n<6>(s, cols, w, n);
+    case 7: return from_tuples_n<7>(s, cols, w, n);
+    default: return from_tuples_n<8>(s, cols, w, n);
+  }
 }
 
 // Tuple accumulator feeding from_tuples.
@@ -746,9 +773,20 @@ int32_t orc_batch_last_key(orc_ctx*, const orc_batch* b, u64* key, int32_t* vali
 int32_t orc_batch_clone(const orc_batch* b, orc_batch** out) { *out = wrap(b->p); return DBSP_OK; }
 int32_t orc_batch_free(orc_batch* b) { delete b; return DBSP_OK; }
 
-int32_t orc_batch_from_sorted(orc_ctx* c, const dbsp_schema* s, const u64* const* cols, const i64* w, u64 n,
-                              int32_t d, orc_batch** out) {
-  return orc_batch_from_tuples(c, s, cols, w, n, d, out);
+// Builder::push ... done (trace/mod.rs:338-368; ordered/mod.rs:468-479,874-888): the rows are already
+// sorted and consolidated — appended in order, no sort.
+int32_t orc_batch_from_sorted(orc_ctx*, const dbsp_schema* s, const u64* const* cols, const i64* w, u64 n,
+                              int32_t, orc_batch** out) {
+  Builder bld(*s);
+  const int nk = s->n_key_lanes, nv = s->n_val_lanes;
+  u64 key[MAXL], val[MAXL];
+  for (u64 i = 0; i < n; i++) {
+    for (int l = 0; l < nk; l++) key[l] = cols[l][i];
+    for (int l = 0; l < nv; l++) val[l] = cols[nk + l][i];
+    bld.push(key, val, w[i]);
+  }
+  *out = wrap(bld.done());
+  return DBSP_OK;
 }
 
 int32_t orc_spine_new(orc_ctx*, const dbsp_schema* s, orc_spine** out) { *out = new orc_spine(*s); return DBSP_OK; }
