@@ -115,7 +115,16 @@ _SIGS = {
     "window_delta": [_P, _P, _P, C.c_int32, _U64P, _U64P, _U64P, _U64P, _PP],
     "map_index": [_P, _P, C.POINTER(CProj), _PP],
     "shard_partition": [_P, _P, C.c_uint32, _PP],
+    "comm_create": [_P, C.c_int32, C.c_int32, C.c_uint64, _P],
+    "comm_connect": [_P, _P],
+    "comm_destroy": [_P],
+    "comm_info": [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _U64P],
+    "shard": [_P, _P, _PP],
+    "shard2": [_P, _P, _P, _PP, _PP],
+    "gather": [_P, _P, C.c_int32, _PP],
+    "allreduce_max_u64": [_P, _U64P],
 }
+COMM_BLOB_BYTES = 128
 
 
 class CApi:

@@ -98,6 +98,8 @@ class RootCircuit:
             backend = Runtime()
         self.be = backend
         self.comm = comm  # parallel.Comm or None (single worker)
+        if comm is not None and getattr(comm, "native", None) is None and hasattr(comm, "attach") and comm.world_size > 1:
+            comm.attach(backend)   # CUDA backend: the exchange moves into the library (csrc/comm.cu)
         self.nodes: list[Node] = []
 
     # -- sources -------------------------------------------------------------

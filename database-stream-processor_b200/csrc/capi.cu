@@ -185,7 +185,9 @@ int32_t dbsp_ctx_create(int32_t device, dbsp_ctx** out) {
 int32_t dbsp_ctx_destroy(dbsp_ctx* c) {
   if (!c) return DBSP_OK;
   print_host_stats(c);
+  cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  comm_free(c);
   cudaFreeHost(c->h_scratch);
   cudaFreeHost((void*)c->h_mail);
   cudaFree(c->d_scratch);
@@ -718,6 +720,60 @@ int32_t dbsp_shard_partition(dbsp_ctx* ctx, const dbsp_batch* b, uint32_t P, dbs
   std::vector<Batch*> o(P, nullptr);
   TRY(op_shard_partition(ctx, B(b), P, o.data()));
   for (uint32_t p = 0; p < P; p++) outs[p] = H(o[p]);
+  return DBSP_OK;
+}
+
+int32_t dbsp_comm_create(dbsp_ctx* ctx, int32_t rank, int32_t world, uint64_t slot_bytes, uint8_t* blob_out) { ENTER(ctx);
+  CHECK_ARG(blob_out != nullptr, "comm_create: blob_out is NULL");
+  return comm_create(ctx, rank, world, slot_bytes, blob_out);
+}
+int32_t dbsp_comm_connect(dbsp_ctx* ctx, const uint8_t* blobs) { ENTER(ctx);
+  CHECK_ARG(blobs != nullptr, "comm_connect: blobs is NULL");
+  return comm_connect(ctx, blobs);
+}
+int32_t dbsp_comm_destroy(dbsp_ctx* ctx) { ENTER(ctx);
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  comm_free(ctx);
+  return DBSP_OK;
+}
+int32_t dbsp_comm_info(dbsp_ctx* ctx, int32_t* rank, int32_t* world, uint64_t* bytes_sent) {
+  int r, w;
+  u64 b;
+  comm_info(ctx, &r, &w, &b);
+  if (rank) *rank = r;
+  if (world) *world = w;
+  if (bytes_sent) *bytes_sent = b;
+  return DBSP_OK;
+}
+int32_t dbsp_shard(dbsp_ctx* ctx, const dbsp_batch* b, dbsp_batch** out) { ENTER(ctx);
+  const Batch* in[1] = {B(b)};
+  Batch* o[1] = {nullptr};
+  TRY(comm_exchange(ctx, in, 1, -1, o));
+  *out = H(o[0]);
+  return DBSP_OK;
+}
+int32_t dbsp_shard2(dbsp_ctx* ctx, const dbsp_batch* a, const dbsp_batch* b, dbsp_batch** out_a, dbsp_batch** out_b) { ENTER(ctx);
+  const Batch* in[2] = {B(a), B(b)};
+  Batch* o[2] = {nullptr, nullptr};
+  TRY(comm_exchange(ctx, in, 2, -1, o));
+  *out_a = H(o[0]);
+  *out_b = H(o[1]);
+  return DBSP_OK;
+}
+int32_t dbsp_gather(dbsp_ctx* ctx, const dbsp_batch* b, int32_t root, dbsp_batch** out) { ENTER(ctx);
+  int r, w;
+  comm_info(ctx, &r, &w, nullptr);
+  CHECK_ARG(root >= 0 && root < w, "gather: root out of range");
+  const Batch* in[1] = {B(b)};
+  Batch* o[1] = {nullptr};
+  TRY(comm_exchange(ctx, in, 1, root, o));
+  *out = H(o[0]);
+  return DBSP_OK;
+}
+int32_t dbsp_allreduce_max_u64(dbsp_ctx* ctx, uint64_t* x) { ENTER(ctx);
+  u64 v = *x;
+  TRY(comm_allreduce_max(ctx, &v));
+  *x = v;
   return DBSP_OK;
 }
 

@@ -22,6 +22,7 @@ typedef uint32_t u32;
 #define MAXL DBSP_MAX_LANES
 
 struct Ctx;
+struct Comm;
 
 void set_error(const std::string& s);
 #define CUDA_TRY(expr)                                                                    \
@@ -97,7 +98,7 @@ struct Spine {
 // stream; bench.py's roofline figures come from here).
 enum KernelId {
   KID_MERGE = 0, KID_MERGE_PARTITION, KID_PROBE_RANGES, KID_PROBE_FILL, KID_PROJECT, KID_RADIX_SORT, KID_PACK,
-  KID_HEADS, KID_EMIT, KID_MINMAX, KID_SEG_REDUCE, KID_LOOKUP, KID_COMPACT, KID_SCAN, KID_AGG_PICK, KID_MISC, KID_COUNT
+  KID_HEADS, KID_EMIT, KID_MINMAX, KID_SEG_REDUCE, KID_LOOKUP, KID_COMPACT, KID_SCAN, KID_AGG_PICK, KID_MISC, KID_SHARD, KID_COUNT
 };
 struct ProfRec {
   cudaEvent_t a, b;
@@ -137,6 +138,7 @@ struct Ctx {
   double t_alloc_us = 0, t_sync_us = 0;
   u64 n_alloc = 0, n_sync = 0;
   int sm_count = 148;
+  Comm* comm = nullptr;   // exchange state (comm.cu), owned by the context
 };
 
 #define LAUNCH_COUNT(ctx) ((ctx)->kernel_launches++)
@@ -163,6 +165,16 @@ int32_t read_back(Ctx* ctx, const void* dsrc, size_t count_u64, u64* hdst);
 int32_t read_back32(Ctx* ctx, const void* dsrc, u32* hdst);
 int32_t exclusive_scan_u32(Ctx* ctx, const u32* in, u32* out, u64 n);   // out[n] = total (n+1 entries)
 int32_t inclusive_scan_i64(Ctx* ctx, const i64* in, i64* out, u64 n);
+
+int32_t mail_wait(Ctx* ctx, u64 seq);   // spin on the host mailbox until `seq` is published
+
+// ---- comm.cu ---------------------------------------------------------------
+int32_t comm_create(Ctx* ctx, int rank, int world, u64 slot_bytes, unsigned char* blob_out);
+int32_t comm_connect(Ctx* ctx, const unsigned char* blobs);
+void comm_free(Ctx* ctx);
+int32_t comm_exchange(Ctx* ctx, const Batch* const* in, int ns, int fixed_dest, Batch** out);
+int32_t comm_allreduce_max(Ctx* ctx, u64* x);
+void comm_info(Ctx* ctx, int* rank, int* world, u64* bytes_sent);
 
 // ---- consolidate.cu ------------------------------------------------------
 // Sort (lanes, weights) rows, sum equal rows, drop zero weights -> batch.

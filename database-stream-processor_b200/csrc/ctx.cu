@@ -25,7 +25,7 @@ const char* get_error() { return g_err.c_str(); }
 
 static const char* KNAMES[KID_COUNT] = {
     "merge_tiles", "merge_partition", "probe_ranges", "probe_fill", "project_rows", "radix_sort", "pack_keys",
-    "heads", "emit", "minmax", "seg_reduce", "lookup", "compact", "scan", "agg_pick", "misc"};
+    "heads", "emit", "minmax", "seg_reduce", "lookup", "compact", "scan", "agg_pick", "misc", "shard_scatter"};
 const char* kernel_name(int id) { return (id >= 0 && id < KID_COUNT) ? KNAMES[id] : "?"; }
 
 ProfScope::ProfScope(Ctx* ctx, int id, u64 bytes) : c(ctx) {
@@ -195,7 +195,7 @@ __global__ void k_publish(volatile u64* mail, const u64* src, int count, int wor
   }
 }
 
-static int32_t mail_wait(Ctx* ctx, u64 seq) {
+int32_t mail_wait(Ctx* ctx, u64 seq) {
   u64 spins = 0;
   while (ctx->h_mail[0] != seq) {
     if ((++spins & 0xffff) == 0) {   // the stream may have faulted: do not spin forever

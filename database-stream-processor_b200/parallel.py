@@ -1,20 +1,24 @@
-"""Multi-GPU plumbing: one process per GPU, `torch.distributed` (NCCL over
-NVLink on the B200 box, gloo in the CPU tests).
+"""Multi-GPU plumbing: one process per GPU.
 
-Mirrors the reference's only distribution scheme: N
-identical circuit replicas, inputs re-partitioned by key hash in front of
-every keyed operator (operator/communication/shard.rs:36-162), one exchange
-round per sharded stream per step (exchange.rs:36-44), gather for
-verification (gather.rs:41-103), watermark all-reduce (watermark.rs:53-70).
-The traces never move: only delta batches cross NVLink.
+Mirrors the reference's only distribution scheme: N identical circuit replicas, inputs
+re-partitioned by key hash in front of every keyed operator (operator/communication/shard.rs:36-162), one
+exchange round per sharded stream per step (exchange.rs:36-44), gather for verification (gather.rs:41-103),
+watermark all-reduce (watermark.rs:53-70).  The traces never move: only delta batches cross NVLink.
 
-Wire format of one exchange: every rank sends to peer p one contiguous int64
-segment [lane 0 rows | lane 1 rows | ... | weights] holding the rows of its
-batch whose hash(key) % P == p — already sorted, so the receiver only merges
-(shard.rs:136-144).  Segment sizes are data dependent: a P-element count
-all-to-all precedes the payload all-to-all.
+Product path (CUDA backend): the exchange lives INSIDE the library — `dbsp_shard / dbsp_shard2 / dbsp_gather /
+dbsp_allreduce_max_u64` (csrc/comm.cu): the partition kernel scatters straight into the peers' receive slots over
+NVLink, counts travel through peer-mapped flag words, the receiver merges in place.  `torch.distributed` is used
+ONCE, at `attach()`, to all-gather the 128-byte region descriptors (the bootstrap any host can do).
+
+Host path (`native` is None): the same protocol through `torch.distributed` collectives on flat tensors — used by
+the CPU test-suite (gloo + the oracle backend, tests/test_shard_gloo.py) and as the `DBSP_EXCHANGE=torch` escape
+hatch.  Wire format of that path: every rank sends to peer p one contiguous int64 segment
+[lane 0 rows | lane 1 rows | ... | weights] of the rows with hash(key) % P == p — already sorted, so the receiver
+only merges (shard.rs:136-144); a P-element count all-to-all precedes the payload all-to-all.
 """
 from __future__ import annotations
+
+import os
 
 import torch
 import torch.distributed as dist
@@ -29,10 +33,38 @@ class Comm:
         self.rank = dist.get_rank(group)
         self.world_size = dist.get_world_size(group)
         self.device = device or torch.device("cpu")
-        self.bytes_sent = 0   # payload bytes that left this rank (for the NVLink roofline)
+        self._bytes_sent = 0   # payload bytes that left this rank through the host path
+        self.native = None     # CUDA backend whose context carries the in-library exchange
+
+    # -- in-library exchange (csrc/comm.cu) ---------------------------------
+    def attach(self, be: Backend, slot_bytes: int = 0):
+        """Create the context's receive region, all-gather the region descriptors, map the peers."""
+        if be.name != "cuda" or os.environ.get("DBSP_EXCHANGE") == "torch":
+            return
+        blob = be.comm_create(self.rank, self.world_size, slot_bytes)
+        mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(self.device)
+        allb = torch.empty(self.world_size * len(blob), dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(allb, mine, group=self.group)
+        be.comm_connect(bytes(allb.cpu().numpy().tobytes()))
+        dist.barrier(group=self.group)   # every rank has mapped every region before the first store
+        self.native = be
+
+    def detach(self):
+        if self.native is not None:
+            dist.barrier(group=self.group)   # no peer still writes into a region that is about to go
+            self.native.comm_destroy()
+            self.native = None
+
+    @property
+    def bytes_sent(self):
+        if self.native is not None:
+            return self.native.comm_info()[2]
+        return self._bytes_sent
 
     # -- scalars -----------------------------------------------------------
     def allreduce_max(self, x: int) -> int:
+        if self.native is not None:
+            return self.native.allreduce_max(x)
         t = torch.tensor([int(x)], dtype=torch.int64, device=self.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         return int(t.item())
@@ -78,7 +110,7 @@ class Comm:
         out_split = [sum(rc[q][i] * L1[i] for i in range(nS)) for q in range(P)]
         recv = torch.empty(sum(out_split), dtype=torch.int64, device=self.device)
         dist.all_to_all_single(recv, send, output_split_sizes=out_split, input_split_sizes=in_split, group=self.group)
-        self.bytes_sent += sum(in_split[p] for p in range(P) if p != self.rank) * 8
+        self._bytes_sent += sum(in_split[p] for p in range(P) if p != self.rank) * 8
         if recv.is_cuda:
             torch.cuda.current_stream(recv.device).synchronize()   # once, before the library adopts the segments
         # offsets of stream i's block inside peer q's segment
@@ -125,17 +157,23 @@ class Comm:
 
     def shard(self, be: Backend, b: Batch) -> Batch:
         """shard (communication/shard.rs:106-162)."""
+        if self.native is be:
+            return be.shard(b)
         parts = be.shard_partition(b, self.world_size)
         return self._merge_all(be, self._exchange(be, parts))
 
     def shard_many(self, be: Backend, batches: list[Batch]) -> list[Batch]:
         """shard() of several streams in one exchange round (the two inputs of a join)."""
+        if self.native is be and len(batches) == 2:
+            return list(be.shard2(batches[0], batches[1]))
         streams = [be.shard_partition(b, self.world_size) for b in batches]
         return [self._merge_all(be, got) for got in self._exchange_many(be, streams)]
 
     def gather(self, be: Backend, b: Batch, root: int = 0) -> Batch:
         """gather (communication/gather.rs:41-103): everything to `root`,
         empty batches elsewhere."""
+        if self.native is be:
+            return be.gather(b, root)
         empty = be.batch_empty(b.schema)
         parts = [b if p == root else empty for p in range(self.world_size)]
         return self._merge_all(be, self._exchange(be, parts))

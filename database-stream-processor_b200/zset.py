@@ -648,6 +648,45 @@ class Backend:
         self.api.call("shard_partition", self.ctx, b.h, n_shards, outs)
         return [Batch(self, outs[i], b.schema) for i in range(n_shards)]
 
+    # -- communication between replicas (include/dbsp_b200.h "communication") ------
+    def comm_create(self, rank: int, world: int, slot_bytes: int = 0) -> bytes:
+        blob = (C.c_uint8 * capi.COMM_BLOB_BYTES)()
+        self.api.call("comm_create", self.ctx, rank, world, slot_bytes, blob)
+        return bytes(blob)
+
+    def comm_connect(self, blobs: bytes):
+        buf = (C.c_uint8 * len(blobs)).from_buffer_copy(blobs)
+        self.api.call("comm_connect", self.ctx, buf)
+
+    def comm_destroy(self):
+        if getattr(self, "ctx", None):
+            self.api.call("comm_destroy", self.ctx)
+
+    def comm_info(self):
+        r, w, b = C.c_int32(), C.c_int32(), C.c_uint64()
+        self.api.call("comm_info", self.ctx, C.byref(r), C.byref(w), C.byref(b))
+        return r.value, w.value, b.value
+
+    def shard(self, b: Batch) -> Batch:
+        out = self._out()
+        self.api.call("shard", self.ctx, b.h, C.byref(out))
+        return Batch(self, out.value, b.schema)
+
+    def shard2(self, a: Batch, b: Batch):
+        oa, ob = self._out(), self._out()
+        self.api.call("shard2", self.ctx, a.h, b.h, C.byref(oa), C.byref(ob))
+        return Batch(self, oa.value, a.schema), Batch(self, ob.value, b.schema)
+
+    def gather(self, b: Batch, root: int = 0) -> Batch:
+        out = self._out()
+        self.api.call("gather", self.ctx, b.h, root, C.byref(out))
+        return Batch(self, out.value, b.schema)
+
+    def allreduce_max(self, x: int) -> int:
+        v = C.c_uint64(int(x) & ((1 << 64) - 1))
+        self.api.call("allreduce_max_u64", self.ctx, C.byref(v))
+        return v.value
+
     # -- flat column access for the exchange (overridden per backend) -------
     def batch_flat_tensors(self, b: Batch):
         """(list of per-lane torch tensors, weight tensor) of the flat rows."""

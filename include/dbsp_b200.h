@@ -336,6 +336,38 @@ int32_t dbsp_map_index(dbsp_ctx* ctx, const dbsp_batch* b,
  * dbsp_batch_device_columns(); the receiver merges (shard.rs:136-144). */
 int32_t dbsp_shard_partition(dbsp_ctx* ctx, const dbsp_batch* b,
                              uint32_t n_shards, dbsp_batch** outs);
+/* ---- communication between circuit replicas (one replica = one context = one GPU) ----------------
+ * Replaces shard (operator/communication/shard.rs:106-162), Exchange (exchange.rs:128-200), gather
+ * (gather.rs:41-103) and the watermark exchange (time_series/watermark.rs:53-70) — the three calls SURVEY.md
+ * §8(b) lists as dbsp_shard / dbsp_gather / dbsp_allreduce_max_u64.  There is no collective library on the
+ * data path: every context owns a device receive region; peers map it (CUDA IPC between processes, peer
+ * access between the contexts of one process) and the partition kernel's stores land in it over NVLink.
+ *
+ * Bootstrap (replaces the ncclUniqueId of the survey's sketch): every rank calls dbsp_comm_create, which
+ * returns a DBSP_COMM_BLOB_BYTES descriptor of its region; the HOST moves the `world` descriptors to every
+ * rank by whatever channel it has (the reference's workers are threads of one process: a shared Vec; one
+ * process per GPU: any all-gather) and hands the rank-ordered array to dbsp_comm_connect.
+ * All replicas must issue the same sequence of exchange calls (they run the same circuit). */
+#define DBSP_COMM_MAX_RANKS 32
+#define DBSP_COMM_BLOB_BYTES 128
+int32_t dbsp_comm_create(dbsp_ctx* ctx, int32_t rank, int32_t world,
+                         uint64_t slot_bytes /* capacity of one (source,destination) segment per round; 0 = 256 MiB */,
+                         uint8_t* blob_out /* DBSP_COMM_BLOB_BYTES */);
+int32_t dbsp_comm_connect(dbsp_ctx* ctx, const uint8_t* blobs /* world * DBSP_COMM_BLOB_BYTES, rank order */);
+int32_t dbsp_comm_destroy(dbsp_ctx* ctx);
+/* rank / world of the context (0 / 1 without a comm) and payload bytes it has sent to other ranks */
+int32_t dbsp_comm_info(dbsp_ctx* ctx, int32_t* rank, int32_t* world, uint64_t* bytes_sent);
+/* Stream::shard (shard.rs:106-162): rows re-partitioned by hash(key) % world; returns this replica's shard,
+ * consolidated (partition + NVLink scatter + receiver merge in one call; identity when world == 1). */
+int32_t dbsp_shard(dbsp_ctx* ctx, const dbsp_batch* b, dbsp_batch** out);
+/* shard() of both inputs of a binary operator (join.rs:265-266) in ONE exchange round. */
+int32_t dbsp_shard2(dbsp_ctx* ctx, const dbsp_batch* a, const dbsp_batch* b,
+                    dbsp_batch** out_a, dbsp_batch** out_b);
+/* Stream::gather (gather.rs:41-103): everything to `root`, empty batches elsewhere. */
+int32_t dbsp_gather(dbsp_ctx* ctx, const dbsp_batch* b, int32_t root, dbsp_batch** out);
+/* max over the replicas of *x (watermark.rs:53-70); every replica gets the result. */
+int32_t dbsp_allreduce_max_u64(dbsp_ctx* ctx, uint64_t* x);
+
 /* Builder path (trace/mod.rs:338-368): adopt rows that are already sorted
  * and consolidated (e.g. a segment received from a peer). */
 int32_t dbsp_batch_from_sorted(dbsp_ctx* ctx, const dbsp_schema* schema,

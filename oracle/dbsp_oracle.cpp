@@ -1081,4 +1081,28 @@ int32_t orc_shard_partition(orc_ctx*, const orc_batch* b, uint32_t P, orc_batch*
   return DBSP_OK;
 }
 
+// Communication entry points of the ABI.  The oracle is one worker: identity for world == 1 (shard.rs:111-114);
+// the multi-worker CPU runs use the in-process exchange of oracle/nexmark_workers.cpp / thread_workers.py.
+int32_t orc_comm_create(orc_ctx*, int32_t rank, int32_t world, u64, uint8_t* blob) {
+  if (world != 1 || rank != 0) { g_err = "oracle: single worker only"; return DBSP_ERR_UNSUPPORTED; }
+  if (blob) memset(blob, 0, DBSP_COMM_BLOB_BYTES);
+  return DBSP_OK;
+}
+int32_t orc_comm_connect(orc_ctx*, const uint8_t*) { return DBSP_OK; }
+int32_t orc_comm_destroy(orc_ctx*) { return DBSP_OK; }
+int32_t orc_comm_info(orc_ctx*, int32_t* rank, int32_t* world, u64* bytes) {
+  if (rank) *rank = 0;
+  if (world) *world = 1;
+  if (bytes) *bytes = 0;
+  return DBSP_OK;
+}
+int32_t orc_shard(orc_ctx*, const orc_batch* b, orc_batch** out) { *out = wrap(b->p); return DBSP_OK; }
+int32_t orc_shard2(orc_ctx*, const orc_batch* a, const orc_batch* b, orc_batch** oa, orc_batch** ob) {
+  *oa = wrap(a->p);
+  *ob = wrap(b->p);
+  return DBSP_OK;
+}
+int32_t orc_gather(orc_ctx*, const orc_batch* b, int32_t, orc_batch** out) { *out = wrap(b->p); return DBSP_OK; }
+int32_t orc_allreduce_max_u64(orc_ctx*, u64*) { return DBSP_OK; }
+
 }  // extern "C"
