@@ -56,33 +56,239 @@ static int32_t stage_columns(Ctx* ctx, const u64* const* cols, int ncols, const 
   return DBSP_OK;
 }
 
-// Spine::insert (trace/spine_fueled.rs:605-634).  The reference assigns the
-// batch to level log2(len.next_power_of_two()) and advances in-progress merges
-// with fuel (:730-812).  The schedule of merges is not observable through
-// cursors (cursor/cursor_list.rs), so the device spine keeps the same
-// geometric invariant with whole merges on the stream: while the two newest
-// batches are within 2x of each other they are merged (K3/K4).
-static int32_t spine_truncate_batch(Ctx* ctx, Spine* s, Batch* b, Batch** out);
-static int32_t spine_merge_newest(Ctx* ctx, Spine* s);
+// ---- Spine: the fuelled LSM of trace/spine_fueled.rs ---------------------------------------------------------------
+// The layer structure and the schedule are the reference's, restated: insert -> introduce_batch (:728-812: apply
+// fuel to the merges in progress, roll_up, insert_at, tidy_layers), roll_up (:819-846), apply_fuel (:856-882),
+// insert_at (:889-908), tidy_layers (:916-974), exert (:561-581), consolidate (:583-600), reduced (:663-680),
+// MergeState / MergeVariant (:1012-1188).  One deliberate difference in *how* a merge spends its fuel: the
+// reference's Merger advances a few thousand rows per call; the GPU merges two whole batches in one launch, so a
+// merge in progress is a fuel account — the two batches stay visible to cursors exactly as long as in the
+// reference (until the fuel paid reaches their length) and the single merge launch happens when the account is
+// settled.  The schedule (which batches meet, when a layer becomes complete) is therefore the reference's.
+static int32_t merge_bounded(Ctx* ctx, const Batch* x, const Batch* y, const u64* vbound, Batch** out);
+
+static u64 level_len(const SpineLevel& l) {   // MergeState::len (:1034-1041)
+  switch (l.kind) {
+    case SpineLevel::SINGLE: return l.a ? l.a->n : 0;
+    case SpineLevel::IN_PROGRESS: return l.a->n + l.b->n;
+    case SpineLevel::COMPLETE: return l.a ? l.a->n : 0;
+    default: return 0;
+  }
+}
+static inline bool level_is_double(const SpineLevel& l) { return l.kind == SpineLevel::IN_PROGRESS || l.kind == SpineLevel::COMPLETE; }
+
+static void spine_refresh_view(Spine* s) {   // the batches a SpineCursor is built from (:179-216)
+  s->batches.clear();
+  for (size_t i = s->merging.size(); i-- > 0;) {
+    const SpineLevel& l = s->merging[i];
+    if (l.kind == SpineLevel::IN_PROGRESS) {
+      if (l.a->n) s->batches.push_back(l.a);
+      if (l.b->n) s->batches.push_back(l.b);
+    } else if ((l.kind == SpineLevel::SINGLE || l.kind == SpineLevel::COMPLETE) && l.a && l.a->n) {
+      s->batches.push_back(l.a);
+    }
+  }
+}
+
+// MergeState::begin_merge (:1106-1124); takes over the references of both batches
+static SpineLevel level_begin_merge(Batch* b1, Batch* b2) {
+  SpineLevel l;
+  if (b1 && b2) {
+    l.kind = SpineLevel::IN_PROGRESS;
+    l.a = b1;
+    l.b = b2;
+    l.remaining = (i64)(b1->n + b2->n);
+  } else {
+    l.kind = SpineLevel::COMPLETE;
+    l.a = b1 ? b1 : b2;
+  }
+  return l;
+}
+
+// MergeVariant::work (:1176-1188): pay `*fuel` into the account; when it is settled the merge runs (one launch)
+// and the layer becomes Complete.  *fuel > 0 afterwards <=> the merge completed (trace/mod.rs:388-395).
+static int32_t level_work(Ctx* ctx, Spine* s, SpineLevel& l, i64* fuel) {
+  if (l.kind != SpineLevel::IN_PROGRESS) return DBSP_OK;
+  if (*fuel < l.remaining) {
+    l.remaining -= *fuel;
+    *fuel = 0;
+    return DBSP_OK;
+  }
+  *fuel = (*fuel == INT64_MAX) ? INT64_MAX : (*fuel - l.remaining > 0 ? *fuel - l.remaining : 1);
+  Batch* merged = nullptr;
+  TRY(merge_bounded(ctx, l.a, l.b, s->has_vbound ? s->vbound : nullptr, &merged));
+  batch_unref(l.a);
+  batch_unref(l.b);
+  l.kind = SpineLevel::COMPLETE;
+  l.a = merged;
+  l.b = nullptr;
+  l.remaining = 0;
+  return DBSP_OK;
+}
+
+// MergeState::complete (:1060-1066): finish whatever the layer holds and take it out (nullptr = nothing)
+static int32_t level_complete(Ctx* ctx, Spine* s, SpineLevel& l, Batch** out) {
+  *out = nullptr;
+  if (l.kind == SpineLevel::IN_PROGRESS) {
+    i64 fuel = INT64_MAX;
+    TRY(level_work(ctx, s, l, &fuel));
+  }
+  if (l.kind == SpineLevel::SINGLE || l.kind == SpineLevel::COMPLETE) *out = l.a;
+  l = SpineLevel();
+  return DBSP_OK;
+}
+
+// insert_at (:889-908)
+static int32_t spine_insert_at(Spine* s, Batch* batch, size_t index) {
+  while (s->merging.size() <= index) s->merging.push_back(SpineLevel());
+  SpineLevel& l = s->merging[index];
+  switch (l.kind) {
+    case SpineLevel::VACANT:
+      l.kind = SpineLevel::SINGLE;
+      l.a = batch;
+      return DBSP_OK;
+    case SpineLevel::SINGLE: {
+      Batch* old = l.a;
+      l = level_begin_merge(old, batch);
+      return DBSP_OK;
+    }
+    default:
+      if (batch) batch_unref(batch);
+      set_error("spine: attempted to insert a batch into an incomplete merge");   // panic! in the reference (:904)
+      return DBSP_ERR_INVALID;
+  }
+}
+
+// apply_fuel (:856-882): every layer receives the same fuel; a merge that completes moves up at once
+static int32_t spine_apply_fuel(Ctx* ctx, Spine* s, i64 fuel_each) {
+  for (size_t index = 0; index < s->merging.size(); index++) {
+    i64 fuel = fuel_each;
+    TRY(level_work(ctx, s, s->merging[index], &fuel));
+    if (s->merging[index].kind == SpineLevel::COMPLETE) {
+      Batch* done = nullptr;
+      TRY(level_complete(ctx, s, s->merging[index], &done));
+      TRY(spine_insert_at(s, done, index + 1));
+    }
+  }
+  return DBSP_OK;
+}
+
+// roll_up (:819-846)
+static int32_t spine_roll_up(Ctx* ctx, Spine* s, size_t index) {
+  while (s->merging.size() <= index) s->merging.push_back(SpineLevel());
+  bool any = false;
+  for (size_t i = 0; i < index; i++) any = any || s->merging[i].kind != SpineLevel::VACANT;
+  if (!any) return DBSP_OK;
+  Batch* merged = nullptr;
+  for (size_t i = 0; i < index; i++) {
+    TRY(spine_insert_at(s, merged, i));
+    TRY(level_complete(ctx, s, s->merging[i], &merged));
+  }
+  TRY(spine_insert_at(s, merged, index));
+  if (level_is_double(s->merging[index])) {
+    Batch* m2 = nullptr;
+    TRY(level_complete(ctx, s, s->merging[index], &m2));
+    TRY(spine_insert_at(s, m2, index + 1));
+  }
+  return DBSP_OK;
+}
+
+// tidy_layers (:916-974)
+static int32_t spine_tidy_layers(Spine* s) {
+  if (s->merging.empty()) return DBSP_OK;
+  size_t length = s->merging.size();
+  if (s->merging[length - 1].kind != SpineLevel::SINGLE) return DBSP_OK;
+  const u64 len = level_len(s->merging[length - 1]);
+  size_t appropriate = 0;   // len.next_power_of_two().trailing_zeros()
+  while ((1ull << appropriate) < len) appropriate++;
+  while (appropriate < length - 1) {
+    SpineLevel& below = s->merging[length - 2];
+    if (below.kind == SpineLevel::VACANT || (below.kind == SpineLevel::SINGLE && below.a == nullptr)) {
+      s->merging.erase(s->merging.begin() + (length - 2));
+      length = s->merging.size();
+    } else if (below.kind == SpineLevel::SINGLE) {
+      u64 smaller = 0;
+      for (size_t i = 0; i + 2 < length; i++) {
+        if (s->merging[i].kind == SpineLevel::SINGLE) smaller += 1ull << i;
+        else if (level_is_double(s->merging[i])) smaller += 2ull << i;
+      }
+      if (smaller <= (1ull << length) / 8) {
+        Batch* batch = below.a;
+        s->merging.erase(s->merging.begin() + (length - 2));
+        TRY(spine_insert_at(s, batch, length - 2));
+      }
+      return DBSP_OK;
+    } else {
+      return DBSP_OK;   // a merge is in progress: nothing to do
+    }
+  }
+  return DBSP_OK;
+}
+
+// introduce_batch (:728-812)
+static int32_t spine_introduce_batch(Ctx* ctx, Spine* s, Batch* batch, size_t batch_index) {
+  i64 fuel = batch_index >= 59 ? INT64_MAX : (i64)((8ull << batch_index) * s->effort);
+  int32_t rc = spine_apply_fuel(ctx, s, fuel);
+  if (rc == DBSP_OK) rc = spine_roll_up(ctx, s, batch_index);
+  if (rc != DBSP_OK) { if (batch) batch_unref(batch); return rc; }
+  TRY(spine_insert_at(s, batch, batch_index));
+  return spine_tidy_layers(s);
+}
+
+// reduced (:663-680)
+static bool spine_reduced(const Spine* s) {
+  int non_empty = 0;
+  for (const SpineLevel& l : s->merging) {
+    if (level_is_double(l)) return false;
+    if (level_len(l) > 0) non_empty++;
+    if (non_empty > 1) return false;
+  }
+  return true;
+}
+
+// exert (:561-581)
+static int32_t spine_exert(Ctx* ctx, Spine* s, i64* effort) {
+  TRY(spine_tidy_layers(s));
+  if (!spine_reduced(s)) {
+    bool any_double = false;
+    for (const SpineLevel& l : s->merging) any_double = any_double || level_is_double(l);
+    if (any_double) {
+      TRY(spine_apply_fuel(ctx, s, *effort));
+    } else {
+      size_t level = 0;   // (*effort as usize).next_power_of_two().trailing_zeros()
+      while ((1ull << level) < (u64)(*effort > 0 ? *effort : 1) && level < 62) level++;
+      TRY(spine_introduce_batch(ctx, s, nullptr, level));
+    }
+  }
+  spine_refresh_view(s);
+  return DBSP_OK;
+}
+
+// truncate_keys_below (spine_fueled.rs:223-233; column_layer/mod.rs:316-319):
+// a zero-copy suffix view of the batch.
+static int32_t spine_truncate_batch(Ctx* ctx, Spine* s, Batch* b, Batch** out) {
+  u64 pos;
+  TRY(batch_lower_bound(ctx, b, s->bound, &pos));
+  if (pos == 0) { batch_ref(b); *out = b; return DBSP_OK; }
+  *out = batch_slice(ctx, b, pos, b->n);
+  return DBSP_OK;
+}
+
+// Trace::insert (:605-634)
 static int32_t spine_insert(Ctx* ctx, Spine* s, Batch* b) {
-  if (b->n == 0) return DBSP_OK;
+  if (b->n == 0) return DBSP_OK;   // empty batches are ignored (:609-611)
   Batch* nb = nullptr;
   if (s->has_bound) {
     TRY(spine_truncate_batch(ctx, s, b, &nb));
-    if (nb->n == 0) { batch_unref(nb); return DBSP_OK; }
   } else {
     batch_ref(b);
     nb = b;
   }
-  s->batches.push_back(nb);
-  while (s->batches.size() >= 2) {
-    size_t m = s->batches.size();
-    Batch* x = s->batches[m - 2];
-    Batch* y = s->batches[m - 1];
-    if (x->n >= 2 * y->n) break;
-    TRY(spine_merge_newest(ctx, s));
-  }
-  return DBSP_OK;
+  size_t index = 0;   // batch.len().next_power_of_two().trailing_zeros()
+  while ((1ull << index) < nb->n) index++;
+  int32_t rc = spine_introduce_batch(ctx, s, nb, index);
+  spine_refresh_view(s);
+  return rc;
 }
 
 // Merge of two batches with the spine's lower value bound applied to the
@@ -96,28 +302,22 @@ static int32_t merge_bounded(Ctx* ctx, const Batch* x, const Batch* y, const u64
   return rc;
 }
 
-static int32_t spine_merge_newest(Ctx* ctx, Spine* s) {
-  size_t m = s->batches.size();
-  Batch* x = s->batches[m - 2];
-  Batch* y = s->batches[m - 1];
-  Batch* merged = nullptr;
-  TRY(merge_bounded(ctx, x, y, s->has_vbound ? s->vbound : nullptr, &merged));
-  s->batches.pop_back();
-  s->batches.pop_back();
-  batch_unref(x);
-  batch_unref(y);
-  if (merged->n) s->batches.push_back(merged); else batch_unref(merged);
+// complete_merges (:977-985)
+static int32_t spine_complete_merges(Ctx* ctx, Spine* s) {
+  for (SpineLevel& l : s->merging) {
+    i64 fuel = INT64_MAX;
+    TRY(level_work(ctx, s, l, &fuel));
+  }
   return DBSP_OK;
 }
 
-// truncate_keys_below (spine_fueled.rs:223-233; column_layer/mod.rs:316-319):
-// a zero-copy suffix view of the batch.
-static int32_t spine_truncate_batch(Ctx* ctx, Spine* s, Batch* b, Batch** out) {
-  u64 pos;
-  TRY(batch_lower_bound(ctx, b, s->bound, &pos));
-  if (pos == 0) { batch_ref(b); *out = b; return DBSP_OK; }
-  *out = batch_slice(ctx, b, pos, b->n);
-  return DBSP_OK;
+static void spine_release(Spine* s) {
+  for (SpineLevel& l : s->merging) {
+    if (l.a) batch_unref(l.a);
+    if (l.b) batch_unref(l.b);
+  }
+  s->merging.clear();
+  s->batches.clear();
 }
 
 // The fuelled Merger (trace/mod.rs:371-396).  On the device a unit of fuel is
@@ -620,11 +820,13 @@ int32_t dbsp_spine_insert(dbsp_ctx* ctx, dbsp_spine* s, const dbsp_batch* b) { E
   return spine_insert(ctx, s, B(b));
 }
 int32_t dbsp_spine_consolidate(dbsp_ctx* ctx, dbsp_spine* s, dbsp_batch** out) { ENTER(ctx);
-  Batch* acc = batch_new_empty(ctx, s->s);
+  // A consolidated read of the trace: the merge of everything a cursor sees, with the value bound applied.
+  // Trace::consolidate (:583-600) consumes the trace; this leaves the layers (and their merge schedule) as they are.
   const u64* vb = s->has_vbound ? s->vbound : nullptr;
-  for (Batch* b : s->batches) {
+  Batch* acc = batch_new_empty(ctx, s->s);
+  for (size_t i = s->batches.size(); i-- > 0;) {   // smallest first: the accumulator grows geometrically
     Batch* m = nullptr;
-    int32_t rc = merge_bounded(ctx, acc, b, vb, &m);
+    int32_t rc = merge_bounded(ctx, acc, s->batches[i], vb, &m);
     batch_unref(acc);
     if (rc) return rc;
     acc = m;
@@ -642,16 +844,18 @@ int32_t dbsp_spine_truncate_keys_below(dbsp_ctx* ctx, dbsp_spine* s, const uint6
     }
   }
   if (!raise) return DBSP_OK;
+  TRY(spine_complete_merges(ctx, s));   // :224
   s->has_bound = true;
   for (int l = 0; l < s->s.n_key_lanes; l++) s->bound[l] = key[l];
-  std::vector<Batch*> keep;
-  for (Batch* b : s->batches) {
-    Batch* v = nullptr;
-    TRY(spine_truncate_batch(ctx, s, b, &v));
-    batch_unref(b);
-    if (v->n) keep.push_back(v); else batch_unref(v);
+  for (SpineLevel& l : s->merging) {   // map_batches_mut (:988-1004)
+    if ((l.kind == SpineLevel::SINGLE || l.kind == SpineLevel::COMPLETE) && l.a) {
+      Batch* v = nullptr;
+      TRY(spine_truncate_batch(ctx, s, l.a, &v));
+      batch_unref(l.a);
+      l.a = v;
+    }
   }
-  s->batches.swap(keep);
+  spine_refresh_view(s);
   return DBSP_OK;
 }
 int32_t dbsp_spine_truncate_values_below(dbsp_ctx*, dbsp_spine* s, const uint64_t* val) {
@@ -669,14 +873,8 @@ int32_t dbsp_spine_truncate_values_below(dbsp_ctx*, dbsp_spine* s, const uint64_
   return DBSP_OK;
 }
 int32_t dbsp_spine_exert(dbsp_ctx* ctx, dbsp_spine* s, int64_t* effort) { ENTER(ctx);
-  while (s->batches.size() >= 2) {
-    size_t m = s->batches.size();
-    int64_t cost = (int64_t)(s->batches[m - 2]->n + s->batches[m - 1]->n);
-    if (cost > *effort) break;
-    TRY(spine_merge_newest(ctx, s));
-    *effort -= cost;
-  }
-  return DBSP_OK;
+  i64 e = *effort;
+  return spine_exert(ctx, s, &e);
 }
 int32_t dbsp_spine_len(const dbsp_spine* s, uint64_t* n, uint32_t* nb) {
   u64 t = 0;
@@ -687,7 +885,7 @@ int32_t dbsp_spine_len(const dbsp_spine* s, uint64_t* n, uint32_t* nb) {
 }
 int32_t dbsp_spine_free(dbsp_spine* s) {
   if (!s) return DBSP_OK;
-  for (Batch* b : s->batches) batch_unref(b);
+  spine_release(s);
   delete s;
   return DBSP_OK;
 }

@@ -84,9 +84,20 @@ struct Batch {
   }
 };
 
+// Spine (trace/spine_fueled.rs:107-119): the LSM of batches behind a trace.  `merging[i]` is the reference's
+// MergeState of layer i (batches of at most 2^i rows); `batches` is the cursor view — every batch a CursorList
+// would see (spine_fueled.rs:179-216), rebuilt after each mutation, borrowed pointers, largest layer first.
+struct SpineLevel {
+  enum Kind { VACANT, SINGLE, IN_PROGRESS, COMPLETE } kind = VACANT;
+  Batch* a = nullptr;   // SINGLE: the batch (nullptr = structurally empty); IN_PROGRESS: batch1; COMPLETE: the result (or nullptr)
+  Batch* b = nullptr;   // IN_PROGRESS: batch2
+  i64 remaining = 0;    // IN_PROGRESS: fuel still to be paid before the merge is due (rows of batch1 + batch2)
+};
 struct Spine {
   dbsp_schema s;
-  std::vector<Batch*> batches;   // oldest (largest) first; each holds one ref
+  std::vector<SpineLevel> merging;
+  std::vector<Batch*> batches;   // cursor view (no references held)
+  u64 effort = 1;
   bool has_bound = false;
   u64 bound[MAXL];
   bool has_vbound = false;   // lower_val_bound (spine_fueled.rs:118)
@@ -98,7 +109,7 @@ struct Spine {
 // stream; bench.py's roofline figures come from here).
 enum KernelId {
   KID_MERGE = 0, KID_MERGE_PARTITION, KID_PROBE_RANGES, KID_PROBE_FILL, KID_PROJECT, KID_RADIX_SORT, KID_PACK,
-  KID_HEADS, KID_EMIT, KID_MINMAX, KID_SEG_REDUCE, KID_LOOKUP, KID_COMPACT, KID_SCAN, KID_AGG_PICK, KID_MISC, KID_SHARD, KID_COUNT
+  KID_HEADS, KID_EMIT, KID_MINMAX, KID_SEG_REDUCE, KID_LOOKUP, KID_COMPACT, KID_SCAN, KID_AGG_PICK, KID_MISC, KID_SHARD, KID_CHUNK_SORT, KID_COUNT
 };
 struct ProfRec {
   cudaEvent_t a, b;

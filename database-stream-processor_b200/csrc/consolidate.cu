@@ -13,17 +13,16 @@
 //      if they are also duplicate- and zero-free the input buffer *becomes*
 //      the batch (no copy).
 //  (3) Otherwise the comparison sort the reference spends "90% of the work"
-//      in (consolidation/mod.rs:101-104) is an LSD radix sort over bit-packed
+//      in (consolidation/mod.rs:101-104) is a radix sort over bit-packed
 //      composite keys: the lanes' significant bits are concatenated (order
 //      preserving, injective) into as few 64-bit words as possible and only
-//      those bits are sorted, as (key word, row id) pairs.  The Nexmark
+//      those bits are sorted, as (key word, row id) pairs, by the hand-written
+//      passes of sort.cu (top digits in HBM, the rest in shared memory; no HBM
+//      pass at all when the leading lane arrives ordered).  The Nexmark
 //      schemas pack into one word of 30-60 bits.
 //  (4) Epilogue: a two-pass reduce-by-key sums runs of equal rows and drops
 //      zero sums; the duplicate-free case is one unpack/gather pass.
-#include <cub/device/device_radix_sort.cuh>
-
 #include "common.cuh"
-#include "segsort.cuh"
 
 namespace {
 
@@ -36,20 +35,21 @@ struct Plan {
 };
 
 // mm[l] = min, mm[L+l] = max of flipped lane l; mm[2L] = # inversions
-// (row i-1 > row i), mm[2L+1] = # adjacent duplicates, mm[2L+2] = # zero weights.
+// (row i-1 > row i), mm[2L+1] = # adjacent duplicates, mm[2L+2] = # zero weights,
+// mm[2L+3] = row count (when it lives on the device), mm[2L+4] = # inversions of lane 0 alone.
 __global__ void k_props(Cols cols, Flips f, int L, const i64* w, u64 n_host, const u32* dn, u64* mm) {
   // the producer may have left the exact row count on the device (dn): the
   // census then returns it with the lane ranges in the same read-back
   const u64 n = dn ? (u64)*dn : n_host;
   if (dn && blockIdx.x == 0 && threadIdx.x == 0) mm[2 * L + 3] = n;
   __shared__ u64 smin[MAXL], smax[MAXL];
-  __shared__ unsigned s_cnt[3];
+  __shared__ unsigned s_cnt[4];
   if (threadIdx.x < MAXL) { smin[threadIdx.x] = ~0ull; smax[threadIdx.x] = 0; }
-  if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   u64 lmin[MAXL], lmax[MAXL];
   for (int l = 0; l < L; l++) { lmin[l] = ~0ull; lmax[l] = 0; }
-  unsigned inv = 0, dup = 0, zero = 0;
+  unsigned inv = 0, dup = 0, zero = 0, inv0 = 0;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
     int c = 0;   // cmp(row i-1, row i)
     for (int l = 0; l < L; l++) {
@@ -59,6 +59,7 @@ __global__ void k_props(Cols cols, Flips f, int L, const i64* w, u64 n_host, con
       if (i > 0 && c == 0) {
         u64 pv = cols.c[l][i - 1] ^ f.f[l];
         if (pv != v) c = pv < v ? -1 : 1;
+        if (l == 0) inv0 += pv > v;
       }
     }
     if (i > 0) { inv += c > 0; dup += c == 0; }
@@ -79,11 +80,13 @@ __global__ void k_props(Cols cols, Flips f, int L, const i64* w, u64 n_host, con
     inv += __shfl_xor_sync(0xffffffffu, inv, o);
     dup += __shfl_xor_sync(0xffffffffu, dup, o);
     zero += __shfl_xor_sync(0xffffffffu, zero, o);
+    inv0 += __shfl_xor_sync(0xffffffffu, inv0, o);
   }
   if ((threadIdx.x & 31) == 0) {
     if (inv) atomicAdd(&s_cnt[0], inv);
     if (dup) atomicAdd(&s_cnt[1], dup);
     if (zero) atomicAdd(&s_cnt[2], zero);
+    if (inv0) atomicAdd(&s_cnt[3], inv0);
   }
   __syncthreads();
   if (threadIdx.x < L) {
@@ -92,12 +95,13 @@ __global__ void k_props(Cols cols, Flips f, int L, const i64* w, u64 n_host, con
   }
   if (threadIdx.x < 3 && s_cnt[threadIdx.x])
     atomicAdd((unsigned long long*)&mm[2 * L + threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+  if (threadIdx.x == 3 && s_cnt[3]) atomicAdd((unsigned long long*)&mm[2 * L + 4], (unsigned long long)s_cnt[3]);
 }
 
 __global__ void k_init_props(u64* mm, int L) {
   int t = threadIdx.x;
   if (t < L) mm[t] = ~0ull;
-  else if (t < 2 * L + 4) mm[t] = 0;
+  else if (t < 2 * L + 5) mm[t] = 0;
 }
 
 // key[i] = word `wd` of row (idx ? idx[i] : i); writes idx_out[i] = i when idx == nullptr.
@@ -124,6 +128,7 @@ __global__ void k_heads(Cols cols, int L, int use_key, const u64* key, const u32
                         i64* ws, u64* counters) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned bad = 0;
+  if (counters && counters[2]) return;   // the sort raised its fallback flag: key / idx are not a permutation yet
   if (i < n) {
     u64 r = idx ? idx[i] : i;
     bool head = true;
@@ -406,24 +411,8 @@ inline int bits_for(u64 range) { return range == 0 ? 0 : 64 - __builtin_clzll(ra
 
 }  // namespace
 
-// ---- experimental prefix-sorted path (segsort.cuh; DBSP_PREFIX_SORT=1) ----------
-// out[0] += inversions on lane 0, out[1] = longest equal-lane-0 run (capped at SEG_RUN_CAP + 1)
-__global__ void k_lane0_props(Cols cols, Flips f, u64 n, u64* out) {
-  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned inv = 0, run = 0;
-  if (i < n) inv = seg_lane0_props(cols.c[0], f.f[0], n, i, &run);
-  const unsigned m = __ballot_sync(0xffffffffu, inv != 0);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) run = max(run, __shfl_xor_sync(0xffffffffu, run, o));
-  if ((threadIdx.x & 31) == 0) {
-    if (m) atomicAdd((unsigned long long*)&out[0], (unsigned long long)__popc(m));
-    if (run) atomicMax((unsigned long long*)&out[1], (unsigned long long)run);
-  }
-}
-__global__ void k_segment_rank(Cols cols, Flips f, int L, u64 n, u32* idx) {
-  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) seg_rank_row(cols.c, f.f, L, n, i, idx);
-}
+int32_t radix_sort_pairs(Ctx* ctx, u64* ka, u64* kb, u32* ia, u32* ib, u64 n, int bits, int presorted_top_bits, bool force_lsd,
+                         unsigned long long* fail, u64** key_out, u32** idx_out, int* hbm_passes);
 
 int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const i64* w, u64 n, const BufP* adopt,
                          Batch** out, const u32* d_n) {
@@ -437,7 +426,7 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
   for (int l = 0; l < MAXL; l++) f.f[l] = (l < L && s.lane_types[l] == DBSP_I64) ? 0x8000000000000000ull : 0;
 
   // ---- (1) lane ranges + order / duplicate / zero-weight census ---------------
-  u64 mm[2 * MAXL + 4];
+  u64 mm[2 * MAXL + 5];
   {
     u64* dmm = ctx->d_scratch + 64;
     k_init_props<<<1, 32, 0, st>>>(dmm, L);
@@ -447,7 +436,7 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
       k_props<<<g, TB, 0, st>>>(cols, f, L, w, n, d_n, dmm);
     }
     ctx->kernel_launches += 2;
-    TRY(read_back(ctx, dmm, 2 * L + 4, mm));
+    TRY(read_back(ctx, dmm, 2 * L + 5, mm));
     if (d_n) {
       n = mm[2 * L + 3];
       if (n == 0) { *out = batch_new_empty(ctx, s); return DBSP_OK; }
@@ -479,32 +468,6 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
     p.W = 1;
     p.use_key = 0;   // compare / copy the lanes themselves, identity order
   } else {
-    // ---- (2b) experimental: lane 0 already ordered, short equal-lane-0 runs ------
-    // (time-ordered event tables): rank every row inside its run instead of sorting
-    // the whole batch.  Off unless DBSP_PREFIX_SORT is set (not yet measured).
-    static const bool prefix_sort = getenv("DBSP_PREFIX_SORT") != nullptr;
-    bool ranked = false;
-    if (prefix_sort && L >= 2 && n > 1) {
-      u64* d = ctx->d_scratch + 44;
-      CUDA_TRY(cudaMemsetAsync(d, 0, 16, st));
-      k_lane0_props<<<nblk, TB, 0, st>>>(cols, f, n, d);
-      LAUNCH_COUNT(ctx);
-      u64 h[2];
-      TRY(read_back(ctx, d, 2, h));
-      if (h[0] == 0 && h[1] <= SEG_RUN_CAP) {
-        TRY(dev_alloc(ctx, (size_t)n * 4, &ibuf));
-        {
-          ProfScope ps(ctx, KID_MISC, n * (u64)L * 8 + n * 4);
-          k_segment_rank<<<nblk, TB, 0, st>>>(cols, f, L, n, (u32*)ibuf->p);
-        }
-        LAUNCH_COUNT(ctx);
-        idx_cur = (u32*)ibuf->p;
-        p.W = 1;
-        p.use_key = 0;   // compare / copy the lanes themselves through the row ids
-        ranked = true;
-      }
-    }
-    if (!ranked) {
     // ---- (3) bit-packing plan: lanes from last (least significant) to first ----
     int word = 0, used = 0;
     for (int l = L - 1; l >= 0; l--) {
@@ -521,66 +484,70 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
     }
     p.W = word + 1;
     p.use_key = p.W == 1;
-
-    // sort (key word, row id) pairs, least significant word first
     TRY(dev_alloc(ctx, (size_t)n * 8 * 2, &kbuf));
     TRY(dev_alloc(ctx, (size_t)n * 4 * 2, &ibuf));
-    u64* ka = (u64*)kbuf->p;
-    u64* kb = ka + n;
-    u32* ia = (u32*)ibuf->p;
-    u32* ib = ia + n;
-    size_t tmp_bytes = 0;
-    {
-      cub::DoubleBuffer<u64> dk(ka, kb);
-      cub::DoubleBuffer<u32> di(ia, ib);
-      CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, di, (int)n, 0, 64, st));
-    }
-    TRY(dev_alloc(ctx, tmp_bytes, &tmp));
-    key_sorted = ka;
+  }
+  u64* const kbufs[2] = {kbuf ? (u64*)kbuf->p : nullptr, kbuf ? (u64*)kbuf->p + n : nullptr};
+  u32* const ibufs[2] = {ibuf ? (u32*)ibuf->p : nullptr, ibuf ? (u32*)ibuf->p + n : nullptr};
+  u64* const cnt = ctx->d_scratch + 32;   // [0] duplicates, [1] zero weights, [2] sort-fallback flag
+  // lane 0 ordered on arrival (event tables come in time order) and the key is one word: its top bits[0] bits are
+  // non-decreasing already, the sort can skip every HBM pass (sort.cu)
+  const int presorted = (p.W == 1 && n_inv != 0 && mm[2 * L + 4] == 0) ? (int)p.bits[0] : 0;
+
+  // sort (key word, row id) pairs word by word, least significant word first (every stage is stable)
+  auto sort_rows = [&](bool force_lsd) -> int32_t {
+    idx_cur = nullptr;
     for (int wd = 0; wd < p.W; wd++) {
-      // Keys of the previous word are dead: always pack into ka.  The row ids
-      // ping-pong between ia and ib.
+      // the keys of the previous word are dead: always pack into key buffer 0; the row ids stay where the
+      // previous word's sort left them
+      u64* kdst = kbufs[0];
+      u32* iother;
       {
         ProfScope ps(ctx, KID_PACK, n * (u64)L * 8 + n * 12);
         if (wd == 0) {
-          k_pack<<<nblk, TB, 0, st>>>(cols, p, wd, nullptr, n, ka, ia);
-          idx_cur = ia;
+          k_pack<<<nblk, TB, 0, st>>>(cols, p, wd, nullptr, n, kdst, ibufs[0]);
+          idx_cur = ibufs[0];
         } else {
-          k_pack<<<nblk, TB, 0, st>>>(cols, p, wd, idx_cur, n, ka, nullptr);
+          k_pack<<<nblk, TB, 0, st>>>(cols, p, wd, idx_cur, n, kdst, nullptr);
         }
       }
       LAUNCH_COUNT(ctx);
-      key_sorted = ka;
+      iother = idx_cur == ibufs[0] ? ibufs[1] : ibufs[0];
+      key_sorted = kdst;
       if (p.wbits[wd] > 0 && n > 1) {
-        cub::DoubleBuffer<u64> dk(ka, kb);
-        cub::DoubleBuffer<u32> di(idx_cur, idx_cur == ia ? ib : ia);
-        {
-          // lower bound: the (key,id) pairs read once and written once; the LSD
-          // sort makes ceil(bits/8) such round trips
-          ProfScope ps(ctx, KID_RADIX_SORT, n * 12 * 2);
-          CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp->p, tmp_bytes, dk, di, (int)n, 0, (int)p.wbits[wd], st));
-        }
-        ctx->kernel_launches += (p.wbits[wd] + 7) / 8 + 1;
-        idx_cur = di.Current();
-        key_sorted = dk.Current();
+        u64* ko;
+        u32* io;
+        TRY(radix_sort_pairs(ctx, kdst, kbufs[1], idx_cur, iother, n, (int)p.wbits[wd], presorted, force_lsd,
+                             (unsigned long long*)(cnt + 2), &ko, &io, nullptr));
+        key_sorted = ko;
+        idx_cur = io;
       }
     }
-    }   // !ranked
+    return DBSP_OK;
+  };
+  if (n_inv != 0) {
+    CUDA_TRY(cudaMemsetAsync(cnt, 0, 24, st));
+    TRY(sort_rows(false));
   }
 
   // ---- (4) epilogue -------------------------------------------------------------
   // After a sort, duplicates are possible iff the input had any equal pair at
   // all — unknown from the census (it only saw adjacent pairs) — so count.
-  u64 hc[2] = {n_dup, n_zero};
+  u64 hc[3] = {n_dup, n_zero, 0};
   if (n_inv != 0) {
-    u64* cnt = ctx->d_scratch + 32;
-    CUDA_TRY(cudaMemsetAsync(cnt, 0, 16, st));
-    {
-      ProfScope ps(ctx, KID_HEADS, n * (u64)(12 + (w ? 8 : 0)));
-      k_heads<<<nblk + 1, TB, 0, st>>>(cols, L, p.use_key, key_sorted, idx_cur, w, n, nullptr, nullptr, cnt);
+    for (int attempt = 0; attempt < 2; attempt++) {
+      {
+        ProfScope ps(ctx, KID_HEADS, n * (u64)(12 + (w ? 8 : 0)));
+        k_heads<<<nblk + 1, TB, 0, st>>>(cols, L, p.use_key, key_sorted, idx_cur, w, n, nullptr, nullptr, cnt);
+      }
+      LAUNCH_COUNT(ctx);
+      TRY(read_back(ctx, cnt, 3, hc));
+      if (hc[2] == 0) break;
+      // a bucket did not fit a shared-memory chunk (heavy key skew): redo with the plain LSD sequence
+      if (attempt == 1) { set_error("consolidate: sort fallback failed"); return DBSP_ERR_CUDA; }
+      CUDA_TRY(cudaMemsetAsync(cnt, 0, 24, st));
+      TRY(sort_rows(true));
     }
-    LAUNCH_COUNT(ctx);
-    TRY(read_back(ctx, cnt, 2, hc));
   }
 
   MCols oc;

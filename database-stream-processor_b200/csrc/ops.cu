@@ -359,11 +359,13 @@ __global__ void k_agg_pick(Cols G, const i64* wG, u64 n, int nk, int nv, int kin
     for (int l = 0; l < out_nv; l++) out.c[l][i] = v[l];
 }
 
-// Max / Min fast path.  Per key and per spine batch the only candidate is the
-// last (Max, max.rs:36-55 walks back from the end) or first (Min, min.rs:38-57)
-// value of the key's range; the winner's weight summed over the batches that
-// hold it is CursorList::weight (cursor_list.rs:200-210).  If that sum is zero
-// the extremum was cancelled and the key is flagged for the general path.
+// Max / Min.  Per key, a walk over the union of the spine batches' value lists from the extreme end — the
+// CursorList walk of max.rs:36-55 (backwards from the end) / min.rs:38-57 (forwards): per batch a cursor into the
+// key's value range; the candidate is the extreme value under the cursors, its weight the sum over the batches that
+// hold it (cursor_list.rs:200-210); a zero sum (the value was retracted by another batch — e.g. a merge still in
+// progress holds +1 and -1 in two batches) steps those cursors and tries the next value.  Keys that need more than
+// AGG_WALK steps are flagged for the general gather path.
+constexpr int AGG_WALK = 64;
 __global__ void k_agg_extremum(Cols K, u64 nkeys, int nk, int nv, BatchRefs tr, Flips f, int is_max, u32* keep,
                                MCols outv, u64* slow_counter) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -371,43 +373,64 @@ __global__ void k_agg_extremum(Cols K, u64 nkeys, int nk, int nv, BatchRefs tr, 
   if (i == nkeys) { keep[nkeys] = 0; return; }
   u64 q[MAXL], best[MAXL];
   for (int l = 0; l < nk; l++) q[l] = K.c[l][i] ^ f.f[l];
-  bool have = false;
-  i64 wsum = 0;
+  // the key's value range [lo, hi) in every batch; cur = next candidate position
+  u32 lo[MAX_REFS], hi[MAX_REFS];
   for (int b = 0; b < tr.nb; b++) {
     const Cols& T = tr.b[b].c;
-    u64 nt = tr.b[b].n, r;
-    if (is_max) {
-      u64 hi = upper_bound_q(T, 0, nt, q, nk, f);
-      if (hi == 0) continue;
-      r = hi - 1;
-    } else {
-      r = lower_bound_q(T, 0, nt, q, nk, f);
-      if (r >= nt) continue;
+    const u64 nt = tr.b[b].n;
+    const u64 l0 = lower_bound_q(T, 0, nt, q, nk, f);
+    u64 h0 = l0;
+    if (l0 < nt && cmp_row_q(T, l0, q, nk, f) == 0) {
+      u64 step = 1;
+      h0 = l0 + 1;
+      while (h0 + step <= nt && cmp_row_q(T, h0 + step - 1, q, nk, f) == 0) { h0 += step; step <<= 1; }
+      const u64 top = h0 + step <= nt ? h0 + step : nt;
+      h0 = upper_bound_q(T, h0, top, q, nk, f);
     }
-    if (cmp_row_q(T, r, q, nk, f) != 0) continue;
-    int c = 0;   // cmp(candidate, best) over the value lanes
-    u64 cand[MAXL];
-    for (int l = 0; l < nv; l++) {
-      cand[l] = T.c[nk + l][r] ^ f.f[nk + l];
-      if (have && c == 0 && cand[l] != best[l]) c = cand[l] < best[l] ? -1 : 1;
+    lo[b] = (u32)l0;
+    hi[b] = (u32)h0;
+  }
+  bool have = false, exhausted = false;
+  i64 wsum = 0;
+  for (int it = 0; it < AGG_WALK; it++) {
+    have = false;
+    for (int b = 0; b < tr.nb; b++) {
+      if (lo[b] >= hi[b]) continue;
+      const Cols& T = tr.b[b].c;
+      const u64 r = is_max ? (u64)hi[b] - 1 : (u64)lo[b];
+      int c = 0;   // cmp(candidate, best) over the value lanes
+      u64 cand[MAXL];
+      for (int l = 0; l < nv; l++) {
+        cand[l] = T.c[nk + l][r] ^ f.f[nk + l];
+        if (have && c == 0 && cand[l] != best[l]) c = cand[l] < best[l] ? -1 : 1;
+      }
+      if (!have || (is_max ? c > 0 : c < 0)) {
+        for (int l = 0; l < nv; l++) best[l] = cand[l];
+        have = true;
+      }
     }
-    bool better = !have || (is_max ? c > 0 : c < 0);
-    if (better) {
-      for (int l = 0; l < nv; l++) best[l] = cand[l];
-      wsum = tr.b[b].w[r];
-      have = true;
-    } else if (c == 0) {
-      wsum = (i64)((u64)wsum + (u64)tr.b[b].w[r]);
+    if (!have) break;   // every cursor ran off its range: the key has no value left
+    wsum = 0;
+    for (int b = 0; b < tr.nb; b++) {
+      if (lo[b] >= hi[b]) continue;
+      const Cols& T = tr.b[b].c;
+      const u64 r = is_max ? (u64)hi[b] - 1 : (u64)lo[b];
+      bool eq = true;
+      for (int l = 0; l < nv; l++) eq = eq && ((T.c[nk + l][r] ^ f.f[nk + l]) == best[l]);
+      if (eq) {
+        wsum = (i64)((u64)wsum + (u64)tr.b[b].w[r]);
+        if (is_max) hi[b]--; else lo[b]++;   // step past the candidate
+      }
     }
+    if (wsum != 0) break;
+    if (it == AGG_WALK - 1) exhausted = true;
   }
   u32 k = 0;
-  if (have) {
-    if (wsum != 0) {
-      k = 1;
-      for (int l = 0; l < nv; l++) outv.c[l][i] = best[l] ^ f.f[nk + l];
-    } else {
-      atomicAdd((unsigned long long*)slow_counter, 1ull);
-    }
+  if (exhausted) {
+    atomicAdd((unsigned long long*)slow_counter, 1ull);
+  } else if (have && wsum != 0) {
+    k = 1;
+    for (int l = 0; l < nv; l++) outv.c[l][i] = best[l] ^ f.f[nk + l];
   }
   keep[i] = k;
 }

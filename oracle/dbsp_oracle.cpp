@@ -20,6 +20,8 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -394,43 +396,201 @@ BatchP truncate_keys_below(const Batch& b, const u64* key) {
 // this oracle — like the CUDA spine — keeps the same geometric invariant with
 // eager merges: after an insert, while the two newest batches are within 2x
 // of each other they are merged.  Documented in DESIGN.md.
+// Spine (trace/spine_fueled.rs:107-119, 537-1188): the fuelled LSM, restated layer by layer.  `merging[i]`
+// is MergeState of layer i; a merge in progress keeps both inputs visible to cursors (:179-216) while the
+// Merger (above) advances by the fuel every insert grants it.  `batches` is the cursor view, rebuilt after
+// every mutation.
 struct Spine {
+  struct Layer {
+    enum Kind { VACANT, SINGLE, IN_PROGRESS, COMPLETE } kind = VACANT;
+    BatchP a, b;                     // SINGLE: a (may be null = structurally empty); IN_PROGRESS: a, b; COMPLETE: a (may be null)
+    std::shared_ptr<Merger> m;       // IN_PROGRESS
+    size_t len() const {             // MergeState::len (:1034-1041)
+      switch (kind) {
+        case SINGLE: case COMPLETE: return a ? a->len() : 0;
+        case IN_PROGRESS: return a->len() + b->len();
+        default: return 0;
+      }
+    }
+    bool is_double() const { return kind == IN_PROGRESS || kind == COMPLETE; }
+  };
   dbsp_schema s;
-  std::vector<BatchP> batches;   // oldest (largest) first
+  std::vector<Layer> merging;
+  std::vector<BatchP> batches;   // cursor view, largest layer first
+  size_t effort = 1;
   bool has_bound = false;
   u64 bound[MAXL];
   bool has_vbound = false;   // lower_val_bound (spine_fueled.rs:118, 644-656)
   u64 vbound[MAXL];
   explicit Spine(const dbsp_schema& sc) : s(sc) {}
   const u64* vb() const { return has_vbound ? vbound : nullptr; }
-  void insert(BatchP b) {
-    if (b->len() == 0) return;   // spine_fueled.rs:606-608
-    if (has_bound) { BatchP t = truncate_keys_below(*b, bound); if (t) b = t; if (b->len() == 0) return; }
-    batches.push_back(b);
-    while (batches.size() >= 2) {
-      size_t m = batches.size();
-      if (batches[m - 2]->len() >= 2 * batches[m - 1]->len()) break;
-      BatchP merged = merge(batches[m - 2], batches[m - 1], vb());
-      batches.pop_back(); batches.pop_back();
-      if (merged->len()) batches.push_back(merged);
+
+  void refresh() {
+    batches.clear();
+    for (size_t i = merging.size(); i-- > 0;) {
+      const Layer& l = merging[i];
+      if (l.kind == Layer::IN_PROGRESS) {
+        if (l.a->len()) batches.push_back(l.a);
+        if (l.b->len()) batches.push_back(l.b);
+      } else if ((l.kind == Layer::SINGLE || l.kind == Layer::COMPLETE) && l.a && l.a->len()) {
+        batches.push_back(l.a);
+      }
     }
   }
-  BatchP consolidate() {   // spine_fueled.rs:583-600
+  static Layer begin_merge(BatchP b1, BatchP b2) {   // MergeState::begin_merge (:1106-1124)
+    Layer l;
+    if (b1 && b2) {
+      l.kind = Layer::IN_PROGRESS;
+      l.a = b1;
+      l.b = b2;
+      l.m = std::make_shared<Merger>(b1, b2);
+    } else {
+      l.kind = Layer::COMPLETE;
+      l.a = b1 ? b1 : b2;
+    }
+    return l;
+  }
+  void work(Layer& l, i64* fuel) {   // MergeVariant::work (:1176-1188)
+    if (l.kind != Layer::IN_PROGRESS) return;
+    l.m->work(vb(), fuel);
+    if (*fuel > 0) {
+      if (!l.m->complete()) {   // fuel left although the inputs are not exhausted cannot happen for a fuelled merger
+        i64 more = INT64_MAX;
+        while (!l.m->complete()) l.m->work(vb(), &more);
+      }
+      l.kind = Layer::COMPLETE;
+      l.a = l.m->out;
+      l.b = nullptr;
+      l.m = nullptr;
+    }
+  }
+  BatchP complete(Layer& l) {   // MergeState::complete (:1060-1066)
+    BatchP r;
+    if (l.kind == Layer::IN_PROGRESS) {
+      while (l.kind == Layer::IN_PROGRESS) { i64 fuel = INT64_MAX; work(l, &fuel); }
+    }
+    if (l.kind == Layer::SINGLE || l.kind == Layer::COMPLETE) r = l.a;
+    l = Layer();
+    return r;
+  }
+  void insert_at(BatchP batch, size_t index) {   // (:889-908)
+    while (merging.size() <= index) merging.push_back(Layer());
+    Layer& l = merging[index];
+    if (l.kind == Layer::VACANT) { l.kind = Layer::SINGLE; l.a = batch; }
+    else if (l.kind == Layer::SINGLE) { BatchP old = l.a; l = begin_merge(old, batch); }
+    else { fprintf(stderr, "oracle spine: attempted to insert a batch into an incomplete merge\n"); abort(); }   // panic! (:904)
+  }
+  void apply_fuel(i64 fuel_each) {   // (:856-882)
+    for (size_t index = 0; index < merging.size(); index++) {
+      i64 fuel = fuel_each;
+      work(merging[index], &fuel);
+      if (merging[index].kind == Layer::COMPLETE) {
+        BatchP done = complete(merging[index]);
+        insert_at(done, index + 1);
+      }
+    }
+  }
+  void roll_up(size_t index) {   // (:819-846)
+    while (merging.size() <= index) merging.push_back(Layer());
+    bool any = false;
+    for (size_t i = 0; i < index; i++) any = any || merging[i].kind != Layer::VACANT;
+    if (!any) return;
+    BatchP merged;
+    for (size_t i = 0; i < index; i++) {
+      insert_at(merged, i);
+      merged = complete(merging[i]);
+    }
+    insert_at(merged, index);
+    if (merging[index].is_double()) {
+      BatchP m2 = complete(merging[index]);
+      insert_at(m2, index + 1);
+    }
+  }
+  void tidy_layers() {   // (:916-974)
+    if (merging.empty()) return;
+    size_t length = merging.size();
+    if (merging[length - 1].kind != Layer::SINGLE) return;
+    size_t len = merging[length - 1].len(), appropriate = 0;
+    while (((size_t)1 << appropriate) < len) appropriate++;
+    while (appropriate < length - 1) {
+      Layer& below = merging[length - 2];
+      if (below.kind == Layer::VACANT || (below.kind == Layer::SINGLE && !below.a)) {
+        merging.erase(merging.begin() + (length - 2));
+        length = merging.size();
+      } else if (below.kind == Layer::SINGLE) {
+        u64 smaller = 0;
+        for (size_t i = 0; i + 2 < length; i++) {
+          if (merging[i].kind == Layer::SINGLE) smaller += 1ull << i;
+          else if (merging[i].is_double()) smaller += 2ull << i;
+        }
+        if (smaller <= (1ull << length) / 8) {
+          BatchP batch = below.a;
+          merging.erase(merging.begin() + (length - 2));
+          insert_at(batch, length - 2);
+        }
+        return;
+      } else {
+        return;
+      }
+    }
+  }
+  void introduce_batch(BatchP batch, size_t batch_index) {   // (:728-812)
+    i64 fuel = batch_index >= 59 ? INT64_MAX : (i64)((8ull << batch_index) * effort);
+    apply_fuel(fuel);
+    roll_up(batch_index);
+    insert_at(batch, batch_index);
+    tidy_layers();
+  }
+  bool reduced() const {   // (:663-680)
+    int non_empty = 0;
+    for (const Layer& l : merging) {
+      if (l.is_double()) return false;
+      if (l.len() > 0) non_empty++;
+      if (non_empty > 1) return false;
+    }
+    return true;
+  }
+  void insert(BatchP b) {   // Trace::insert (:605-634)
+    if (b->len() == 0) return;
+    if (has_bound) { BatchP t = truncate_keys_below(*b, bound); if (t) b = t; }
+    size_t index = 0;
+    while (((size_t)1 << index) < b->len()) index++;
+    introduce_batch(b, index);
+    refresh();
+  }
+  void exert(i64* effort_) {   // Trace::exert (:561-581)
+    tidy_layers();
+    if (!reduced()) {
+      bool any_double = false;
+      for (const Layer& l : merging) any_double = any_double || l.is_double();
+      if (any_double) apply_fuel(*effort_);
+      else {
+        size_t level = 0;
+        while ((1ull << level) < (u64)(*effort_ > 0 ? *effort_ : 1) && level < 62) level++;
+        introduce_batch(nullptr, level);
+      }
+    }
+    refresh();
+  }
+  // A consolidated read of the trace: the merge of everything a cursor sees, the value bound applied.
+  // (Trace::consolidate (:583-600) consumes the trace; this leaves the layers as they are.)
+  BatchP consolidate() {
     BatchP acc = std::make_shared<Batch>(s);
     for (auto& b : batches) acc = merge(acc, b, vb());
     return acc;
   }
-  void truncate(const u64* key) {   // spine_fueled.rs:223-233
+  void truncate(const u64* key) {   // truncate_keys_below (:223-233)
     if (has_bound && cmp_tuples(s.lane_types, s.n_key_lanes, key, bound) <= 0) return;   // bound = max(old, new)
+    for (Layer& l : merging) { i64 fuel = INT64_MAX; while (l.kind == Layer::IN_PROGRESS) work(l, &fuel); }   // complete_merges (:977-985)
     has_bound = true;
     for (int l = 0; l < s.n_key_lanes; l++) bound[l] = key[l];
-    std::vector<BatchP> keep;
-    for (auto& b : batches) {
-      BatchP t = truncate_keys_below(*b, bound);
-      if (!t) t = b;
-      if (t->len()) keep.push_back(t);
+    for (Layer& l : merging) {   // map_batches_mut (:988-1004)
+      if ((l.kind == Layer::SINGLE || l.kind == Layer::COMPLETE) && l.a) {
+        BatchP t = truncate_keys_below(*l.a, bound);
+        if (t) l.a = t;
+      }
     }
-    batches.swap(keep);
+    refresh();
   }
   // truncate_values_below (spine_fueled.rs:644-652): the bound only grows; it is
   // applied by later merges (:866, :911, :981), contents below it are undefined.
@@ -439,20 +599,6 @@ struct Spine {
     if (!has_vbound || cmp_tuples(ty, s.n_val_lanes, val, vbound) > 0)
       for (int l = 0; l < s.n_val_lanes; l++) vbound[l] = val[l];
     has_vbound = true;
-  }
-  // exert (spine_fueled.rs:627-634 -> apply_fuel): this spine merges eagerly, so
-  // there is never an in-progress merge; effort buys extra compaction instead —
-  // the two newest batches are merged while their size fits the effort.
-  void exert(i64* effort) {
-    while (batches.size() >= 2) {
-      size_t m = batches.size();
-      i64 cost = (i64)(batches[m - 2]->len() + batches[m - 1]->len());
-      if (cost > *effort) break;
-      BatchP merged = merge(batches[m - 2], batches[m - 1], vb());
-      batches.pop_back(); batches.pop_back();
-      if (merged->len()) batches.push_back(merged);
-      *effort -= cost;
-    }
   }
   size_t len() const { size_t n = 0; for (auto& b : batches) n += b->len(); return n; }
 };

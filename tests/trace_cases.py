@@ -122,7 +122,10 @@ def run_truncate_value_bounded_memory(be, seed=3):
         tr.insert(be.batch_from_rows(s, rows))
         tr.truncate_values_below([i * 20])
         if i % 10 == 9:
-            tr.exert(1 << 40)   # compaction applies the bound to every batch
+            for _ in range(64):   # Trace::exert until reduced (the loop of Trace::consolidate, spine_fueled.rs:583-589):
+                tr.exert(1 << 40)   # the merges apply the bound
+                if tr.stats()[1] <= 1:
+                    break
             n_tuples, _ = tr.stats()
             # live window: values in [i*20, i*20+100) for 50 keys
             assert n_tuples <= 50 * 200, n_tuples
@@ -192,19 +195,49 @@ def run_merger_fuel(be, seed=5, schema=None, n=3000, fuels=(1, 7, 100, 1000, 1 <
 
 
 def run_spine_exert(be, seed=6):
+    """Trace::exert (spine_fueled.rs:561-581): effort moves merges along without changing what cursors see; with
+    unbounded effort, repeated until the spine is reduced (the loop of Trace::consolidate, :583-589), one batch is left."""
     rng = np.random.default_rng(seed)
     s = Schema("u", "u")
     tr, ref = Spine(be, s), Model(s)
-    for n in (4000, 1500, 600, 200, 70, 20, 5):   # geometric sizes: no merge on insert
+    for n in (4000, 1500, 600, 200, 70, 20, 5):
         rows = rand_rows(rng, n, 1 << 20, 1 << 20, 2)
         tr.insert(be.batch_from_rows(s, rows))
         ref.insert(rows)
-    _, nb0 = tr.stats()
-    assert nb0 > 2
-    left = tr.exert(10)            # too little for any pair
-    assert left == 10 and tr.stats()[1] == nb0
-    left = tr.exert(1 << 40)       # everything collapses into one batch
-    assert tr.stats()[1] == 1 and left < (1 << 40)
+    n0, nb0 = tr.stats()
+    assert nb0 >= 2
+    tr.exert(10)                   # a little effort: contents unchanged
+    assert signed_rows(tr.consolidate()) == ref.rows()
+    for _ in range(64):
+        tr.exert(1 << 40)
+        if tr.stats()[1] <= 1:
+            break
+    assert tr.stats()[1] == 1
+    assert signed_rows(tr.consolidate()) == ref.rows()
+    # inserting after compaction keeps working
+    rows = rand_rows(rng, 100, 1 << 20, 1 << 20, 2)
+    tr.insert(be.batch_from_rows(s, rows))
+    ref.insert(rows)
+    assert signed_rows(tr.consolidate()) == ref.rows()
+
+
+def run_spine_schedule(be, seed=8):
+    """The fuelled merge schedule (spine_fueled.rs:728-974): many inserts of mixed sizes — the number of batches a
+    cursor has to visit stays logarithmic (at most two per layer), the contents always equal the model."""
+    rng = np.random.default_rng(seed)
+    s = Schema("u", "u")
+    tr, ref = Spine(be, s), Model(s)
+    total = 0
+    for i in range(120):
+        n = int(rng.choice([1, 3, 40, 700, 5000]))
+        rows = rand_rows(rng, n, 1 << 12, 1 << 8, 2)
+        tr.insert(be.batch_from_rows(s, rows))
+        ref.insert(rows)
+        total += n
+        n_tuples, nb = tr.stats()
+        assert nb <= 2 * (total.bit_length() + 2), (i, nb, total)
+        if i % 7 == 0:
+            assert signed_rows(tr.consolidate()) == ref.rows(), i
     assert signed_rows(tr.consolidate()) == ref.rows()
 
 
@@ -220,4 +253,5 @@ ALL_CASES = {
     "merger_fuel_zset": lambda be: run_merger_fuel(be, seed=16, schema=Schema("i")),
     "merger_fuel_wide": lambda be: run_merger_fuel(be, seed=17, schema=Schema("uu", "iuu"), n=1200, fuels=(13, 500, 1 << 30)),
     "spine_exert": run_spine_exert,
+    "spine_schedule": run_spine_schedule,
 }
