@@ -105,6 +105,8 @@ _SIGS = {
     "spine_exert": [_P, _P, _I64P],
     "spine_len": [_P, _U64P, C.POINTER(C.c_uint32)],
     "spine_free": [_P],
+    "spine_save": [_P, _P, C.c_char_p],
+    "spine_load": [_P, C.c_char_p, _PP],
     "join_delta_trace": [_P, _P, _P, C.POINTER(CProj), C.c_int32, _PP],
     "join_batches": [_P, _P, _P, C.POINTER(CProj), _PP],
     "semijoin": [_P, _P, _P, _PP],

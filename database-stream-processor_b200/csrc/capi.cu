@@ -1,6 +1,7 @@
 // capi.cu — the extern "C" boundary declared in include/dbsp_b200.h, plus the
 // host-side Spine (trace) logic.  No CPU compute path lives here: every
 // data-touching call launches kernels from consolidate.cu / merge.cu / ops.cu.
+#include <cstdio>
 #include <cstdlib>
 
 #include "ops.cuh"
@@ -887,6 +888,112 @@ int32_t dbsp_spine_free(dbsp_spine* s) {
   if (!s) return DBSP_OK;
   spine_release(s);
   delete s;
+  return DBSP_OK;
+}
+
+// ---- checkpoint / resume (include/dbsp_b200.h "Checkpoint"; format shared with oracle/dbsp_oracle.cpp) -------------
+static const char SPINE_MAGIC[8] = {'D', 'B', 'S', 'P', 'S', 'P', 'N', '1'};
+static bool fwrite_all(FILE* f, const void* p, size_t n) { return n == 0 || fwrite(p, 1, n, f) == n; }
+static bool fread_all(FILE* f, void* p, size_t n) { return n == 0 || fread(p, 1, n, f) == n; }
+
+static int32_t save_batch(Ctx* ctx, FILE* f, const Batch* b, std::vector<u64>& stage) {
+  const u64 n = b ? b->n : 0;
+  const u64 present = b ? 1 : 0;
+  if (!fwrite_all(f, &present, 8) || !fwrite_all(f, &n, 8)) { set_error("spine_save: write failed"); return DBSP_ERR_INVALID; }
+  if (!n) return DBSP_OK;
+  const int L = b->nl();
+  for (int l = 0; l <= L; l++) {
+    const void* src = l < L ? (const void*)b->col[l] : (const void*)b->w;
+    for (u64 off = 0; off < n; off += stage.size()) {
+      const u64 m = std::min<u64>(stage.size(), n - off);
+      CUDA_TRY(cudaMemcpyAsync(stage.data(), (const u64*)src + off, m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      ctx->d2h_bytes += m * 8;
+      if (!fwrite_all(f, stage.data(), m * 8)) { set_error("spine_save: write failed"); return DBSP_ERR_INVALID; }
+    }
+  }
+  return DBSP_OK;
+}
+static int32_t load_batch(Ctx* ctx, FILE* f, const dbsp_schema& sc, Batch** out, std::vector<u64>& stage) {
+  u64 present = 0, n = 0;
+  *out = nullptr;
+  if (!fread_all(f, &present, 8) || !fread_all(f, &n, 8)) { set_error("spine_load: truncated file"); return DBSP_ERR_INVALID; }
+  if (!present) return DBSP_OK;
+  if (!n) { *out = batch_new_empty(ctx, sc); return DBSP_OK; }
+  Batch* b;
+  MCols oc;
+  i64* ow;
+  TRY(batch_alloc(ctx, sc, n, &b, &oc, &ow));
+  const int L = sc.n_key_lanes + sc.n_val_lanes;
+  for (int l = 0; l <= L; l++) {
+    u64* dst = l < L ? oc.c[l] : (u64*)ow;
+    for (u64 off = 0; off < n; off += stage.size()) {
+      const u64 m = std::min<u64>(stage.size(), n - off);
+      if (!fread_all(f, stage.data(), m * 8)) { batch_unref(b); set_error("spine_load: truncated file"); return DBSP_ERR_INVALID; }
+      cudaError_t e = cudaMemcpyAsync(dst + off, stage.data(), m * 8, cudaMemcpyHostToDevice, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess) { batch_unref(b); set_error(cudaGetErrorString(e)); return DBSP_ERR_CUDA; }
+      ctx->h2d_bytes += m * 8;
+    }
+  }
+  *out = b;
+  return DBSP_OK;
+}
+
+int32_t dbsp_spine_save(dbsp_ctx* ctx, const dbsp_spine* s, const char* path) { ENTER(ctx);
+  FILE* f = fopen(path, "wb");
+  if (!f) { set_error(std::string("spine_save: cannot open ") + path); return DBSP_ERR_INVALID; }
+  std::vector<u64> stage((size_t)8 << 20);   // 64 MiB staging
+  u64 hdr[4] = {s->has_bound ? 1ull : 0ull, s->has_vbound ? 1ull : 0ull, s->effort, (u64)s->merging.size()};
+  bool ok = fwrite_all(f, SPINE_MAGIC, 8) && fwrite_all(f, &s->s, sizeof(dbsp_schema)) && fwrite_all(f, hdr, sizeof(hdr)) &&
+            fwrite_all(f, s->bound, sizeof(u64) * MAXL) && fwrite_all(f, s->vbound, sizeof(u64) * MAXL);
+  int32_t rc = ok ? DBSP_OK : DBSP_ERR_INVALID;
+  for (size_t i = 0; rc == DBSP_OK && i < s->merging.size(); i++) {
+    const SpineLevel& l = s->merging[i];
+    u64 lh[2] = {(u64)l.kind, (u64)l.remaining};
+    if (!fwrite_all(f, lh, sizeof(lh))) { rc = DBSP_ERR_INVALID; break; }
+    rc = save_batch(ctx, f, l.a, stage);
+    if (rc == DBSP_OK) rc = save_batch(ctx, f, l.b, stage);
+  }
+  if (fclose(f) != 0 && rc == DBSP_OK) rc = DBSP_ERR_INVALID;
+  if (rc == DBSP_ERR_INVALID && !ok) set_error("spine_save: write failed");
+  return rc;
+}
+int32_t dbsp_spine_load(dbsp_ctx* ctx, const char* path, dbsp_spine** out) { ENTER(ctx);
+  FILE* f = fopen(path, "rb");
+  if (!f) { set_error(std::string("spine_load: cannot open ") + path); return DBSP_ERR_INVALID; }
+  std::vector<u64> stage((size_t)8 << 20);
+  char magic[8];
+  u64 hdr[4];
+  dbsp_spine* sp = new dbsp_spine();
+  sp->ctx = ctx;
+  int32_t rc = DBSP_OK;
+  if (!fread_all(f, magic, 8) || memcmp(magic, SPINE_MAGIC, 8) != 0 || !fread_all(f, &sp->s, sizeof(dbsp_schema)) ||
+      !fread_all(f, hdr, sizeof(hdr)) || !fread_all(f, sp->bound, sizeof(u64) * MAXL) || !fread_all(f, sp->vbound, sizeof(u64) * MAXL)) {
+    set_error("spine_load: not a spine snapshot");
+    rc = DBSP_ERR_INVALID;
+  }
+  if (rc == DBSP_OK) {
+    sp->has_bound = hdr[0] != 0;
+    sp->has_vbound = hdr[1] != 0;
+    sp->effort = hdr[2] ? hdr[2] : 1;
+    if (hdr[3] > 64) { set_error("spine_load: corrupt layer count"); rc = DBSP_ERR_INVALID; }
+  }
+  for (u64 i = 0; rc == DBSP_OK && i < hdr[3]; i++) {
+    u64 lh[2];
+    if (!fread_all(f, lh, sizeof(lh)) || lh[0] > (u64)SpineLevel::COMPLETE) { set_error("spine_load: truncated file"); rc = DBSP_ERR_INVALID; break; }
+    SpineLevel l;
+    l.kind = (SpineLevel::Kind)lh[0];
+    l.remaining = (i64)lh[1];
+    rc = load_batch(ctx, f, sp->s, &l.a, stage);
+    if (rc == DBSP_OK) rc = load_batch(ctx, f, sp->s, &l.b, stage);
+    if (rc == DBSP_OK && l.kind == SpineLevel::IN_PROGRESS && (!l.a || !l.b)) { set_error("spine_load: corrupt layer"); rc = DBSP_ERR_INVALID; }
+    sp->merging.push_back(l);
+  }
+  fclose(f);
+  if (rc != DBSP_OK) { spine_release(sp); delete sp; return rc; }
+  spine_refresh_view(sp);
+  *out = sp;
   return DBSP_OK;
 }
 

@@ -304,11 +304,25 @@ class Upload:
 class Spine:
     """Owning handle of a trace (trace/spine_fueled.rs:107-119)."""
 
-    def __init__(self, be: "Backend", schema: Schema):
+    def __init__(self, be: "Backend", schema: Schema, _handle=None):
         self.be, self.schema = be, schema
+        if _handle is not None:
+            self.h = _handle
+            return
         h = C.c_void_p()
         be.api.call("spine_new", be.ctx, C.byref(schema.c()), C.byref(h))
         self.h = h.value
+
+    def save(self, path: str):
+        """Checkpoint the trace to `path` (dbsp_spine_save)."""
+        self.be.api.call("spine_save", self.be.ctx, self.h, str(path).encode())
+
+    @staticmethod
+    def load(be: "Backend", path: str, schema: Schema) -> "Spine":
+        """Resume a trace from a checkpoint written by save() — by this library or by the oracle."""
+        h = C.c_void_p()
+        be.api.call("spine_load", be.ctx, str(path).encode(), C.byref(h))
+        return Spine(be, schema, _handle=h.value)
 
     def __del__(self):
         try:

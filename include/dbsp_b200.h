@@ -285,6 +285,14 @@ int32_t dbsp_spine_len(const dbsp_spine* s, uint64_t* n_tuples,
                        uint32_t* n_batches);
 int32_t dbsp_spine_free(dbsp_spine* s);
 
+/* Checkpoint / resume of a trace: the device-side replacement of the RocksDB-backed
+ * PersistentTrace (crates/dbsp/src/trace/persistent/) for snapshots.  One little-endian file: magic "DBSPSPN1",
+ * the schema, key / value bounds, effort, then every layer of the spine (spine_fueled.rs:1012-1027: Vacant /
+ * Single / Double{InProgress, Complete}) with its batches as flat lanes + weights and, for a merge in progress,
+ * the fuel still owed — so a loaded spine resumes the same merge schedule.  The format is shared with the oracle. */
+int32_t dbsp_spine_save(dbsp_ctx* ctx, const dbsp_spine* s, const char* path);
+int32_t dbsp_spine_load(dbsp_ctx* ctx, const char* path, dbsp_spine** out);
+
 /* ---- operators ------------------------------------------------------ */
 /* JoinTrace::eval (operator/join.rs:732-863), Time = (): delta joined with
  * every batch of the trace, weights multiplied, join_func = proj, result

@@ -1227,6 +1227,102 @@ int32_t orc_shard_partition(orc_ctx*, const orc_batch* b, uint32_t P, orc_batch*
   return DBSP_OK;
 }
 
+// Checkpoint / resume of a trace: the file format of dbsp_spine_save (include/dbsp_b200.h), so that a snapshot
+// written by either library loads in the other.
+static const char SPINE_MAGIC[8] = {'D', 'B', 'S', 'P', 'S', 'P', 'N', '1'};
+static bool wr(FILE* f, const void* p, size_t n) { return n == 0 || fwrite(p, 1, n, f) == n; }
+static bool rd(FILE* f, void* p, size_t n) { return n == 0 || fread(p, 1, n, f) == n; }
+static bool save_flat(FILE* f, const BatchP& b) {
+  u64 present = b ? 1 : 0, n = b ? b->len() : 0;
+  if (!wr(f, &present, 8) || !wr(f, &n, 8)) return false;
+  if (!n) return true;
+  const Batch& B = *b;
+  const int nk = B.s.n_key_lanes, nv = B.s.n_val_lanes;
+  std::vector<u64> lane(n);
+  for (int l = 0; l < nk; l++) {   // flat rows: every key repeated over its value range
+    size_t o = 0;
+    for (size_t k = 0; k < B.K.n; k++) { size_t lo, hi; B.vrange(k, lo, hi); for (size_t v = lo; v < hi; v++) lane[o++] = B.K.c[l][k]; }
+    if (!wr(f, lane.data(), n * 8)) return false;
+  }
+  for (int l = 0; l < nv; l++) if (!wr(f, B.V.c[l].data(), n * 8)) return false;
+  return wr(f, B.w.data(), n * 8);
+}
+static bool load_flat(FILE* f, const dbsp_schema& sc, BatchP* out, bool* present_out) {
+  u64 present = 0, n = 0;
+  if (!rd(f, &present, 8) || !rd(f, &n, 8)) return false;
+  *present_out = present != 0;
+  *out = nullptr;
+  if (!present) return true;
+  const int L = sc.n_key_lanes + sc.n_val_lanes;
+  std::vector<std::vector<u64>> cols((size_t)L, std::vector<u64>(n));
+  std::vector<i64> w(n);
+  for (int l = 0; l < L; l++) if (!rd(f, cols[(size_t)l].data(), n * 8)) return false;
+  if (!rd(f, w.data(), n * 8)) return false;
+  Builder bld(sc);
+  u64 key[MAXL], val[MAXL];
+  for (u64 i = 0; i < n; i++) {
+    for (int l = 0; l < sc.n_key_lanes; l++) key[l] = cols[(size_t)l][i];
+    for (int l = 0; l < sc.n_val_lanes; l++) val[l] = cols[(size_t)(sc.n_key_lanes + l)][i];
+    bld.push(key, val, w[i]);
+  }
+  *out = bld.done();
+  return true;
+}
+int32_t orc_spine_save(orc_ctx*, const orc_spine* sp, const char* path) {
+  const Spine& s = sp->s;
+  FILE* f = fopen(path, "wb");
+  if (!f) { g_err = "spine_save: cannot open file"; return DBSP_ERR_INVALID; }
+  u64 hdr[4] = {s.has_bound ? 1ull : 0ull, s.has_vbound ? 1ull : 0ull, (u64)s.effort, (u64)s.merging.size()};
+  bool ok = wr(f, SPINE_MAGIC, 8) && wr(f, &s.s, sizeof(dbsp_schema)) && wr(f, hdr, sizeof(hdr)) && wr(f, s.bound, 8 * MAXL) && wr(f, s.vbound, 8 * MAXL);
+  for (size_t i = 0; ok && i < s.merging.size(); i++) {
+    const Spine::Layer& l = s.merging[i];
+    // a merge in progress is written as its two inputs plus the fuel still owed (inputs not yet consumed)
+    u64 owed = 0;
+    if (l.kind == Spine::Layer::IN_PROGRESS) owed = (u64)(l.a->len() + l.b->len());
+    u64 lh[2] = {(u64)l.kind, owed};
+    ok = wr(f, lh, sizeof(lh)) && save_flat(f, l.a) && save_flat(f, l.kind == Spine::Layer::IN_PROGRESS ? l.b : nullptr);
+  }
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) { g_err = "spine_save: write failed"; return DBSP_ERR_INVALID; }
+  return DBSP_OK;
+}
+int32_t orc_spine_load(orc_ctx*, const char* path, orc_spine** out) {
+  FILE* f = fopen(path, "rb");
+  if (!f) { g_err = "spine_load: cannot open file"; return DBSP_ERR_INVALID; }
+  char magic[8];
+  dbsp_schema sc;
+  u64 hdr[4];
+  if (!rd(f, magic, 8) || memcmp(magic, SPINE_MAGIC, 8) != 0 || !rd(f, &sc, sizeof(sc)) || !rd(f, hdr, sizeof(hdr))) {
+    fclose(f);
+    g_err = "spine_load: not a spine snapshot";
+    return DBSP_ERR_INVALID;
+  }
+  orc_spine* sp = new orc_spine(sc);
+  Spine& s = sp->s;
+  bool ok = rd(f, s.bound, 8 * MAXL) && rd(f, s.vbound, 8 * MAXL) && hdr[3] <= 64;
+  s.has_bound = hdr[0] != 0;
+  s.has_vbound = hdr[1] != 0;
+  s.effort = hdr[2] ? (size_t)hdr[2] : 1;
+  for (u64 i = 0; ok && i < hdr[3]; i++) {
+    u64 lh[2];
+    Spine::Layer l;
+    bool pa = false, pb = false;
+    ok = rd(f, lh, sizeof(lh)) && lh[0] <= (u64)Spine::Layer::COMPLETE && load_flat(f, sc, &l.a, &pa) && load_flat(f, sc, &l.b, &pb);
+    if (!ok) break;
+    l.kind = (Spine::Layer::Kind)lh[0];
+    if (l.kind == Spine::Layer::IN_PROGRESS) {
+      if (!l.a || !l.b) { ok = false; break; }
+      l.m = std::make_shared<Merger>(l.a, l.b);   // the merge restarts; its inputs and its place in the schedule are kept
+    }
+    s.merging.push_back(l);
+  }
+  fclose(f);
+  if (!ok) { delete sp; g_err = "spine_load: truncated or corrupt file"; return DBSP_ERR_INVALID; }
+  s.refresh();
+  *out = sp;
+  return DBSP_OK;
+}
+
 // Communication entry points of the ABI.  The oracle is one worker: identity for world == 1 (shard.rs:111-114);
 // the multi-worker CPU runs use the in-process exchange of oracle/nexmark_workers.cpp / thread_workers.py.
 int32_t orc_comm_create(orc_ctx*, int32_t rank, int32_t world, u64, uint8_t* blob) {
