@@ -116,94 +116,58 @@ __global__ void k_pack(Cols cols, Plan p, int wd, const u32* idx, u64 n, u64* ke
   if (!idx) idx_out[i] = (u32)i;
 }
 
-__device__ __forceinline__ bool rows_differ(const Cols& cols, int L, u64 a, u64 b) {
-  for (int l = 0; l < L; l++)
-    if (cols.c[l][a] != cols.c[l][b]) return true;
-  return false;
-}
-
-// Head flags (row differs from its predecessor in sorted order) + gathered
-// weights; `counters` (optional) accumulate # non-heads and # zero weights.
-__global__ void k_heads(Cols cols, int L, int use_key, const u64* key, const u32* idx, const i64* w, u64 n, u32* flags,
-                        i64* ws, u64* counters) {
-  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned bad = 0;
-  if (counters && counters[2]) return;   // the sort raised its fallback flag: key / idx are not a permutation yet
-  if (i < n) {
-    u64 r = idx ? idx[i] : i;
-    bool head = true;
-    if (i > 0) head = use_key ? (key[i] != key[i - 1]) : rows_differ(cols, L, r, idx ? idx[i - 1] : i - 1);
-    i64 wt = w ? w[r] : 1;
-    if (flags) { flags[i] = head ? 1u : 0u; ws[i] = wt; }
-    bad = (!head ? 1u : 0u) | (wt == 0 ? 2u : 0u);
-  } else if (i == n && flags) {
-    flags[n] = 0;
-  }
-  if (counters) {
-    unsigned d = __ballot_sync(0xffffffffu, bad & 1u), z = __ballot_sync(0xffffffffu, bad & 2u);
-    if ((threadIdx.x & 31) == 0 && (d | z)) {
-      if (d) atomicAdd((unsigned long long*)&counters[0], (unsigned long long)__popc(d));
-      if (z) atomicAdd((unsigned long long*)&counters[1], (unsigned long long)__popc(z));
-    }
-  }
-}
-
 __device__ __forceinline__ u64 unpack_lane(const Plan& p, int l, u64 key) {
   u64 v = p.bits[l] ? ((key >> p.shift[l]) & p.mask[l]) : 0;
   return (v + p.mn[l]) ^ p.flip[l];
 }
 
-// Duplicate-free fast path: output row i = input row idx[i].
-__global__ void k_emit_unique(Cols cols, Plan p, const u64* key, const u32* idx, const i64* w, u64 n, MCols out,
-                              i64* out_w) {
-  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  u64 r = idx ? idx[i] : i;
-  if (p.use_key) {
-    u64 k = key[i];
-    for (int l = 0; l < p.L; l++) out.c[l][i] = unpack_lane(p, l, k);
-  } else {
-    for (int l = 0; l < p.L; l++) out.c[l][i] = cols.c[l][r];
-  }
-  out_w[i] = w ? w[r] : 1;
-}
-
 // ---------------------------------------------------------------------------
-// Reduce-by-key over rows that are already in sorted order (identity order, or
-// through the row ids of the radix sort): every run of equal rows becomes one
-// row carrying the sum of the run's weights; zero sums are dropped.  Two data
-// passes around a small per-tile scan:
-//   pass 0: per tile of RBK_TILE rows — #heads, weight of the rows before the
-//           first head (continuation of the run entering the tile), weight
-//           since the last head, #kept runs that lie entirely inside the tile;
-//   k_rbk_scan: carries the open run's weight across tiles (flag/sum monoid)
-//           and turns kept counts into output offsets;
-//   pass 1: recomputes the tile with its carry-in and writes the kept runs.
-// Replaces the dedup+retain of consolidate (consolidation/mod.rs:32-52).
-constexpr int RBK_THREADS = 256, RBK_R = 4, RBK_TILE = RBK_THREADS * RBK_R;
-struct RbkTile {
-  i64 pre, post;      // weight before the first head / since the last head (all rows if no head)
-  u32 nheads, inner_kept, closed_last, pad;
-};
-struct RbkCarry {
-  i64 carry_in;
-  u32 out_base, pad;
-};
+// k_reduce_emit — the dedup + retain of consolidate (consolidation/mod.rs:32-52) and the Builder
+// (ordered/mod.rs:874-888) in ONE pass over the rows in sorted order (identity order, or through the row ids of
+// the sort): every run of equal rows becomes one output row carrying the sum of the run's weights, zero sums are
+// dropped.  Per tile of RE_TILE rows:
+//   (1) head / tail flags and weights of the thread's rows; block scan with the (has-head, weight-since-last-head)
+//       monoid gives every row the weight of the run open before it inside the tile;
+//   (2) look-back #1 (same monoid, across tiles): the weight of the run that enters the tile.  A predecessor
+//       that contains a head ends the walk, so the usual distance is one tile;
+//   (3) run totals at the tails, kept flags (total != 0), block scan of the kept counts;
+//   (4) look-back #2 (plain sum): the tile's first output slot;
+//   (5) the kept rows are written (unpacked from the key word, or gathered through the row id), weights = totals.
+// Tiles take their index from a ticket, so every predecessor a look-back waits on is already running.
+constexpr int RE_THREADS = 256, RE_R = 4, RE_TILE = RE_THREADS * RE_R;
 struct HS {
   u32 h;
   i64 s;
 };
-struct HSOp {
-  __device__ __forceinline__ HS operator()(const HS& a, const HS& b) const {
-    HS r;
-    r.h = a.h | b.h;
-    r.s = b.h ? b.s : (i64)((u64)a.s + (u64)b.s);
-    return r;
-  }
+__device__ __forceinline__ HS hs_op(const HS& a, const HS& b) {   // a then b
+  HS r;
+  r.h = a.h | b.h;
+  r.s = b.h ? b.s : (i64)((u64)a.s + (u64)b.s);
+  return r;
+}
+// per-tile status: [0] aggregate {flag|h, s}, [1] inclusive prefix {flag|h, s}, [2] kept-count word (2-bit flag | value)
+struct ReStatus {
+  u64 agg_f, agg_s, pre_f, pre_s, cnt, pad_[3];
 };
+__device__ __forceinline__ u64 re_ld_acq(const u64* p) {
+  u64 v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void re_st_rel(u64* p, u64 v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u64 re_ld(const u64* p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void re_st(u64* p, u64 v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
-__device__ __forceinline__ bool rbk_differs(const Cols& cols, int L, int use_key, const u64* key, const u32* idx, u64 i,
-                                            u64 j) {
+__device__ __forceinline__ bool re_differs(const Cols& cols, int L, int use_key, const u64* key, const u32* idx, u64 i,
+                                           u64 j) {
   if (use_key) return key[i] != key[j];
   u64 a = idx ? idx[i] : i, b = idx ? idx[j] : j;
   for (int l = 0; l < L; l++)
@@ -211,133 +175,159 @@ __device__ __forceinline__ bool rbk_differs(const Cols& cols, int L, int use_key
   return false;
 }
 
-template <int PHASE>
-__global__ void __launch_bounds__(RBK_THREADS)
-k_rbk(Cols cols, Plan p, const u64* key, const u32* idx, const i64* w, u64 n, RbkTile* tiles, const RbkCarry* carry,
-      MCols out, i64* out_w) {
-  __shared__ HS s_warp_hs[RBK_THREADS / 32];
-  __shared__ u32 s_warp_u[RBK_THREADS / 32];
-  __shared__ i64 s_pre;
-  __shared__ u32 s_inner, s_closed;
+// result[0] = number of output rows; result[2] (the sort's fallback flag) != 0 on entry => nothing is done
+__global__ void __launch_bounds__(RE_THREADS)
+k_reduce_emit(Cols cols, Plan p, const u64* key, const u32* idx, const i64* w, u64 n, ReStatus* status, u32* ticket, MCols out,
+              i64* out_w, u64* result) {
+  __shared__ HS s_warp_hs[RE_THREADS / 32];
+  __shared__ u32 s_warp_u[RE_THREADS / 32];
+  __shared__ u32 s_tile;
+  __shared__ i64 s_cin;
+  __shared__ u64 s_base;
+  if (result[2]) return;   // the sort raised its fallback flag: key / idx are not a permutation yet
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const u64 tile_s = (u64)blockIdx.x * RBK_TILE;
-  const u64 tile_e = tile_s + RBK_TILE < n ? tile_s + RBK_TILE : n;
-  const u64 r0 = tile_s + (u64)tid * RBK_R;
-  if (tid == 0) { s_pre = 0; s_inner = 0; s_closed = 0; }
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const u32 tile = s_tile;
+  const u64 tile_s = (u64)tile * RE_TILE;
+  const u64 tile_e = tile_s + RE_TILE < n ? tile_s + RE_TILE : n;
+  const u64 r0 = tile_s + (u64)tid * RE_R;
 
-  // per-row head / tail flags and weights of this thread's rows
-  bool hd[RBK_R], tl[RBK_R], valid[RBK_R];
-  i64 wt[RBK_R];
+  bool hd[RE_R], tl[RE_R], valid[RE_R];
+  i64 wt[RE_R];
 #pragma unroll
-  for (int k = 0; k < RBK_R; k++) {
+  for (int k = 0; k < RE_R; k++) {
     const u64 i = r0 + k;
     valid[k] = i < tile_e;
     hd[k] = false; tl[k] = false; wt[k] = 0;
     if (valid[k]) {
-      hd[k] = (i == 0) || rbk_differs(cols, p.L, p.use_key, key, idx, i, i - 1);
+      hd[k] = (i == 0) || re_differs(cols, p.L, p.use_key, key, idx, i, i - 1);
       wt[k] = w ? w[idx ? idx[i] : i] : 1;
     }
   }
 #pragma unroll
-  for (int k = 0; k < RBK_R; k++) {
+  for (int k = 0; k < RE_R; k++) {
     const u64 i = r0 + k;
     if (valid[k]) {
-      if (k + 1 < RBK_R && r0 + k + 1 < tile_e) tl[k] = hd[k + 1];
-      else tl[k] = (i + 1 >= n) || rbk_differs(cols, p.L, p.use_key, key, idx, i + 1, i);
+      if (k + 1 < RE_R && r0 + k + 1 < tile_e) tl[k] = hd[k + 1];
+      else tl[k] = (i + 1 >= n) || re_differs(cols, p.L, p.use_key, key, idx, i + 1, i);
     }
   }
-  // thread aggregate: (has head, weight since last head / total)
+  // (1) thread aggregate and block scan with the flag/sum monoid
   HS agg; agg.h = 0; agg.s = 0;
-  i64 pre_t = 0;   // weight before this thread's first head
 #pragma unroll
-  for (int k = 0; k < RBK_R; k++) {
+  for (int k = 0; k < RE_R; k++) {
     if (!valid[k]) continue;
     if (hd[k]) { agg.h = 1; agg.s = wt[k]; }
-    else { agg.s = (i64)((u64)agg.s + (u64)wt[k]); if (!agg.h) pre_t = agg.s; }
+    else agg.s = (i64)((u64)agg.s + (u64)wt[k]);
   }
-  // block exclusive scan of the aggregates with the flag/sum monoid
-  HSOp op;
   HS incl = agg;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     HS v;
     v.h = __shfl_up_sync(0xffffffffu, incl.h, o);
     v.s = __shfl_up_sync(0xffffffffu, incl.s, o);
-    if (lane >= o) incl = op(v, incl);
+    if (lane >= o) incl = hs_op(v, incl);
   }
   if (lane == 31) s_warp_hs[wid] = incl;
   __syncthreads();
   HS wprefix; wprefix.h = 0; wprefix.s = 0;
-  for (int k = 0; k < wid; k++) wprefix = op(wprefix, s_warp_hs[k]);
+  for (int k = 0; k < wid; k++) wprefix = hs_op(wprefix, s_warp_hs[k]);
   HS excl_in_warp;
   excl_in_warp.h = __shfl_up_sync(0xffffffffu, incl.h, 1);
   excl_in_warp.s = __shfl_up_sync(0xffffffffu, incl.s, 1);
   if (lane == 0) { excl_in_warp.h = 0; excl_in_warp.s = 0; }
-  const HS excl = op(wprefix, excl_in_warp);   // open run before this thread, within the tile
+  const HS excl = hs_op(wprefix, excl_in_warp);   // open run before this thread, within the tile
 
-  const i64 cin = PHASE ? carry[blockIdx.x].carry_in : 0;
-  // running weight of the run open at this thread's first row
+  // (2) look-back #1: weight of the run entering the tile
+  if (tid == RE_THREADS - 1) {
+    const HS tile_agg = hs_op(wprefix, incl);   // inclusive over the whole tile
+    ReStatus* me = &status[tile];
+    HS carry; carry.h = 0; carry.s = 0;   // fold of the tiles before this one, as far back as needed
+    if (tile == 0) {
+      re_st(&me->pre_s, (u64)tile_agg.s);
+      re_st_rel(&me->pre_f, 2ull | ((u64)tile_agg.h << 2));
+    } else {
+      re_st(&me->agg_s, (u64)tile_agg.s);
+      re_st_rel(&me->agg_f, 1ull | ((u64)tile_agg.h << 2));
+      long long q = (long long)tile - 1;
+      while (true) {
+        const ReStatus* pr = &status[q];
+        HS v;
+        bool is_prefix;
+        while (true) {
+          const u64 pf = re_ld_acq(&pr->pre_f);
+          if (pf & 3) { v.h = (u32)((pf >> 2) & 1); v.s = (i64)re_ld(&pr->pre_s); is_prefix = true; break; }
+          const u64 af = re_ld_acq(&pr->agg_f);
+          if (af & 3) { v.h = (u32)((af >> 2) & 1); v.s = (i64)re_ld(&pr->agg_s); is_prefix = false; break; }
+        }
+        carry = hs_op(v, carry);
+        if (carry.h || is_prefix || q == 0) break;   // a head further back makes everything before it irrelevant
+        q--;
+      }
+      const HS pre = hs_op(carry, tile_agg);
+      re_st(&me->pre_s, (u64)pre.s);
+      re_st_rel(&me->pre_f, 2ull | ((u64)pre.h << 2));
+    }
+    s_cin = carry.s;
+  }
+  __syncthreads();
+  const i64 cin = s_cin;
+
+  // (3) run totals at the tails, kept flags
   i64 run = excl.h ? excl.s : (i64)((u64)excl.s + (u64)cin);
-  bool head_seen = excl.h != 0;
-  u32 kept = 0, inner = 0;
-  i64 tot[RBK_R];
-  bool kp[RBK_R];
+  u32 kept = 0;
+  i64 tot[RE_R];
+  bool kp[RE_R];
 #pragma unroll
-  for (int k = 0; k < RBK_R; k++) {
+  for (int k = 0; k < RE_R; k++) {
     kp[k] = false; tot[k] = 0;
     if (!valid[k]) continue;
-    if (hd[k]) { run = wt[k]; head_seen = true; }
+    if (hd[k]) run = wt[k];
     else run = (i64)((u64)run + (u64)wt[k]);
-    if (tl[k]) {
-      tot[k] = run;
-      if (PHASE) { kp[k] = run != 0; kept += kp[k]; }
-      else if (head_seen) inner += (run != 0);   // a run that lies entirely inside this tile
-    }
+    if (tl[k]) { tot[k] = run; kp[k] = run != 0; kept += kp[k]; }
   }
-
-  if (PHASE == 0) {
-    // tile aggregate
-    if (!excl.h) {   // no head before this thread in the tile: its leading rows continue the entering run
-      i64 c = agg.h ? pre_t : agg.s;
-      if (c) atomicAdd((unsigned long long*)&s_pre, (unsigned long long)c);
-    }
-    if (inner) atomicAdd(&s_inner, inner);
-    if (r0 < tile_e && r0 + RBK_R >= tile_e) {   // owner of the tile's last row
-      int lastk = (int)(tile_e - 1 - r0);
-      bool c = false;
-#pragma unroll
-      for (int k = 0; k < RBK_R; k++) if (k == lastk) c = tl[k];
-      s_closed = c ? 1u : 0u;
-    }
-    __syncthreads();
-    if (tid == RBK_THREADS - 1) {
-      HS tile = op(wprefix, incl);   // inclusive over the whole tile (this is the last thread)
-      RbkTile t;
-      t.pre = s_pre;
-      t.post = tile.s;
-      t.nheads = tile.h;
-      t.inner_kept = s_inner;
-      t.closed_last = s_closed;
-      t.pad = 0;
-      tiles[blockIdx.x] = t;
-    }
-    return;
-  }
-
-  // PHASE 1: ranks of the kept runs and output
   u32 kincl = kept;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    u32 v = __shfl_up_sync(0xffffffffu, kincl, o);
+    const u32 v = __shfl_up_sync(0xffffffffu, kincl, o);
     if (lane >= o) kincl += v;
   }
   if (lane == 31) s_warp_u[wid] = kincl;
   __syncthreads();
-  u32 woff = 0;
-  for (int k = 0; k < wid; k++) woff += s_warp_u[k];
-  u32 pos = carry[blockIdx.x].out_base + woff + kincl - kept;
+  u32 woff = 0, tile_kept = 0;
 #pragma unroll
-  for (int k = 0; k < RBK_R; k++) {
+  for (int k = 0; k < RE_THREADS / 32; k++) {
+    const u32 v = s_warp_u[k];
+    if (k < wid) woff += v;
+    tile_kept += v;
+  }
+  // (4) look-back #2: first output slot of the tile
+  if (tid == 0) {
+    ReStatus* me = &status[tile];
+    u64 base = 0;
+    if (tile == 0) {
+      re_st(&me->cnt, (2ull << 62) | (u64)tile_kept);
+    } else {
+      re_st(&me->cnt, (1ull << 62) | (u64)tile_kept);
+      long long q = (long long)tile - 1;
+      while (true) {
+        u64 v;
+        do { v = re_ld(&status[q].cnt); } while ((v >> 62) == 0);
+        base += v & ((1ull << 62) - 1);
+        if ((v >> 62) == 2) break;
+        q--;
+      }
+      re_st(&me->cnt, (2ull << 62) | (base + tile_kept));
+    }
+    s_base = base;
+    if (tile_e == n) result[0] = base + tile_kept;   // the last tile knows the total
+  }
+  __syncthreads();
+  // (5) output
+  u64 pos = s_base + woff + kincl - kept;
+#pragma unroll
+  for (int k = 0; k < RE_R; k++) {
     if (!kp[k]) continue;
     const u64 i = r0 + k;
     if (p.use_key) {
@@ -349,61 +339,6 @@ k_rbk(Cols cols, Plan p, const u64* key, const u32* idx, const i64* w, u64 n, Rb
     }
     out_w[pos] = tot[k];
     pos++;
-  }
-}
-
-// One CTA: carry the open run's weight across tiles and prefix-sum the kept counts.
-__global__ void k_rbk_scan(const RbkTile* tiles, u32 ntiles, RbkCarry* carry, u32* total_out) {
-  __shared__ HS s_hs[1024];
-  __shared__ u32 s_cnt[1024];
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const u32 chunk = (ntiles + nt - 1) / nt;
-  const u32 lo = min(ntiles, tid * chunk), hi = min(ntiles, lo + chunk);
-  HSOp op;
-  // element of tile t for the carry recurrence: carry_out = closes ? 0 : (h ? post : carry_in + pre)
-  auto elem = [&](const RbkTile& t) {
-    HS e;
-    const bool ends = t.closed_last != 0;
-    e.h = (t.nheads || ends) ? 1u : 0u;
-    e.s = ends ? 0 : (t.nheads ? t.post : t.pre);
-    return e;
-  };
-  HS agg; agg.h = 0; agg.s = 0;
-  for (u32 t = lo; t < hi; t++) agg = op(agg, elem(tiles[t]));
-  s_hs[tid] = agg;
-  __syncthreads();
-  if (tid == 0) {   // serial exclusive scan over <= 1024 chunk aggregates
-    HS run; run.h = 0; run.s = 0;
-    for (int k = 0; k < nt; k++) { HS v = s_hs[k]; s_hs[k] = run; run = op(run, v); }
-  }
-  __syncthreads();
-  HS cur = s_hs[tid];
-  u32 cnt = 0;
-  for (u32 t = lo; t < hi; t++) {
-    const RbkTile tl = tiles[t];
-    const i64 cin = cur.s;   // weight of the run open at the tile's first row (0 if none)
-    carry[t].carry_in = cin;
-    const bool ends_here = tl.nheads || tl.closed_last;
-    cnt += tl.inner_kept + ((ends_here && (i64)((u64)cin + (u64)tl.pre) != 0) ? 1u : 0u);
-    cur = op(cur, elem(tl));
-  }
-  s_cnt[tid] = cnt;
-  __syncthreads();
-  if (tid == 0) {
-    u32 run = 0;
-    for (int k = 0; k < nt; k++) { u32 v = s_cnt[k]; s_cnt[k] = run; run += v; }
-    *total_out = run;
-  }
-  __syncthreads();
-  u32 base = s_cnt[tid];
-  cur = s_hs[tid];
-  for (u32 t = lo; t < hi; t++) {
-    const RbkTile tl = tiles[t];
-    carry[t].out_base = base;
-    const i64 cin = cur.s;
-    const bool ends_here = tl.nheads || tl.closed_last;
-    base += tl.inner_kept + ((ends_here && (i64)((u64)cin + (u64)tl.pre) != 0) ? 1u : 0u);
-    cur = op(cur, elem(tl));
   }
 }
 
@@ -530,65 +465,49 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
     TRY(sort_rows(false));
   }
 
-  // ---- (4) epilogue -------------------------------------------------------------
-  // After a sort, duplicates are possible iff the input had any equal pair at
-  // all — unknown from the census (it only saw adjacent pairs) — so count.
-  u64 hc[3] = {n_dup, n_zero, 0};
-  if (n_inv != 0) {
-    for (int attempt = 0; attempt < 2; attempt++) {
-      {
-        ProfScope ps(ctx, KID_HEADS, n * (u64)(12 + (w ? 8 : 0)));
-        k_heads<<<nblk + 1, TB, 0, st>>>(cols, L, p.use_key, key_sorted, idx_cur, w, n, nullptr, nullptr, cnt);
-      }
-      LAUNCH_COUNT(ctx);
-      TRY(read_back(ctx, cnt, 3, hc));
-      if (hc[2] == 0) break;
-      // a bucket did not fit a shared-memory chunk (heavy key skew): redo with the plain LSD sequence
-      if (attempt == 1) { set_error("consolidate: sort fallback failed"); return DBSP_ERR_CUDA; }
-      CUDA_TRY(cudaMemsetAsync(cnt, 0, 24, st));
-      TRY(sort_rows(true));
-    }
-  }
-
+  // ---- (4) epilogue: one pass — sum runs of equal rows, drop zero sums, build the batch -------
+  const u32 ntiles = (u32)((n + RE_TILE - 1) / RE_TILE);
+  BufP tbuf;
+  TRY(dev_alloc(ctx, (size_t)ntiles * sizeof(ReStatus) + 16, &tbuf));
+  ReStatus* status = (ReStatus*)tbuf->p;
+  u32* ticket = (u32*)(status + ntiles);
+  Batch* b = nullptr;
   MCols oc;
   i64* ow;
-  if (hc[0] == 0 && hc[1] == 0) {
-    Batch* b;
-    TRY(batch_alloc(ctx, s, n, &b, &oc, &ow));
+  TRY(batch_alloc(ctx, s, n, &b, &oc, &ow));   // capacity n: the exact count comes back with the kernel
+  u64 res[3] = {0, 0, 0};
+  for (int attempt = 0; attempt < 2; attempt++) {
+    if (n_inv == 0) CUDA_TRY(cudaMemsetAsync(cnt, 0, 24, st));
+    CUDA_TRY(cudaMemsetAsync(tbuf->p, 0, (size_t)ntiles * sizeof(ReStatus) + 16, st));
     {
-      ProfScope ps(ctx, KID_EMIT, n * (u64)(12 + (w ? 8 : 0)) + n * (u64)(L + 1) * 8);
-      k_emit_unique<<<nblk, TB, 0, st>>>(cols, p, key_sorted, idx_cur, w, n, oc, ow);
+      ProfScope pseg(ctx, KID_SEG_REDUCE, n * (u64)((p.use_key ? 12 : (L * 8 + (idx_cur ? 4 : 0))) + (w ? 8 : 0)) + n * (u64)(L + 1) * 8);
+      k_reduce_emit<<<ntiles, RE_THREADS, 0, st>>>(cols, p, key_sorted, idx_cur, w, n, status, ticket, oc, ow, cnt);
     }
     LAUNCH_COUNT(ctx);
-    *out = b;
-    return DBSP_OK;
+    int32_t rc = read_back(ctx, cnt, 3, res);
+    if (rc) { batch_unref(b); return rc; }
+    if (res[2] == 0) break;
+    // a bucket did not fit a shared-memory chunk (heavy key skew): redo the sort with the plain LSD sequence
+    if (attempt == 1 || n_inv == 0) { batch_unref(b); set_error("consolidate: sort fallback failed"); return DBSP_ERR_CUDA; }
+    CUDA_TRY(cudaMemsetAsync(cnt, 0, 24, st));
+    rc = sort_rows(true);
+    if (rc) { batch_unref(b); return rc; }
   }
-
-  // duplicates and/or zero weights: fused reduce-by-key over the sorted order
-  const u32 ntiles = (u32)((n + RBK_TILE - 1) / RBK_TILE);
-  BufP tbuf;
-  TRY(dev_alloc(ctx, (size_t)ntiles * (sizeof(RbkTile) + sizeof(RbkCarry)) + 64, &tbuf));
-  RbkTile* tiles = (RbkTile*)tbuf->p;
-  RbkCarry* carry = (RbkCarry*)(tiles + ntiles);
-  u32* d_total = (u32*)(carry + ntiles);
-  MCols none;
-  for (int l = 0; l < MAXL; l++) none.c[l] = nullptr;
-  {
-    ProfScope pseg(ctx, KID_SEG_REDUCE, 0);
-    k_rbk<0><<<ntiles, RBK_THREADS, 0, st>>>(cols, p, key_sorted, idx_cur, w, n, tiles, nullptr, none, nullptr);
-    k_rbk_scan<<<1, 1024, 0, st>>>(tiles, ntiles, carry, d_total);
-    ctx->kernel_launches += 2;
+  const u64 nout = res[0];
+  if (nout == 0) { batch_unref(b); *out = batch_new_empty(ctx, s); return DBSP_OK; }
+  b->n = nout;
+  if (nout * 2 < n && n > 4096) {
+    // heavy reduction: do not keep a capacity-n buffer alive behind a small batch
+    Batch* small;
+    MCols sc;
+    i64* sw;
+    int32_t rc = batch_alloc(ctx, s, nout, &small, &sc, &sw);
+    if (rc) { batch_unref(b); return rc; }
+    for (int l = 0; l < L; l++) cudaMemcpyAsync(sc.c[l], oc.c[l], nout * 8, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(sw, ow, nout * 8, cudaMemcpyDeviceToDevice, st);
+    batch_unref(b);
+    b = small;
   }
-  u32 nout;
-  TRY(read_back32(ctx, d_total, &nout));
-  if (nout == 0) { *out = batch_new_empty(ctx, s); return DBSP_OK; }
-  Batch* b;
-  TRY(batch_alloc(ctx, s, nout, &b, &oc, &ow));
-  {
-    ProfScope pseg(ctx, KID_SEG_REDUCE, n * (u64)(L + 1) * 8 * 2 + (u64)nout * (L + 1) * 8);
-    k_rbk<1><<<ntiles, RBK_THREADS, 0, st>>>(cols, p, key_sorted, idx_cur, w, n, tiles, carry, oc, ow);
-  }
-  LAUNCH_COUNT(ctx);
   *out = b;
   return DBSP_OK;
 }

@@ -165,44 +165,87 @@ __global__ void k_row_counts(const u32* head_exscan, const u32* ktot, u64 nd, u3
 // needs no sort.  proj_mode 1: join_func(k, v1, v2) with filter
 // (join.rs:751-787), weight w1*w2, rejected rows keep their slot with weight 0;
 // proj_mode 0: copy the trace row (gather of a key group).
-__global__ void k_probe_fill(Cols D, const i64* wD, u64 nd, BatchRefs tr, int nk, int nvD, int nvT, const u32* lo,
-                             const u32* cnt, const u32* ki, const u32* exscan, u64 total, int proj_mode,
-                             int delta_is_left, dbsp_proj proj, MCols out, i64* out_w) {
-  u64 o = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= total) return;
-  // largest i with exscan[i] <= o
-  u64 a = 0, b = nd;
-  while (b - a > 1) {
-    u64 mid = (a + b) >> 1;
-    if (exscan[mid] <= o) a = mid; else b = mid;
+// Load balancing: a CTA owns PF_TILE consecutive output slots whatever the fan-out of the keys behind them
+// (skew-proof).  Two threads bisect the scanned match counts for the delta rows of the tile's first and last
+// slot; the counts in between are staged in shared memory, where every slot finds its delta row — one global
+// bisection per 1024 slots instead of one per slot.  Consecutive slots read consecutive trace rows and
+// the same / adjacent delta rows, and write consecutive output rows.
+constexpr int PF_TILE = 1024, PF_SMEM_ROWS = 3072;
+__global__ void __launch_bounds__(256)
+k_probe_fill(Cols D, const i64* wD, u64 nd, BatchRefs tr, int nk, int nvD, int nvT, const u32* lo, const u32* cnt,
+             const u32* ki, const u32* exscan, u64 total, int proj_mode, int delta_is_left, dbsp_proj proj, MCols out,
+             i64* out_w) {
+  __shared__ u32 s_ex[PF_SMEM_ROWS + 1];
+  __shared__ u64 s_rows[2];
+  const int tid = threadIdx.x;
+  const u64 o0 = (u64)blockIdx.x * PF_TILE;
+  if (o0 >= total) return;
+  const u64 o1 = o0 + PF_TILE < total ? o0 + PF_TILE : total;
+  if (tid < 2) {   // largest i with exscan[i] <= target
+    const u64 target = tid == 0 ? o0 : o1 - 1;
+    u64 a = 0, b = nd;
+    while (b - a > 1) {
+      const u64 mid = (a + b) >> 1;
+      if (exscan[mid] <= target) a = mid; else b = mid;
+    }
+    s_rows[tid] = a;
   }
-  const u64 i = a;
-  u32 r = (u32)(o - exscan[i]);
-  const u64 kbase = (u64)ki[i] * tr.nb;
-  int bb = 0;
-  while (bb < tr.nb - 1 && r >= cnt[kbase + bb]) { r -= cnt[kbase + bb]; bb++; }
-  const Cols& T = tr.b[bb].c;
-  const u64 t = (u64)lo[kbase + bb] + r;
-  u64 row[MAXL];
-  i64 wout;
-  int nl_out;
-  bool ok = true;
-  if (proj_mode == 0) {
-    nl_out = nk + nvT;
-    for (int l = 0; l < nl_out; l++) row[l] = T.c[l][t];
-    wout = tr.b[bb].w[t];
-  } else {
-    u64 key[MAXL], dv[MAXL], tv[MAXL];
-    for (int l = 0; l < nk; l++) key[l] = D.c[l][i];
-    for (int l = 0; l < nvD; l++) dv[l] = D.c[nk + l][i];
-    for (int l = 0; l < nvT; l++) tv[l] = T.c[nk + l][t];
-    Env e = delta_is_left ? Env{key, dv, tv} : Env{key, tv, dv};
-    ok = project(proj, e, row);
-    nl_out = proj.out_schema.n_key_lanes + proj.out_schema.n_val_lanes;
-    wout = (i64)((u64)wD[i] * (u64)tr.b[bb].w[t]);
+  __syncthreads();
+  const u64 row_lo = s_rows[0], row_hi = s_rows[1];
+  const u64 nr = row_hi - row_lo + 1;
+  const bool staged = nr <= (u64)PF_SMEM_ROWS;
+  if (staged)
+    for (u64 k = tid; k <= nr; k += 256) s_ex[k] = exscan[row_lo + k];
+  __syncthreads();
+#pragma unroll 1
+  for (int qq = 0; qq < PF_TILE / 256; qq++) {
+    const u64 o = o0 + (u64)qq * 256 + tid;
+    if (o >= o1) break;
+    u64 i;
+    u32 r;
+    if (staged) {
+      u32 a = 0, b = (u32)nr;
+      while (b - a > 1) {
+        const u32 mid = (a + b) >> 1;
+        if (s_ex[mid] <= o) a = mid; else b = mid;
+      }
+      i = row_lo + a;
+      r = (u32)(o - s_ex[a]);
+    } else {
+      u64 a = row_lo, b = row_hi + 1;
+      while (b - a > 1) {
+        const u64 mid = (a + b) >> 1;
+        if (exscan[mid] <= o) a = mid; else b = mid;
+      }
+      i = a;
+      r = (u32)(o - exscan[i]);
+    }
+    const u64 kbase = (u64)ki[i] * tr.nb;
+    int bb = 0;
+    while (bb < tr.nb - 1 && r >= cnt[kbase + bb]) { r -= cnt[kbase + bb]; bb++; }
+    const Cols& T = tr.b[bb].c;
+    const u64 t = (u64)lo[kbase + bb] + r;
+    u64 row[MAXL];
+    i64 wout;
+    int nl_out;
+    bool ok = true;
+    if (proj_mode == 0) {
+      nl_out = nk + nvT;
+      for (int l = 0; l < nl_out; l++) row[l] = T.c[l][t];
+      wout = tr.b[bb].w[t];
+    } else {
+      u64 key[MAXL], dv[MAXL], tv[MAXL];
+      for (int l = 0; l < nk; l++) key[l] = D.c[l][i];
+      for (int l = 0; l < nvD; l++) dv[l] = D.c[nk + l][i];
+      for (int l = 0; l < nvT; l++) tv[l] = T.c[nk + l][t];
+      Env e = delta_is_left ? Env{key, dv, tv} : Env{key, tv, dv};
+      ok = project(proj, e, row);
+      nl_out = proj.out_schema.n_key_lanes + proj.out_schema.n_val_lanes;
+      wout = (i64)((u64)wD[i] * (u64)tr.b[bb].w[t]);
+    }
+    for (int l = 0; l < nl_out; l++) out.c[l][o] = row[l];
+    out_w[o] = ok ? wout : 0;
   }
-  for (int l = 0; l < nl_out; l++) out.c[l][o] = row[l];
-  out_w[o] = ok ? wout : 0;
 }
 
 // Sum over one trace batch of the weight of the *exact* row (all L lanes).
@@ -782,7 +825,7 @@ static int32_t probe_chunk(Ctx* ctx, const Batch* delta, int nk, Batch* const* t
     // matched trace rows read once, delta rows read once, output rows written once
     ProfScope ps(ctx, KID_PROBE_FILL, (u64)total * (u64)(tb[0]->nl() - nk + 1) * 8 + nd * (u64)(delta->nl() + 1) * 8 +
                                           (u64)total * (u64)(Lo + 1) * 8);
-    k_probe_fill<<<blocks(total), TB, 0, st>>>(delta->cols(), delta->w, nd, refs, nk, delta->nl() - nk, tb[0]->nl() - nk, lo,
+    k_probe_fill<<<(unsigned)((total + PF_TILE - 1) / PF_TILE), 256, 0, st>>>(delta->cols(), delta->w, nd, refs, nk, delta->nl() - nk, tb[0]->nl() - nk, lo,
                                                cnt, ki, ex, total, proj ? 1 : 0, delta_is_left, pj, t.c, t.w);
   }
   LAUNCH_COUNT(ctx);
