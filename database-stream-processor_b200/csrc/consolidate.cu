@@ -28,7 +28,7 @@ namespace {
 
 struct Plan {
   int L, W;
-  int use_key;   // epilogue may compare / unpack the single packed word
+  int use_key;   // 1 / 2: the epilogue compares and unpacks the packed key word(s); 0: it goes through the row ids
   u64 mn[MAXL], flip[MAXL], mask[MAXL];
   unsigned char word[MAXL], shift[MAXL], bits[MAXL];
   unsigned char wbits[MAXL];
@@ -116,6 +116,21 @@ __global__ void k_pack(Cols cols, Plan p, int wd, const u32* idx, u64 n, u64* ke
   if (!idx) idx_out[i] = (u32)i;
 }
 
+// both words of a one- or two-word key in one read of the rows, plus the identity row ids
+__global__ void k_pack12(Cols cols, Plan p, u64 n, u64* key0, u64* key1, u32* idx_out) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 k0 = 0, k1 = 0;
+  for (int l = 0; l < p.L; l++) {
+    if (!p.bits[l]) continue;
+    const u64 v = ((cols.c[l][i] ^ p.flip[l]) - p.mn[l]) << p.shift[l];
+    if (p.word[l] == 0) k0 |= v; else k1 |= v;
+  }
+  key0[i] = k0;
+  if (key1) key1[i] = k1;
+  idx_out[i] = (u32)i;
+}
+
 __device__ __forceinline__ u64 unpack_lane(const Plan& p, int l, u64 key) {
   u64 v = p.bits[l] ? ((key >> p.shift[l]) & p.mask[l]) : 0;
   return (v + p.mn[l]) ^ p.flip[l];
@@ -166,9 +181,10 @@ __device__ __forceinline__ void re_st(u64* p, u64 v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__device__ __forceinline__ bool re_differs(const Cols& cols, int L, int use_key, const u64* key, const u32* idx, u64 i,
-                                           u64 j) {
-  if (use_key) return key[i] != key[j];
+__device__ __forceinline__ bool re_differs(const Cols& cols, int L, int use_key, const u64* key, const u64* key1, const u32* idx,
+                                           u64 i, u64 j) {
+  if (use_key == 1) return key[i] != key[j];
+  if (use_key == 2) return key[i] != key[j] || key1[i] != key1[j];
   u64 a = idx ? idx[i] : i, b = idx ? idx[j] : j;
   for (int l = 0; l < L; l++)
     if (cols.c[l][a] != cols.c[l][b]) return true;
@@ -177,8 +193,8 @@ __device__ __forceinline__ bool re_differs(const Cols& cols, int L, int use_key,
 
 // result[0] = number of output rows; result[2] (the sort's fallback flag) != 0 on entry => nothing is done
 __global__ void __launch_bounds__(RE_THREADS)
-k_reduce_emit(Cols cols, Plan p, const u64* key, const u32* idx, const i64* w, u64 n, ReStatus* status, u32* ticket, MCols out,
-              i64* out_w, u64* result) {
+k_reduce_emit(Cols cols, Plan p, const u64* key, const u64* key1, const u32* idx, const i64* w, u64 n, ReStatus* status, u32* ticket,
+              MCols out, i64* out_w, u64* result) {
   __shared__ HS s_warp_hs[RE_THREADS / 32];
   __shared__ u32 s_warp_u[RE_THREADS / 32];
   __shared__ u32 s_tile;
@@ -201,7 +217,7 @@ k_reduce_emit(Cols cols, Plan p, const u64* key, const u32* idx, const i64* w, u
     valid[k] = i < tile_e;
     hd[k] = false; tl[k] = false; wt[k] = 0;
     if (valid[k]) {
-      hd[k] = (i == 0) || re_differs(cols, p.L, p.use_key, key, idx, i, i - 1);
+      hd[k] = (i == 0) || re_differs(cols, p.L, p.use_key, key, key1, idx, i, i - 1);
       wt[k] = w ? w[idx ? idx[i] : i] : 1;
     }
   }
@@ -210,7 +226,7 @@ k_reduce_emit(Cols cols, Plan p, const u64* key, const u32* idx, const i64* w, u
     const u64 i = r0 + k;
     if (valid[k]) {
       if (k + 1 < RE_R && r0 + k + 1 < tile_e) tl[k] = hd[k + 1];
-      else tl[k] = (i + 1 >= n) || re_differs(cols, p.L, p.use_key, key, idx, i + 1, i);
+      else tl[k] = (i + 1 >= n) || re_differs(cols, p.L, p.use_key, key, key1, idx, i + 1, i);
     }
   }
   // (1) thread aggregate and block scan with the flag/sum monoid
@@ -331,8 +347,8 @@ k_reduce_emit(Cols cols, Plan p, const u64* key, const u32* idx, const i64* w, u
     if (!kp[k]) continue;
     const u64 i = r0 + k;
     if (p.use_key) {
-      const u64 kk = key[i];
-      for (int l = 0; l < p.L; l++) out.c[l][pos] = unpack_lane(p, l, kk);
+      const u64 kk0 = key[i], kk1 = p.use_key == 2 ? key1[i] : 0;
+      for (int l = 0; l < p.L; l++) out.c[l][pos] = unpack_lane(p, l, p.word[l] ? kk1 : kk0);
     } else {
       const u64 r = idx ? idx[i] : i;
       for (int l = 0; l < p.L; l++) out.c[l][pos] = cols.c[l][r];
@@ -346,8 +362,8 @@ inline int bits_for(u64 range) { return range == 0 ? 0 : 64 - __builtin_clzll(ra
 
 }  // namespace
 
-int32_t radix_sort_pairs(Ctx* ctx, u64* ka, u64* kb, u32* ia, u32* ib, u64 n, int bits, int presorted_top_bits, bool force_lsd,
-                         unsigned long long* fail, u64** key_out, u32** idx_out, int* hbm_passes);
+int32_t radix_sort_pairs(Ctx* ctx, int words, u64* k0a, u64* k0b, u64* k1a, u64* k1b, u32* ida, u32* idb, u64 n, int bits_lo, int bits_hi,
+                         int presorted_top_bits, bool force_lsd, unsigned long long* fail, int* which, int* hbm_passes);
 
 int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const i64* w, u64 n, const BufP* adopt,
                          Batch** out, const u32* d_n) {
@@ -418,25 +434,41 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
       p.wbits[word] = (unsigned char)used;
     }
     p.W = word + 1;
-    p.use_key = p.W == 1;
-    TRY(dev_alloc(ctx, (size_t)n * 8 * 2, &kbuf));
+    p.use_key = p.W <= 2 ? p.W : 0;
+    TRY(dev_alloc(ctx, (size_t)n * 8 * 2 * (p.W == 2 ? 2 : 1), &kbuf));
     TRY(dev_alloc(ctx, (size_t)n * 4 * 2, &ibuf));
   }
   u64* const kbufs[2] = {kbuf ? (u64*)kbuf->p : nullptr, kbuf ? (u64*)kbuf->p + n : nullptr};
+  u64* const k1bufs[2] = {(kbuf && p.W == 2) ? (u64*)kbuf->p + 2 * n : nullptr, (kbuf && p.W == 2) ? (u64*)kbuf->p + 3 * n : nullptr};
   u32* const ibufs[2] = {ibuf ? (u32*)ibuf->p : nullptr, ibuf ? (u32*)ibuf->p + n : nullptr};
-  u64* const cnt = ctx->d_scratch + 32;   // [0] duplicates, [1] zero weights, [2] sort-fallback flag
-  // lane 0 ordered on arrival (event tables come in time order) and the key is one word: its top bits[0] bits are
-  // non-decreasing already, the sort can skip every HBM pass (sort.cu)
-  const int presorted = (p.W == 1 && n_inv != 0 && mm[2 * L + 4] == 0) ? (int)p.bits[0] : 0;
+  u64* const cnt = ctx->d_scratch + 32;   // [0] output rows, [2] sort-fallback flag
+  const u64* key1_sorted = nullptr;
+  // lane 0 ordered on arrival (event tables come in time order): the top bits[0] bits of the key are non-decreasing
+  // already, the sort needs no HBM pass (sort.cu)
+  const int presorted = (p.W <= 2 && n_inv != 0 && mm[2 * L + 4] == 0) ? (int)p.bits[0] : 0;
 
-  // sort (key word, row id) pairs word by word, least significant word first (every stage is stable)
   auto sort_rows = [&](bool force_lsd) -> int32_t {
     idx_cur = nullptr;
+    if (p.W <= 2) {
+      // one- or two-word keys: pack once, one sort over the whole key
+      {
+        ProfScope ps(ctx, KID_PACK, n * (u64)L * 8 + n * (u64)(8 * p.W + 4));
+        k_pack12<<<nblk, TB, 0, st>>>(cols, p, n, kbufs[0], k1bufs[0], ibufs[0]);
+      }
+      LAUNCH_COUNT(ctx);
+      int which = 0;
+      TRY(radix_sort_pairs(ctx, p.W, kbufs[0], kbufs[1], k1bufs[0], k1bufs[1], ibufs[0], ibufs[1], n, (int)p.wbits[0],
+                           p.W == 2 ? (int)p.wbits[1] : 0, presorted, force_lsd, (unsigned long long*)(cnt + 2), &which, nullptr));
+      key_sorted = kbufs[which];
+      key1_sorted = k1bufs[which];
+      idx_cur = ibufs[which];
+      return DBSP_OK;
+    }
+    // wider keys: word by word, least significant word first (every stage is stable)
     for (int wd = 0; wd < p.W; wd++) {
       // the keys of the previous word are dead: always pack into key buffer 0; the row ids stay where the
       // previous word's sort left them
       u64* kdst = kbufs[0];
-      u32* iother;
       {
         ProfScope ps(ctx, KID_PACK, n * (u64)L * 8 + n * 12);
         if (wd == 0) {
@@ -447,15 +479,14 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
         }
       }
       LAUNCH_COUNT(ctx);
-      iother = idx_cur == ibufs[0] ? ibufs[1] : ibufs[0];
+      u32* iother = idx_cur == ibufs[0] ? ibufs[1] : ibufs[0];
       key_sorted = kdst;
       if (p.wbits[wd] > 0 && n > 1) {
-        u64* ko;
-        u32* io;
-        TRY(radix_sort_pairs(ctx, kdst, kbufs[1], idx_cur, iother, n, (int)p.wbits[wd], presorted, force_lsd,
-                             (unsigned long long*)(cnt + 2), &ko, &io, nullptr));
-        key_sorted = ko;
-        idx_cur = io;
+        int which = 0;
+        TRY(radix_sort_pairs(ctx, 1, kdst, kbufs[1], nullptr, nullptr, idx_cur, iother, n, (int)p.wbits[wd], 0, 0, force_lsd,
+                             (unsigned long long*)(cnt + 2), &which, nullptr));
+        key_sorted = which ? kbufs[1] : kdst;
+        idx_cur = which ? iother : idx_cur;
       }
     }
     return DBSP_OK;
@@ -480,8 +511,8 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
     if (n_inv == 0) CUDA_TRY(cudaMemsetAsync(cnt, 0, 24, st));
     CUDA_TRY(cudaMemsetAsync(tbuf->p, 0, (size_t)ntiles * sizeof(ReStatus) + 16, st));
     {
-      ProfScope pseg(ctx, KID_SEG_REDUCE, n * (u64)((p.use_key ? 12 : (L * 8 + (idx_cur ? 4 : 0))) + (w ? 8 : 0)) + n * (u64)(L + 1) * 8);
-      k_reduce_emit<<<ntiles, RE_THREADS, 0, st>>>(cols, p, key_sorted, idx_cur, w, n, status, ticket, oc, ow, cnt);
+      ProfScope pseg(ctx, KID_SEG_REDUCE, n * (u64)((p.use_key ? 8 * p.use_key + 4 : (L * 8 + (idx_cur ? 4 : 0))) + (w ? 8 : 0)) + n * (u64)(L + 1) * 8);
+      k_reduce_emit<<<ntiles, RE_THREADS, 0, st>>>(cols, p, key_sorted, key1_sorted, idx_cur, w, n, status, ticket, oc, ow, cnt);
     }
     LAUNCH_COUNT(ctx);
     int32_t rc = read_back(ctx, cnt, 3, res);

@@ -59,3 +59,49 @@ def test_sort_multiword(cuda, oracle):
     for c in cols[:2]:
         c[n // 2:] = c[: n - n // 2]   # equal leading lanes: the low words decide
     check(cuda, oracle, s, cols, rng.integers(-1, 2, n), "three words")
+
+
+@pytest.mark.parametrize("n", [262_143, 262_144, 700_001, 3_000_000])
+@pytest.mark.parametrize("dist", ["uniform", "loguniform", "hitters", "fewvalues"])
+def test_sort_splitter_mode(cuda, oracle, n, dist):
+    """n >= 256 K rows: bucket ids from sampled splitters, whatever the key distribution (log-uniform prices put a
+    quarter of the rows under one top-bits prefix; heavy hitters end up in equality buckets that need no sorting)."""
+    rng = np.random.default_rng(n % 1000 + len(dist))
+    s = Schema("u", "uu")
+    if dist == "uniform":
+        k = rng.integers(0, 1 << 40, n)
+    elif dist == "loguniform":
+        k = np.ceil(np.power(10.0, rng.random(n) * 6.0) * 100.0).astype(np.int64)
+    elif dist == "hitters":
+        k = np.where(rng.random(n) < 0.6, rng.choice(np.array([5, 77, 1 << 33]), n), rng.integers(0, 1 << 35, n))
+    else:
+        k = rng.integers(0, 7, n)
+    cols = [k.astype(np.uint64), rng.integers(0, 1 << 18, n).astype(np.uint64), rng.integers(0, 50, n).astype(np.uint64)]
+    check(cuda, oracle, s, cols, rng.integers(-1, 3, n), f"splitters n={n} {dist}")
+
+
+@pytest.mark.parametrize("n", [5_000, 200_000, 2_000_000])
+def test_sort_two_word_keys(cuda, oracle, n):
+    """Rows wider than 64 packed bits (two key words): one sort over the whole key, the epilogue unpacks both words."""
+    rng = np.random.default_rng(n)
+    s = Schema("u", "uuuuu")   # the shape of q7's bids_by_price: (price, auction, bidder, price, date_time, extra)
+    price = np.ceil(np.power(10.0, rng.random(n) * 6.0) * 100.0).astype(np.uint64)
+    cols = [price, rng.integers(1000, 300_000, n).astype(np.uint64), rng.integers(1000, 100_000, n).astype(np.uint64), price,
+            (np.uint64(1436918400000) + rng.integers(0, 10_000, n).astype(np.uint64)), rng.integers(0, 1 << 32, n).astype(np.uint64)]
+    # exact duplicates and cancelling pairs
+    for c in cols:
+        c[: n // 10] = c[n // 10: 2 * (n // 10)]
+    w = rng.integers(-1, 2, n)
+    check(cuda, oracle, s, cols, w, f"two words n={n}")
+
+
+def test_sort_two_word_presorted(cuda, oracle):
+    """Time-ordered table with rows wider than one word (q7's bids_by_time): no HBM pass, two-word chunk sort."""
+    n = 1_500_000
+    rng = np.random.default_rng(9)
+    s = Schema("u", "uuuu")
+    t = np.uint64(1436918400000) + (np.arange(n) // 920).astype(np.uint64)
+    price = np.ceil(np.power(10.0, rng.random(n) * 6.0) * 100.0).astype(np.uint64)
+    cols = [t, rng.integers(1000, 300_000, n).astype(np.uint64), rng.integers(1000, 100_000, n).astype(np.uint64), price,
+            rng.integers(0, 1 << 32, n).astype(np.uint64)]
+    check(cuda, oracle, s, cols, np.ones(n, np.int64), "two words, presorted lane 0")
