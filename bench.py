@@ -298,8 +298,10 @@ def run_b200(args, query, rank, world, comm, device, do_e2e=True):
     be.sync()
     import gc
 
-    if comm is not None and hasattr(comm, "detach"):
-        comm.detach()
+    if comm is not None:
+        res["nvlink_bytes_sent"] = getattr(comm, "bytes_sent", None)
+        if hasattr(comm, "detach"):
+            comm.detach()
     gc.collect()
     be.close()
     return res
@@ -322,7 +324,7 @@ def parity_check(rank, world, comm, device, queries=("q3", "q4", "q7"), events=1
     ok_all = True
     try:
         for q in queries:
-            rate = 100_000 if q == "q7" else 0            # q7: a 10 s window = 1 M events, closes every few steps
+            rate = 20_000 if q == "q7" else 0             # q7: 10 s of event time = 200 k events: windows close from step 2 on
             mine = gen_steps(q, rank, world, n_steps, events, pinned=False, rate=rate)
             c = dbsp_b200.RootCircuit(be, comm)
             inp, handles = nq.add_nexmark_input(c)
@@ -548,7 +550,7 @@ def main():
             "circuit_step_latency_ms": {"p50": res["circuit_step_ms_p50"], "p99": res["circuit_step_ms_p99"], "max": res["circuit_step_ms_max"]},
             "roofline": roofline_from_profile(res["profile"], primary), "kernel_profile": kernel_table(res["profile"])}
     if comm is not None:
-        line["nvlink_bytes_sent_rank0"] = getattr(comm, "bytes_sent", None)
+        line["nvlink_bytes_sent_rank0"] = res.get("nvlink_bytes_sent")
 
     if not args.no_extras and args.query is None:
         extras = {}

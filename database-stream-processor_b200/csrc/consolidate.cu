@@ -318,26 +318,37 @@ k_reduce_emit(Cols cols, Plan p, const u64* key, const u64* key1, const u32* idx
     if (k < wid) woff += v;
     tile_kept += v;
   }
-  // (4) look-back #2: first output slot of the tile
-  if (tid == 0) {
+  // (4) look-back #2: first output slot of the tile.  Warp 0 inspects 32 predecessor status words per round trip
+  // (tile q - lane per lane); aggregates of tiles that have not resolved their own prefix yet are summed on the way.
+  if (wid == 0) {
     ReStatus* me = &status[tile];
     u64 base = 0;
     if (tile == 0) {
-      re_st(&me->cnt, (2ull << 62) | (u64)tile_kept);
+      if (lane == 0) re_st(&me->cnt, (2ull << 62) | (u64)tile_kept);
     } else {
-      re_st(&me->cnt, (1ull << 62) | (u64)tile_kept);
-      long long q = (long long)tile - 1;
+      if (lane == 0) re_st(&me->cnt, (1ull << 62) | (u64)tile_kept);
+      long long q0 = (long long)tile - 1;
       while (true) {
-        u64 v;
-        do { v = re_ld(&status[q].cnt); } while ((v >> 62) == 0);
-        base += v & ((1ull << 62) - 1);
-        if ((v >> 62) == 2) break;
-        q--;
+        const long long q = q0 - lane;
+        u64 v = 2ull << 62;   // tiles before 0 contribute an empty prefix
+        if (q >= 0) {
+          do { v = re_ld(&status[q].cnt); } while ((v >> 62) == 0);
+        }
+        const unsigned isp = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+        const int first = isp ? (__ffs(isp) - 1) : 32;
+        u64 c = (lane <= first) ? (v & ((1ull << 62) - 1)) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        base += c;
+        if (isp) break;
+        q0 -= 32;
       }
-      re_st(&me->cnt, (2ull << 62) | (base + tile_kept));
+      if (lane == 0) re_st(&me->cnt, (2ull << 62) | (base + tile_kept));
     }
-    s_base = base;
-    if (tile_e == n) result[0] = base + tile_kept;   // the last tile knows the total
+    if (lane == 0) {
+      s_base = base;
+      if (tile_e == n) result[0] = base + tile_kept;   // the last tile knows the total
+    }
   }
   __syncthreads();
   // (5) output
