@@ -367,12 +367,82 @@ static Batch* segment_view(Ctx* ctx, const dbsp_schema& sc, char* seg, u64 cnt) 
   return v;   // no bufs: the region outlives the round's consumers (double buffering, see the header)
 }
 
+struct SegList {
+  const u64* base[MAXP];   // lane 0 of the segment; lanes are `stride` rows apart, weights follow the last lane
+  u64 cnt[MAXP], stride[MAXP], off[MAXP];
+  int nseg;
+};
+// P-way merge of small deltas by rank: every row finds its place in the union by bisecting the other segments
+// (rows of earlier segments sort before equal rows of later ones), so the P sorted segments land merged in one
+// launch; equal rows from different sources end up adjacent and are summed by the epilogue (reduce_sorted_rows).
+__global__ void k_pway_rank(SegList sl, int L, Flips f, u64 total, u64 out_stride, u64* out) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int sgm = 0;
+  while (sgm + 1 < sl.nseg && i >= sl.off[sgm + 1]) sgm++;
+  const u64 r = i - sl.off[sgm];
+  u64 raw[MAXL + 1], q[MAXL];
+  for (int l = 0; l <= L; l++) raw[l] = sl.base[sgm][(u64)l * sl.stride[sgm] + r];
+  for (int l = 0; l < L; l++) q[l] = raw[l] ^ f.f[l];
+  u64 pos = r;
+  for (int t = 0; t < sl.nseg; t++) {
+    if (t == sgm) continue;
+    const u64* tb = sl.base[t];
+    const u64 ts = sl.stride[t];
+    u64 lo = 0, hi = sl.cnt[t];
+    while (lo < hi) {   // rows of segment t that sort before this row (t < sgm: ties count too)
+      const u64 mid = lo + ((hi - lo) >> 1);
+      int c = 0;
+      for (int l = 0; l < L && c == 0; l++) {
+        const u64 a = tb[(u64)l * ts + mid] ^ f.f[l];
+        if (a != q[l]) c = a < q[l] ? -1 : 1;
+      }
+      const bool before = c < 0 || (c == 0 && t < sgm);
+      if (before) lo = mid + 1; else hi = mid;
+    }
+    pos += lo;
+  }
+  for (int l = 0; l <= L; l++) out[(u64)l * out_stride + pos] = raw[l];
+}
+constexpr u64 CONCAT_SORT_MAX_ROWS = 1ull << 20;
+
 static int32_t merge_views(Ctx* ctx, std::vector<Batch*>& parts, const dbsp_schema& s, Batch** out) {
-  // balanced merge tree of the P sorted segments (receiver side of shard(), shard.rs:136-144)
+  // receiver side of shard() (shard.rs:136-144): a balanced merge tree of the P sorted segments, or — for small
+  // deltas from more than two sources — ONE rank-merge launch + the reduce epilogue instead of P-1 merge launches
   std::vector<Batch*> live;
   for (Batch* p : parts) { if (p->n) live.push_back(p); else batch_unref(p); }
   parts.clear();
   int32_t rc = DBSP_OK;
+  u64 total = 0;
+  for (Batch* b : live) total += b->n;
+  if (live.size() > 2 && total <= CONCAT_SORT_MAX_ROWS) {
+    const int L = s.n_key_lanes + s.n_val_lanes;
+    const u64 cap = (total + 32) & ~31ull;
+    BufP buf;
+    rc = dev_alloc(ctx, (size_t)cap * 8 * (L + 1), &buf);
+    if (rc) { for (Batch* b : live) batch_unref(b); return rc; }
+    SegList sl;
+    sl.nseg = (int)live.size();
+    u64 off = 0;
+    for (size_t k = 0; k < live.size(); k++) {
+      sl.base[k] = live[k]->col[0];
+      sl.cnt[k] = live[k]->n;
+      sl.stride[k] = (live[k]->n + 32) & ~31ull;   // the segment's lane stride (segment_view)
+      sl.off[k] = off;
+      off += live[k]->n;
+    }
+    Flips f;
+    for (int l = 0; l < MAXL; l++) f.f[l] = (l < L && s.lane_types[l] == DBSP_I64) ? 0x8000000000000000ull : 0ull;
+    {
+      ProfScope ps(ctx, KID_SHARD, total * (u64)(L + 1) * 8 * 2);
+      k_pway_rank<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(sl, L, f, total, cap, (u64*)buf->p);
+    }
+    LAUNCH_COUNT(ctx);
+    for (Batch* b : live) batch_unref(b);
+    Cols c;
+    for (int l = 0; l < MAXL; l++) c.c[l] = l < L ? (const u64*)buf->p + (size_t)l * cap : nullptr;
+    return reduce_sorted_rows(ctx, s, c, (const i64*)((const u64*)buf->p + (size_t)L * cap), total, out);
+  }
   while (live.size() > 1 && rc == DBSP_OK) {
     std::vector<Batch*> nxt;
     size_t i = 0;

@@ -197,6 +197,8 @@ void comm_info(Ctx* ctx, int* rank, int* world, u64* bytes_sent);
 int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const i64* w, u64 n, const BufP* adopt,
                          Batch** out, const u32* d_n = nullptr);
 
+int32_t reduce_sorted_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const i64* w, u64 n, Batch** out);
+
 // ---- merge.cu --------------------------------------------------------------
 int32_t merge_batches(Ctx* ctx, const Batch* a, const Batch* b, Batch** out);
 int32_t merge_path_split(Ctx* ctx, const Batch* a, const Batch* b, u64 d, u64* na, u64* nb);

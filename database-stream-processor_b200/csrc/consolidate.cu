@@ -32,11 +32,13 @@ struct Plan {
   u64 mn[MAXL], flip[MAXL], mask[MAXL];
   unsigned char word[MAXL], shift[MAXL], bits[MAXL];
   unsigned char wbits[MAXL];
+  signed char alias[MAXL];   // >= 0: the lane always equals that earlier lane (not packed; copied on unpack)
 };
 
 // mm[l] = min, mm[L+l] = max of flipped lane l; mm[2L] = # inversions
 // (row i-1 > row i), mm[2L+1] = # adjacent duplicates, mm[2L+2] = # zero weights,
-// mm[2L+3] = row count (when it lives on the device), mm[2L+4] = # inversions of lane 0 alone.
+// mm[2L+3] = row count (when it lives on the device), mm[2L+4] = # inversions of lane 0 alone,
+// mm[2L+5] = bit (l*(l-1)/2 + j) set when lane l differs from the earlier lane j in some row.
 __global__ void k_props(Cols cols, Flips f, int L, const i64* w, u64 n_host, const u32* dn, u64* mm) {
   // the producer may have left the exact row count on the device (dn): the
   // census then returns it with the lane ranges in the same read-back
@@ -49,11 +51,13 @@ __global__ void k_props(Cols cols, Flips f, int L, const i64* w, u64 n_host, con
   __syncthreads();
   u64 lmin[MAXL], lmax[MAXL];
   for (int l = 0; l < L; l++) { lmin[l] = ~0ull; lmax[l] = 0; }
-  unsigned inv = 0, dup = 0, zero = 0, inv0 = 0;
+  unsigned inv = 0, dup = 0, zero = 0, inv0 = 0, neq = 0;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
     int c = 0;   // cmp(row i-1, row i)
+    u64 raw[MAXL];
     for (int l = 0; l < L; l++) {
-      u64 v = cols.c[l][i] ^ f.f[l];
+      raw[l] = cols.c[l][i];
+      u64 v = raw[l] ^ f.f[l];
       lmin[l] = min(lmin[l], v);
       lmax[l] = max(lmax[l], v);
       if (i > 0 && c == 0) {
@@ -64,6 +68,9 @@ __global__ void k_props(Cols cols, Flips f, int L, const i64* w, u64 n_host, con
     }
     if (i > 0) { inv += c > 0; dup += c == 0; }
     if (w && w[i] == 0) zero++;
+    for (int l = 1; l < L; l++)
+      for (int j = 0; j < l; j++)
+        if (raw[l] != raw[j]) neq |= 1u << (l * (l - 1) / 2 + j);
   }
   for (int l = 0; l < L; l++) {
     u64 a = lmin[l], b = lmax[l];
@@ -81,8 +88,10 @@ __global__ void k_props(Cols cols, Flips f, int L, const i64* w, u64 n_host, con
     dup += __shfl_xor_sync(0xffffffffu, dup, o);
     zero += __shfl_xor_sync(0xffffffffu, zero, o);
     inv0 += __shfl_xor_sync(0xffffffffu, inv0, o);
+    neq |= __shfl_xor_sync(0xffffffffu, neq, o);
   }
   if ((threadIdx.x & 31) == 0) {
+    if (neq) atomicOr((unsigned long long*)&mm[2 * L + 5], (unsigned long long)neq);
     if (inv) atomicAdd(&s_cnt[0], inv);
     if (dup) atomicAdd(&s_cnt[1], dup);
     if (zero) atomicAdd(&s_cnt[2], zero);
@@ -101,7 +110,7 @@ __global__ void k_props(Cols cols, Flips f, int L, const i64* w, u64 n_host, con
 __global__ void k_init_props(u64* mm, int L) {
   int t = threadIdx.x;
   if (t < L) mm[t] = ~0ull;
-  else if (t < 2 * L + 5) mm[t] = 0;
+  else if (t < 2 * L + 6) mm[t] = 0;
 }
 
 // key[i] = word `wd` of row (idx ? idx[i] : i); writes idx_out[i] = i when idx == nullptr.
@@ -359,7 +368,11 @@ k_reduce_emit(Cols cols, Plan p, const u64* key, const u64* key1, const u32* idx
     const u64 i = r0 + k;
     if (p.use_key) {
       const u64 kk0 = key[i], kk1 = p.use_key == 2 ? key1[i] : 0;
-      for (int l = 0; l < p.L; l++) out.c[l][pos] = unpack_lane(p, l, p.word[l] ? kk1 : kk0);
+      u64 v[MAXL];
+      for (int l = 0; l < p.L; l++) {
+        v[l] = p.alias[l] >= 0 ? v[p.alias[l]] : unpack_lane(p, l, p.word[l] ? kk1 : kk0);
+        out.c[l][pos] = v[l];
+      }
     } else {
       const u64 r = idx ? idx[i] : i;
       for (int l = 0; l < p.L; l++) out.c[l][pos] = cols.c[l][r];
@@ -388,7 +401,7 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
   for (int l = 0; l < MAXL; l++) f.f[l] = (l < L && s.lane_types[l] == DBSP_I64) ? 0x8000000000000000ull : 0;
 
   // ---- (1) lane ranges + order / duplicate / zero-weight census ---------------
-  u64 mm[2 * MAXL + 5];
+  u64 mm[2 * MAXL + 6];
   {
     u64* dmm = ctx->d_scratch + 64;
     k_init_props<<<1, 32, 0, st>>>(dmm, L);
@@ -398,7 +411,7 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
       k_props<<<g, TB, 0, st>>>(cols, f, L, w, n, d_n, dmm);
     }
     ctx->kernel_launches += 2;
-    TRY(read_back(ctx, dmm, 2 * L + 5, mm));
+    TRY(read_back(ctx, dmm, 2 * L + 6, mm));
     if (d_n) {
       n = mm[2 * L + 3];
       if (n == 0) { *out = batch_new_empty(ctx, s); return DBSP_OK; }
@@ -410,6 +423,7 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
   Plan p;
   memset(&p, 0, sizeof(p));
   p.L = L;
+  for (int l = 0; l < MAXL; l++) p.alias[l] = -1;
   u32* idx_cur = nullptr;
   const u64* key_sorted = nullptr;
   BufP kbuf, ibuf, tmp;
@@ -431,9 +445,15 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
     p.use_key = 0;   // compare / copy the lanes themselves, identity order
   } else {
     // ---- (3) bit-packing plan: lanes from last (least significant) to first ----
+    // a lane that equals an earlier lane in every row never breaks a tie: it is left out of the key and copied
+    // back when the rows are unpacked (q7's (price, auction, bidder, price, ..) rows)
+    const u64 neq = mm[2 * L + 5];
+    for (int l = 1; l < L; l++)
+      for (int j = 0; j < l && p.alias[l] < 0; j++)
+        if (!((neq >> (l * (l - 1) / 2 + j)) & 1)) p.alias[l] = (signed char)j;
     int word = 0, used = 0;
     for (int l = L - 1; l >= 0; l--) {
-      int b = bits_for(mm[L + l] - mm[l]);
+      int b = p.alias[l] >= 0 ? 0 : bits_for(mm[L + l] - mm[l]);
       if (used + b > 64) { word++; used = 0; }
       p.word[l] = (unsigned char)word;
       p.shift[l] = (unsigned char)used;
@@ -553,3 +573,43 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
   *out = b;
   return DBSP_OK;
 }
+
+// The epilogue alone: rows that are already in sorted order (equal rows adjacent) — sum the weights of equal rows,
+// drop zero sums, build the batch.  One launch, one read-back.  Used by the receiver side of the exchange.
+int32_t reduce_sorted_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const i64* w, u64 n, Batch** out) {
+  const int L = s.n_key_lanes + s.n_val_lanes;
+  if (n == 0) { *out = batch_new_empty(ctx, s); return DBSP_OK; }
+  if (n >= (1ull << 32)) { set_error("reduce: more than 2^32-1 rows in one batch"); return DBSP_ERR_UNSUPPORTED; }
+  cudaStream_t st = ctx->stream;
+  Plan p;
+  memset(&p, 0, sizeof(p));
+  p.L = L;
+  p.W = 1;
+  p.use_key = 0;
+  for (int l = 0; l < MAXL; l++) p.alias[l] = -1;
+  const u32 ntiles = (u32)((n + RE_TILE - 1) / RE_TILE);
+  BufP tbuf;
+  TRY(dev_alloc(ctx, (size_t)ntiles * sizeof(ReStatus) + 16, &tbuf));
+  ReStatus* status = (ReStatus*)tbuf->p;
+  u32* ticket = (u32*)(status + ntiles);
+  u64* const cnt = ctx->d_scratch + 32;
+  Batch* b = nullptr;
+  MCols oc;
+  i64* ow;
+  TRY(batch_alloc(ctx, s, n, &b, &oc, &ow));
+  CUDA_TRY(cudaMemsetAsync(cnt, 0, 24, st));
+  CUDA_TRY(cudaMemsetAsync(tbuf->p, 0, (size_t)ntiles * sizeof(ReStatus) + 16, st));
+  {
+    ProfScope pseg(ctx, KID_SEG_REDUCE, n * (u64)(L + 1) * 8 * 2);
+    k_reduce_emit<<<ntiles, RE_THREADS, 0, st>>>(cols, p, nullptr, nullptr, nullptr, w, n, status, ticket, oc, ow, cnt);
+  }
+  LAUNCH_COUNT(ctx);
+  u64 res[3];
+  int32_t rc = read_back(ctx, cnt, 3, res);
+  if (rc) { batch_unref(b); return rc; }
+  if (res[0] == 0) { batch_unref(b); *out = batch_new_empty(ctx, s); return DBSP_OK; }
+  b->n = res[0];
+  *out = b;
+  return DBSP_OK;
+}
+

@@ -105,3 +105,22 @@ def test_sort_two_word_presorted(cuda, oracle):
     cols = [t, rng.integers(1000, 300_000, n).astype(np.uint64), rng.integers(1000, 100_000, n).astype(np.uint64), price,
             rng.integers(0, 1 << 32, n).astype(np.uint64)]
     check(cuda, oracle, s, cols, np.ones(n, np.int64), "two words, presorted lane 0")
+
+
+def test_sort_aliased_lanes(cuda, oracle):
+    """A lane that repeats an earlier lane in every row is left out of the key and restored on unpack (q7's
+    (price, auction, bidder, price, date_time, extra)); one differing row must disable the shortcut."""
+    rng = np.random.default_rng(12)
+    n = 400_000
+    s = Schema("u", "uuuuu")
+    price = np.ceil(np.power(10.0, rng.random(n) * 6.0) * 100.0).astype(np.uint64)
+    base = [price, rng.integers(1000, 300_000, n).astype(np.uint64), rng.integers(1000, 100_000, n).astype(np.uint64), price.copy(),
+            np.uint64(1436918400000) + rng.integers(0, 10_000, n).astype(np.uint64), rng.integers(0, 1 << 32, n).astype(np.uint64)]
+    w = rng.integers(-1, 2, n)
+    check(cuda, oracle, s, base, w, "lane 3 == lane 0")
+    almost = [c.copy() for c in base]
+    almost[3][n // 2] += np.uint64(1)
+    check(cuda, oracle, s, almost, w, "lane 3 differs from lane 0 in one row")
+    three = [c.copy() for c in base]
+    three[2] = three[1].copy()   # lane 2 == lane 1 as well
+    check(cuda, oracle, Schema("uu", "iuuu"), three, w, "two aliased lanes, mixed types")
