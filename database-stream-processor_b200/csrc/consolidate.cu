@@ -22,6 +22,9 @@
 //      schemas pack into one word of 30-60 bits.
 //  (4) Epilogue: a two-pass reduce-by-key sums runs of equal rows and drops
 //      zero sums; the duplicate-free case is one unpack/gather pass.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -33,13 +36,15 @@ struct Plan {
   unsigned char word[MAXL], shift[MAXL], bits[MAXL];
   unsigned char wbits[MAXL];
   signed char alias[MAXL];   // >= 0: the lane always equals that earlier lane (not packed; copied on unpack)
+  unsigned char pos[MAXL];   // W <= 2: bit position of the lane inside the 128-bit concatenation (key1 : key0)
 };
 
 // mm[l] = min, mm[L+l] = max of flipped lane l; mm[2L] = # inversions
 // (row i-1 > row i), mm[2L+1] = # adjacent duplicates, mm[2L+2] = # zero weights,
 // mm[2L+3] = row count (when it lives on the device), mm[2L+4] = # inversions of lane 0 alone,
 // mm[2L+5] = bit (l*(l-1)/2 + j) set when lane l differs from the earlier lane j in some row.
-__global__ void k_props(Cols cols, Flips f, int L, const i64* w, u64 n_host, const u32* dn, u64* mm) {
+template <int L>   // compile-time lane count: the per-lane state stays in registers, every loop unrolls
+__global__ void __launch_bounds__(256) k_props(Cols cols, Flips f, const i64* w, u64 n_host, const u32* dn, u64* mm) {
   // the producer may have left the exact row count on the device (dn): the
   // census then returns it with the lane ranges in the same read-back
   const u64 n = dn ? (u64)*dn : n_host;
@@ -49,12 +54,14 @@ __global__ void k_props(Cols cols, Flips f, int L, const i64* w, u64 n_host, con
   if (threadIdx.x < MAXL) { smin[threadIdx.x] = ~0ull; smax[threadIdx.x] = 0; }
   if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
   __syncthreads();
-  u64 lmin[MAXL], lmax[MAXL];
+  u64 lmin[L], lmax[L];
+#pragma unroll
   for (int l = 0; l < L; l++) { lmin[l] = ~0ull; lmax[l] = 0; }
   unsigned inv = 0, dup = 0, zero = 0, inv0 = 0, neq = 0;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
     int c = 0;   // cmp(row i-1, row i)
-    u64 raw[MAXL];
+    u64 raw[L];
+#pragma unroll
     for (int l = 0; l < L; l++) {
       raw[l] = cols.c[l][i];
       u64 v = raw[l] ^ f.f[l];
@@ -68,10 +75,13 @@ __global__ void k_props(Cols cols, Flips f, int L, const i64* w, u64 n_host, con
     }
     if (i > 0) { inv += c > 0; dup += c == 0; }
     if (w && w[i] == 0) zero++;
+#pragma unroll
     for (int l = 1; l < L; l++)
+#pragma unroll
       for (int j = 0; j < l; j++)
         if (raw[l] != raw[j]) neq |= 1u << (l * (l - 1) / 2 + j);
   }
+#pragma unroll
   for (int l = 0; l < L; l++) {
     u64 a = lmin[l], b = lmax[l];
     for (int o = 16; o > 0; o >>= 1) {
@@ -125,23 +135,40 @@ __global__ void k_pack(Cols cols, Plan p, int wd, const u32* idx, u64 n, u64* ke
   if (!idx) idx_out[i] = (u32)i;
 }
 
-// both words of a one- or two-word key in one read of the rows, plus the identity row ids
+// both words of a one- or two-word key in one read of the rows, plus the identity row ids.  The lanes' bits are
+// packed back to back over the 128-bit concatenation (key1 : key0); a lane may straddle the word boundary.
 __global__ void k_pack12(Cols cols, Plan p, u64 n, u64* key0, u64* key1, u32* idx_out) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   u64 k0 = 0, k1 = 0;
   for (int l = 0; l < p.L; l++) {
     if (!p.bits[l]) continue;
-    const u64 v = ((cols.c[l][i] ^ p.flip[l]) - p.mn[l]) << p.shift[l];
-    if (p.word[l] == 0) k0 |= v; else k1 |= v;
+    const u64 v = (cols.c[l][i] ^ p.flip[l]) - p.mn[l];
+    const int ps = p.pos[l];
+    if (ps >= 64) k1 |= v << (ps - 64);
+    else {
+      k0 |= v << ps;
+      if (ps + p.bits[l] > 64) k1 |= v >> (64 - ps);
+    }
   }
   key0[i] = k0;
   if (key1) key1[i] = k1;
   idx_out[i] = (u32)i;
 }
 
-__device__ __forceinline__ u64 unpack_lane(const Plan& p, int l, u64 key) {
+__device__ __forceinline__ u64 unpack_lane(const Plan& p, int l, u64 key) {   // word-granular packing (W >= 3 path)
   u64 v = p.bits[l] ? ((key >> p.shift[l]) & p.mask[l]) : 0;
+  return (v + p.mn[l]) ^ p.flip[l];
+}
+__device__ __forceinline__ u64 unpack_lane12(const Plan& p, int l, u64 k0, u64 k1) {
+  u64 v = 0;
+  if (p.bits[l]) {
+    const int ps = p.pos[l];
+    if (ps >= 64) v = k1 >> (ps - 64);
+    else if (ps + p.bits[l] <= 64) v = k0 >> ps;
+    else v = (k0 >> ps) | (k1 << (64 - ps));
+    v &= p.mask[l];
+  }
   return (v + p.mn[l]) ^ p.flip[l];
 }
 
@@ -370,7 +397,7 @@ k_reduce_emit(Cols cols, Plan p, const u64* key, const u64* key1, const u32* idx
       const u64 kk0 = key[i], kk1 = p.use_key == 2 ? key1[i] : 0;
       u64 v[MAXL];
       for (int l = 0; l < p.L; l++) {
-        v[l] = p.alias[l] >= 0 ? v[p.alias[l]] : unpack_lane(p, l, p.word[l] ? kk1 : kk0);
+        v[l] = p.alias[l] >= 0 ? v[p.alias[l]] : unpack_lane12(p, l, kk0, kk1);
         out.c[l][pos] = v[l];
       }
     } else {
@@ -408,7 +435,16 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
     int g = (int)std::min<u64>((n + TB - 1) / TB, (u64)ctx->sm_count * 8);
     {
       ProfScope ps(ctx, KID_MINMAX, n * (u64)(L + (w ? 1 : 0)) * 8);
-      k_props<<<g, TB, 0, st>>>(cols, f, L, w, n, d_n, dmm);
+      switch (L) {
+        case 1: k_props<1><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm); break;
+        case 2: k_props<2><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm); break;
+        case 3: k_props<3><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm); break;
+        case 4: k_props<4><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm); break;
+        case 5: k_props<5><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm); break;
+        case 6: k_props<6><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm); break;
+        case 7: k_props<7><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm); break;
+        default: k_props<8><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm); break;
+      }
     }
     ctx->kernel_launches += 2;
     TRY(read_back(ctx, dmm, 2 * L + 6, mm));
@@ -451,21 +487,43 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
     for (int l = 1; l < L; l++)
       for (int j = 0; j < l && p.alias[l] < 0; j++)
         if (!((neq >> (l * (l - 1) / 2 + j)) & 1)) p.alias[l] = (signed char)j;
-    int word = 0, used = 0;
+    int total_bits = 0;
     for (int l = L - 1; l >= 0; l--) {
-      int b = p.alias[l] >= 0 ? 0 : bits_for(mm[L + l] - mm[l]);
-      if (used + b > 64) { word++; used = 0; }
-      p.word[l] = (unsigned char)word;
-      p.shift[l] = (unsigned char)used;
+      const int b = p.alias[l] >= 0 ? 0 : bits_for(mm[L + l] - mm[l]);
       p.bits[l] = (unsigned char)b;
       p.mn[l] = mm[l];
       p.flip[l] = f.f[l];
       p.mask[l] = b >= 64 ? ~0ull : ((1ull << b) - 1);
-      used += b;
-      p.wbits[word] = (unsigned char)used;
+      total_bits += b;
     }
-    p.W = word + 1;
+    if (total_bits <= 128) {
+      // one or two key words: the lanes' bits back to back, last lane least significant
+      int at = 0;
+      for (int l = L - 1; l >= 0; l--) { p.pos[l] = (unsigned char)at; at += p.bits[l]; }
+      p.W = total_bits <= 64 ? 1 : 2;
+      p.wbits[0] = (unsigned char)(total_bits <= 64 ? total_bits : 64);
+      p.wbits[1] = (unsigned char)(total_bits <= 64 ? 0 : total_bits - 64);
+    } else {
+      // wider rows: whole lanes per word, sorted word by word
+      int word = 0, used = 0;
+      for (int l = L - 1; l >= 0; l--) {
+        const int b = p.bits[l];
+        if (used + b > 64) { word++; used = 0; }
+        p.word[l] = (unsigned char)word;
+        p.shift[l] = (unsigned char)used;
+        used += b;
+        p.wbits[word] = (unsigned char)used;
+      }
+      p.W = word + 1;
+    }
     p.use_key = p.W <= 2 ? p.W : 0;
+    static const bool debug_plan = getenv("DBSP_DEBUG_PLAN") != nullptr;
+    if (debug_plan) {
+      fprintf(stderr, "[dbsp plan] n=%llu L=%d W=%d neq=%llx inv0=%llu bits:", (unsigned long long)n, L, p.W, (unsigned long long)neq,
+              (unsigned long long)mm[2 * L + 4]);
+      for (int l = 0; l < L; l++) fprintf(stderr, " %d%s", (int)p.bits[l], p.alias[l] >= 0 ? "a" : "");
+      fprintf(stderr, "\n");
+    }
     TRY(dev_alloc(ctx, (size_t)n * 8 * 2 * (p.W == 2 ? 2 : 1), &kbuf));
     TRY(dev_alloc(ctx, (size_t)n * 4 * 2, &ibuf));
   }
