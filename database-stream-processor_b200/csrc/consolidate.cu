@@ -217,20 +217,16 @@ __device__ __forceinline__ void re_st(u64* p, u64 v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__device__ __forceinline__ bool re_differs(const Cols& cols, int L, int use_key, const u64* key, const u64* key1, const u32* idx,
-                                           u64 i, u64 j) {
-  if (use_key == 1) return key[i] != key[j];
-  if (use_key == 2) return key[i] != key[j] || key1[i] != key1[j];
-  u64 a = idx ? idx[i] : i, b = idx ? idx[j] : j;
-  for (int l = 0; l < L; l++)
-    if (cols.c[l][a] != cols.c[l][b]) return true;
-  return false;
-}
-
-// result[0] = number of output rows; result[2] (the sort's fallback flag) != 0 on entry => nothing is done
+// result[0] = number of output rows; result[2] (the sort's fallback flag) != 0 on entry => nothing is done.
+// Global traffic is coalesced on both sides: the tile's key words (or row ids) and gathered weights are loaded
+// striped and staged in shared memory, the flag / scan work runs on the blocked arrangement out of shared memory,
+// and the kept rows are staged by output rank and written striped.
 __global__ void __launch_bounds__(RE_THREADS)
 k_reduce_emit(Cols cols, Plan p, const u64* key, const u64* key1, const u32* idx, const i64* w, u64 n, ReStatus* status, u32* ticket,
               MCols out, i64* out_w, u64* result) {
+  __shared__ u64 s_a[RE_TILE + 2];   // slot j+1 = row tile_s + j: key word 0 (use_key) or the row id; 0 / cnt+1 = halo rows
+  __shared__ u64 s_b[RE_TILE + 2];   // key word 1 (use_key == 2)
+  __shared__ i64 s_wt[RE_TILE];
   __shared__ HS s_warp_hs[RE_THREADS / 32];
   __shared__ u32 s_warp_u[RE_THREADS / 32];
   __shared__ u32 s_tile;
@@ -243,26 +239,59 @@ k_reduce_emit(Cols cols, Plan p, const u64* key, const u64* key1, const u32* idx
   const u32 tile = s_tile;
   const u64 tile_s = (u64)tile * RE_TILE;
   const u64 tile_e = tile_s + RE_TILE < n ? tile_s + RE_TILE : n;
-  const u64 r0 = tile_s + (u64)tid * RE_R;
+  const int cnt = (int)(tile_e - tile_s);
+  const int uk = p.use_key;
 
+  // ---- striped, coalesced load into shared memory (+ one halo row on each side) ----
+  auto stage = [&](int slot, u64 i) {
+    if (uk) {
+      s_a[slot] = key[i];
+      if (uk == 2) s_b[slot] = key1[i];
+    } else {
+      s_a[slot] = idx ? (u64)idx[i] : i;
+    }
+  };
+#pragma unroll
+  for (int k = 0; k < RE_R; k++) {
+    const int j = k * RE_THREADS + tid;
+    if (j < cnt) {
+      const u64 i = tile_s + j;
+      stage(j + 1, i);
+      s_wt[j] = w ? w[idx ? idx[i] : i] : 1;
+    }
+  }
+  if (tid == 0 && tile_s > 0) stage(0, tile_s - 1);
+  if (tid == 32 && tile_e < n) stage(cnt + 1, tile_e);
+  __syncthreads();
+  auto differs = [&](int sa, int sb) -> bool {   // staged rows in slots sa, sb
+    if (uk == 1) return s_a[sa] != s_a[sb];
+    if (uk == 2) return s_a[sa] != s_a[sb] || s_b[sa] != s_b[sb];
+    const u64 a = s_a[sa], b = s_a[sb];
+    for (int l = 0; l < p.L; l++)
+      if (cols.c[l][a] != cols.c[l][b]) return true;
+    return false;
+  };
+
+  // ---- blocked arrangement out of shared memory: thread t owns rows t*RE_R .. t*RE_R+RE_R-1 of the tile ----
+  const int j0 = tid * RE_R;
   bool hd[RE_R], tl[RE_R], valid[RE_R];
   i64 wt[RE_R];
 #pragma unroll
   for (int k = 0; k < RE_R; k++) {
-    const u64 i = r0 + k;
-    valid[k] = i < tile_e;
+    const int j = j0 + k;
+    valid[k] = j < cnt;
     hd[k] = false; tl[k] = false; wt[k] = 0;
     if (valid[k]) {
-      hd[k] = (i == 0) || re_differs(cols, p.L, p.use_key, key, key1, idx, i, i - 1);
-      wt[k] = w ? w[idx ? idx[i] : i] : 1;
+      hd[k] = (tile_s + j == 0) || differs(j + 1, j);
+      wt[k] = s_wt[j];
     }
   }
 #pragma unroll
   for (int k = 0; k < RE_R; k++) {
-    const u64 i = r0 + k;
+    const int j = j0 + k;
     if (valid[k]) {
-      if (k + 1 < RE_R && r0 + k + 1 < tile_e) tl[k] = hd[k + 1];
-      else tl[k] = (i + 1 >= n) || re_differs(cols, p.L, p.use_key, key, key1, idx, i + 1, i);
+      if (k + 1 < RE_R && j + 1 < cnt) tl[k] = hd[k + 1];
+      else tl[k] = (tile_s + j + 1 >= n) || differs(j + 2, j + 1);
     }
   }
   // (1) thread aggregate and block scan with the flag/sum monoid
@@ -346,6 +375,13 @@ k_reduce_emit(Cols cols, Plan p, const u64* key, const u64* key1, const u32* idx
     if (lane >= o) kincl += v;
   }
   if (lane == 31) s_warp_u[wid] = kincl;
+  // the kept rows' staged words are read before shared memory is reused for the output staging
+  u64 ka[RE_R], kb[RE_R];
+#pragma unroll
+  for (int k = 0; k < RE_R; k++) {
+    ka[k] = 0; kb[k] = 0;
+    if (kp[k]) { ka[k] = s_a[j0 + k + 1]; if (uk == 2) kb[k] = s_b[j0 + k + 1]; }
+  }
   __syncthreads();
   u32 woff = 0, tile_kept = 0;
 #pragma unroll
@@ -353,6 +389,18 @@ k_reduce_emit(Cols cols, Plan p, const u64* key, const u64* key1, const u32* idx
     const u32 v = s_warp_u[k];
     if (k < wid) woff += v;
     tile_kept += v;
+  }
+  // stage the kept rows by output rank
+  {
+    u32 lr = woff + kincl - kept;
+#pragma unroll
+    for (int k = 0; k < RE_R; k++) {
+      if (!kp[k]) continue;
+      s_a[lr] = ka[k];
+      if (uk == 2) s_b[lr] = kb[k];
+      s_wt[lr] = tot[k];
+      lr++;
+    }
   }
   // (4) look-back #2: first output slot of the tile.  Warp 0 inspects 32 predecessor status words per round trip
   // (tile q - lane per lane); aggregates of tiles that have not resolved their own prefix yet are summed on the way.
@@ -387,25 +435,22 @@ k_reduce_emit(Cols cols, Plan p, const u64* key, const u64* key1, const u32* idx
     }
   }
   __syncthreads();
-  // (5) output
-  u64 pos = s_base + woff + kincl - kept;
-#pragma unroll
-  for (int k = 0; k < RE_R; k++) {
-    if (!kp[k]) continue;
-    const u64 i = r0 + k;
-    if (p.use_key) {
-      const u64 kk0 = key[i], kk1 = p.use_key == 2 ? key1[i] : 0;
+  // (5) striped, coalesced output
+  const u64 base = s_base;
+  for (u32 o = tid; o < tile_kept; o += RE_THREADS) {
+    const u64 pos = base + o;
+    if (uk) {
+      const u64 kk0 = s_a[o], kk1 = uk == 2 ? s_b[o] : 0;
       u64 v[MAXL];
       for (int l = 0; l < p.L; l++) {
         v[l] = p.alias[l] >= 0 ? v[p.alias[l]] : unpack_lane12(p, l, kk0, kk1);
         out.c[l][pos] = v[l];
       }
     } else {
-      const u64 r = idx ? idx[i] : i;
+      const u64 r = s_a[o];
       for (int l = 0; l < p.L; l++) out.c[l][pos] = cols.c[l][r];
     }
-    out_w[pos] = tot[k];
-    pos++;
+    out_w[pos] = s_wt[o];
   }
 }
 

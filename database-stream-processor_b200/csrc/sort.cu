@@ -31,7 +31,14 @@
 namespace {
 
 constexpr int RS_THREADS = 256, RS_IPT = 12, RS_TILE = RS_THREADS * RS_IPT, RS_WARPS = RS_THREADS / 32;
-constexpr int CS_THREADS = 512, CS_IPT = 12, CS_CAP = CS_THREADS * CS_IPT, CS_WARPS = CS_THREADS / 32, CS_HALF = CS_CAP / 2;
+// chunk sort: 6144 pairs per CTA.  One-word keys: 512 threads x 12 pairs (64 registers, 2 CTAs/SM); two-word keys:
+// 1024 threads x 6 pairs (64 registers, one CTA of 32 warps per SM — measured 1.6x faster than 512 x 12 at 128 registers).
+constexpr int CS_CAP = 6144, CS_HALF = CS_CAP / 2;
+template <int W> struct CsCfg {
+  static constexpr int THREADS = W == 1 ? 512 : 1024;
+  static constexpr int IPT = CS_CAP / THREADS;
+  static constexpr int WARPS = THREADS / 32;
+};
 constexpr int MAX_PASSES = 16;
 constexpr u64 RS_AGG = 1ull << 62, RS_PREFIX = 2ull << 62, RS_MASK = (1ull << 62) - 1;
 constexpr u64 SPLITTER_MODE_MIN_ROWS = 262144;
@@ -272,8 +279,9 @@ constexpr size_t rs_smem_bytes() {
 // first bucket start inside the next window — whole buckets, at most CS_CAP rows when no bucket exceeds CS_HALF rows
 // (else *fail is raised).
 template <int W, bool BID>
-__global__ void __launch_bounds__(CS_THREADS, W == 1 ? 2 : 1)
+__global__ void __launch_bounds__(CsCfg<W>::THREADS, W == 1 ? 2 : 1)
 k_chunk_sort(PairPtrs in, MPairPtrs out, u64 n, int bits_total, int bits_lo, int bshift, unsigned long long* fail) {
+  constexpr int CS_THREADS = CsCfg<W>::THREADS, CS_IPT = CsCfg<W>::IPT, CS_WARPS = CsCfg<W>::WARPS;
   extern __shared__ __align__(16) unsigned char cs_smem[];
   u64* s_key0 = (u64*)cs_smem;
   u64* s_key1 = s_key0 + CS_CAP;                                   // W == 2 only
@@ -428,7 +436,7 @@ k_chunk_sort(PairPtrs in, MPairPtrs out, u64 n, int bits_total, int bits_lo, int
 }
 template <int W>
 constexpr size_t cs_smem_bytes() {
-  return (size_t)CS_CAP * (8 * W + 4) + (size_t)CS_WARPS * 257 * 4;
+  return (size_t)CS_CAP * (8 * W + 4) + (size_t)CsCfg<W>::WARPS * 257 * 4;
 }
 
 // strided sample with a per-sample jitter (robust to periodic inputs)
@@ -550,7 +558,7 @@ int32_t run_chunks(Ctx* ctx, Bufs& B, int& cur, u64 n, int bits_total, int bits_
   MPairPtrs out{B.k0[cur ^ 1], B.k1[cur ^ 1], B.id[cur ^ 1], B.bid[cur ^ 1]};
   {
     ProfScope ps(ctx, KID_CHUNK_SORT, n * (u64)(2 * (8 * W + 4) + (BID ? 2 : 0)));
-    k_chunk_sort<W, BID><<<nwin, CS_THREADS, SMEM, ctx->stream>>>(in, out, n, bits_total, bits_lo, bshift, fail);
+    k_chunk_sort<W, BID><<<nwin, CsCfg<W>::THREADS, SMEM, ctx->stream>>>(in, out, n, bits_total, bits_lo, bshift, fail);
   }
   LAUNCH_COUNT(ctx);
   cur ^= 1;
