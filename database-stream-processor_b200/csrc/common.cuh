@@ -23,6 +23,13 @@ typedef uint32_t u32;
 
 struct Ctx;
 struct Comm;
+// A producer kernel may publish its small result (row count, census words) to the host mailbox itself, which
+// saves the separate publish launch of read_back(): the host passes a Mail, the designated last tile / last block of
+// the kernel calls mail_publish, the host collects the words with mail_finish.
+struct Mail {
+  volatile uint64_t* p;   // device alias of the mapped host mailbox (nullptr: do not publish)
+  uint64_t seq;
+};
 
 void set_error(const std::string& s);
 #define CUDA_TRY(expr)                                                                    \
@@ -174,10 +181,12 @@ inline void batch_ref(Batch* b) { b->refs.fetch_add(1); }
 // Copy `count` u64 from device to pinned host scratch and wait.
 int32_t read_back(Ctx* ctx, const void* dsrc, size_t count_u64, u64* hdst);
 int32_t read_back32(Ctx* ctx, const void* dsrc, u32* hdst);
-int32_t exclusive_scan_u32(Ctx* ctx, const u32* in, u32* out, u64 n);   // out[n] = total (n+1 entries)
+int32_t exclusive_scan_u32(Ctx* ctx, const u32* in, u32* out, u64 n, const Mail* total_mail = nullptr);   // out[n] = total (n+1 entries); total_mail: the kernel publishes it
 int32_t inclusive_scan_i64(Ctx* ctx, const i64* in, i64* out, u64 n);
 
 int32_t mail_wait(Ctx* ctx, u64 seq);   // spin on the host mailbox until `seq` is published
+Mail mail_begin(Ctx* ctx);
+int32_t mail_finish(Ctx* ctx, const Mail& m, u64* out, int count);
 
 // ---- comm.cu ---------------------------------------------------------------
 int32_t comm_create(Ctx* ctx, int rank, int world, u64 slot_bytes, unsigned char* blob_out);
@@ -205,6 +214,13 @@ int32_t merge_path_split(Ctx* ctx, const Batch* a, const Batch* b, u64 d, u64* n
 
 // ---- device helpers ----------------------------------------------------------
 #ifdef __CUDACC__
+// called by ONE thread after the values it publishes are final
+__device__ __forceinline__ void mail_publish(const Mail& m, const u64* vals, int count) {
+  if (!m.p) return;
+  for (int i = 0; i < count; i++) m.p[8 + i] = vals[i];
+  __threadfence_system();
+  m.p[0] = m.seq;
+}
 // lexicographic compare of row i of A against row j of B over lanes [0,nl)
 __device__ __forceinline__ int cmp_rows_g(const Cols& A, u64 i, const Cols& B, u64 j, int nl, const Flips& f) {
   for (int l = 0; l < nl; l++) {

@@ -44,7 +44,7 @@ struct Plan {
 // mm[2L+3] = row count (when it lives on the device), mm[2L+4] = # inversions of lane 0 alone,
 // mm[2L+5] = bit (l*(l-1)/2 + j) set when lane l differs from the earlier lane j in some row.
 template <int L>   // compile-time lane count: the per-lane state stays in registers, every loop unrolls
-__global__ void __launch_bounds__(256) k_props(Cols cols, Flips f, const i64* w, u64 n_host, const u32* dn, u64* mm) {
+__global__ void __launch_bounds__(256) k_props(Cols cols, Flips f, const i64* w, u64 n_host, const u32* dn, u64* mm, Mail mail) {
   // the producer may have left the exact row count on the device (dn): the
   // census then returns it with the lane ranges in the same read-back
   const u64 n = dn ? (u64)*dn : n_host;
@@ -115,12 +115,24 @@ __global__ void __launch_bounds__(256) k_props(Cols cols, Flips f, const i64* w,
   if (threadIdx.x < 3 && s_cnt[threadIdx.x])
     atomicAdd((unsigned long long*)&mm[2 * L + threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
   if (threadIdx.x == 3 && s_cnt[3]) atomicAdd((unsigned long long*)&mm[2 * L + 4], (unsigned long long)s_cnt[3]);
+  // the last block to finish publishes the census to the host mailbox (mm[2L+6] counts finished blocks)
+  __shared__ unsigned s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd((unsigned long long*)&mm[2 * L + 6], 1ull) == (unsigned long long)(gridDim.x - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    u64 vals[2 * L + 6];
+    for (int i = 0; i < 2 * L + 6; i++) vals[i] = ((volatile u64*)mm)[i];
+    mail_publish(mail, vals, 2 * L + 6);
+  }
 }
 
 __global__ void k_init_props(u64* mm, int L) {
   int t = threadIdx.x;
   if (t < L) mm[t] = ~0ull;
-  else if (t < 2 * L + 6) mm[t] = 0;
+  else if (t < 2 * L + 7) mm[t] = 0;
 }
 
 // key[i] = word `wd` of row (idx ? idx[i] : i); writes idx_out[i] = i when idx == nullptr.
@@ -223,7 +235,7 @@ __device__ __forceinline__ void re_st(u64* p, u64 v) {
 // and the kept rows are staged by output rank and written striped.
 __global__ void __launch_bounds__(RE_THREADS)
 k_reduce_emit(Cols cols, Plan p, const u64* key, const u64* key1, const u32* idx, const i64* w, u64 n, ReStatus* status, u32* ticket,
-              MCols out, i64* out_w, u64* result) {
+              MCols out, i64* out_w, u64* result, Mail mail) {
   __shared__ u64 s_a[RE_TILE + 2];   // slot j+1 = row tile_s + j: key word 0 (use_key) or the row id; 0 / cnt+1 = halo rows
   __shared__ u64 s_b[RE_TILE + 2];   // key word 1 (use_key == 2)
   __shared__ i64 s_wt[RE_TILE];
@@ -232,7 +244,13 @@ k_reduce_emit(Cols cols, Plan p, const u64* key, const u64* key1, const u32* idx
   __shared__ u32 s_tile;
   __shared__ i64 s_cin;
   __shared__ u64 s_base;
-  if (result[2]) return;   // the sort raised its fallback flag: key / idx are not a permutation yet
+  if (result[2]) {   // the sort raised its fallback flag: key / idx are not a permutation yet
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      const u64 vals[3] = {0, 0, result[2]};
+      mail_publish(mail, vals, 3);
+    }
+    return;
+  }
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
   __syncthreads();
@@ -431,7 +449,11 @@ k_reduce_emit(Cols cols, Plan p, const u64* key, const u64* key1, const u32* idx
     }
     if (lane == 0) {
       s_base = base;
-      if (tile_e == n) result[0] = base + tile_kept;   // the last tile knows the total
+      if (tile_e == n) {   // the last tile knows the total: it goes straight to the host mailbox
+        const u64 vals[3] = {base + tile_kept, 0, 0};
+        result[0] = vals[0];
+        mail_publish(mail, vals, 3);
+      }
     }
   }
   __syncthreads();
@@ -477,22 +499,23 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
   {
     u64* dmm = ctx->d_scratch + 64;
     k_init_props<<<1, 32, 0, st>>>(dmm, L);
+    const Mail mail = mail_begin(ctx);
     int g = (int)std::min<u64>((n + TB - 1) / TB, (u64)ctx->sm_count * 8);
     {
       ProfScope ps(ctx, KID_MINMAX, n * (u64)(L + (w ? 1 : 0)) * 8);
       switch (L) {
-        case 1: k_props<1><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm); break;
-        case 2: k_props<2><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm); break;
-        case 3: k_props<3><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm); break;
-        case 4: k_props<4><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm); break;
-        case 5: k_props<5><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm); break;
-        case 6: k_props<6><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm); break;
-        case 7: k_props<7><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm); break;
-        default: k_props<8><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm); break;
+        case 1: k_props<1><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm, mail); break;
+        case 2: k_props<2><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm, mail); break;
+        case 3: k_props<3><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm, mail); break;
+        case 4: k_props<4><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm, mail); break;
+        case 5: k_props<5><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm, mail); break;
+        case 6: k_props<6><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm, mail); break;
+        case 7: k_props<7><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm, mail); break;
+        default: k_props<8><<<g, TB, 0, st>>>(cols, f, w, n, d_n, dmm, mail); break;
       }
     }
     ctx->kernel_launches += 2;
-    TRY(read_back(ctx, dmm, 2 * L + 6, mm));
+    TRY(mail_finish(ctx, mail, mm, 2 * L + 6));
     if (d_n) {
       n = mm[2 * L + 3];
       if (n == 0) { *out = batch_new_empty(ctx, s); return DBSP_OK; }
@@ -641,15 +664,18 @@ int32_t consolidate_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, const
   i64* ow;
   TRY(batch_alloc(ctx, s, n, &b, &oc, &ow));   // capacity n: the exact count comes back with the kernel
   u64 res[3] = {0, 0, 0};
+  Mail rmail_seq;
   for (int attempt = 0; attempt < 2; attempt++) {
     if (n_inv == 0) CUDA_TRY(cudaMemsetAsync(cnt, 0, 24, st));
     CUDA_TRY(cudaMemsetAsync(tbuf->p, 0, (size_t)ntiles * sizeof(ReStatus) + 16, st));
     {
       ProfScope pseg(ctx, KID_SEG_REDUCE, n * (u64)((p.use_key ? 8 * p.use_key + 4 : (L * 8 + (idx_cur ? 4 : 0))) + (w ? 8 : 0)) + n * (u64)(L + 1) * 8);
-      k_reduce_emit<<<ntiles, RE_THREADS, 0, st>>>(cols, p, key_sorted, key1_sorted, idx_cur, w, n, status, ticket, oc, ow, cnt);
+      const Mail rmail = mail_begin(ctx);
+      k_reduce_emit<<<ntiles, RE_THREADS, 0, st>>>(cols, p, key_sorted, key1_sorted, idx_cur, w, n, status, ticket, oc, ow, cnt, rmail);
+      LAUNCH_COUNT(ctx);
+      rmail_seq = rmail;
     }
-    LAUNCH_COUNT(ctx);
-    int32_t rc = read_back(ctx, cnt, 3, res);
+    int32_t rc = mail_finish(ctx, rmail_seq, res, 3);
     if (rc) { batch_unref(b); return rc; }
     if (res[2] == 0) break;
     // a bucket did not fit a shared-memory chunk (heavy key skew): redo the sort with the plain LSD sequence
@@ -702,13 +728,14 @@ int32_t reduce_sorted_rows(Ctx* ctx, const dbsp_schema& s, const Cols& cols, con
   TRY(batch_alloc(ctx, s, n, &b, &oc, &ow));
   CUDA_TRY(cudaMemsetAsync(cnt, 0, 24, st));
   CUDA_TRY(cudaMemsetAsync(tbuf->p, 0, (size_t)ntiles * sizeof(ReStatus) + 16, st));
+  const Mail rmail = mail_begin(ctx);
   {
     ProfScope pseg(ctx, KID_SEG_REDUCE, n * (u64)(L + 1) * 8 * 2);
-    k_reduce_emit<<<ntiles, RE_THREADS, 0, st>>>(cols, p, nullptr, nullptr, nullptr, w, n, status, ticket, oc, ow, cnt);
+    k_reduce_emit<<<ntiles, RE_THREADS, 0, st>>>(cols, p, nullptr, nullptr, nullptr, w, n, status, ticket, oc, ow, cnt, rmail);
   }
   LAUNCH_COUNT(ctx);
   u64 res[3];
-  int32_t rc = read_back(ctx, cnt, 3, res);
+  int32_t rc = mail_finish(ctx, rmail, res, 3);
   if (rc) { batch_unref(b); return rc; }
   if (res[0] == 0) { batch_unref(b); *out = batch_new_empty(ctx, s); return DBSP_OK; }
   b->n = res[0];

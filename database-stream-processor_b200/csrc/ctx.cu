@@ -212,6 +212,22 @@ int32_t mail_wait(Ctx* ctx, u64 seq) {
   return DBSP_OK;
 }
 
+Mail mail_begin(Ctx* ctx) {
+  Mail m;
+  m.p = (volatile u64*)ctx->d_mail;
+  m.seq = ++ctx->mail_seq;
+  return m;
+}
+int32_t mail_finish(Ctx* ctx, const Mail& m, u64* out, int count) {
+  double t0 = now_us();
+  TRY(mail_wait(ctx, m.seq));
+  ctx->t_sync_us += now_us() - t0;
+  ctx->n_sync++;
+  for (int i = 0; i < count; i++) out[i] = ctx->h_mail[8 + i];
+  ctx->d2h_bytes += (u64)count * 8;
+  return DBSP_OK;
+}
+
 int32_t read_back(Ctx* ctx, const void* dsrc, size_t count_u64, u64* hdst) {
   if (count_u64 > 256) { set_error("read_back: too large"); return DBSP_ERR_INVALID; }
   double t0 = now_us();
@@ -254,7 +270,7 @@ __device__ __forceinline__ void sc_st(u64* p, u64 v) {
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_exscan_u32(const u32* __restrict__ in, u32* __restrict__ out, u64 m,
-                                                            u32* ticket, u64* status) {
+                                                            u32* ticket, u64* status, Mail mail) {
   __shared__ u32 s_tile, s_warp[SCAN_THREADS / 32];
   __shared__ u64 s_base;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -315,11 +331,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_exscan_u32(const u32* __restri
 #pragma unroll
   for (int k = 0; k < SCAN_IPT; k++) {
     if (base_i + k < m) out[base_i + k] = run;
+    if (base_i + k == m - 1) {   // the last entry is the total: publish it to the host if asked to
+      const u64 tot = run;
+      mail_publish(mail, &tot, 1);
+    }
     run += v[k];
   }
 }
 
-int32_t exclusive_scan_u32(Ctx* ctx, const u32* in, u32* out, u64 n) {
+int32_t exclusive_scan_u32(Ctx* ctx, const u32* in, u32* out, u64 n, const Mail* total_mail) {
   // out has n+1 entries: out[n] = total.  Scans the n+1 inputs (callers keep
   // in[n] == 0).
   const u64 m = n + 1;
@@ -331,7 +351,11 @@ int32_t exclusive_scan_u32(Ctx* ctx, const u32* in, u32* out, u64 n) {
   u32* ticket = (u32*)(status + ntiles);
   {
     ProfScope ps(ctx, KID_SCAN, m * 8);
-    k_exscan_u32<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(in, out, m, ticket, status);
+    Mail mm;
+    mm.p = nullptr;
+    mm.seq = 0;
+    if (total_mail) mm = *total_mail;
+    k_exscan_u32<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(in, out, m, ticket, status, mm);
   }
   LAUNCH_COUNT(ctx);
   return DBSP_OK;

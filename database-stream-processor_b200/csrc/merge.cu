@@ -195,7 +195,7 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, const i64* __restric
                                                    unsigned short* perm, const int oa, const int ob, const int na,
                                                    const int nb, const bool has_prev, const bool has_next, const u32 t,
                                                    const u32 ntiles, u64* status, const MCols& O, i64* wO, u64* n_out,
-                                                   const Flips& f, const TileScratch& sc) {
+                                                   const Flips& f, const TileScratch& sc, const Mail& mail) {
   constexpr int IPT = MergeCfg<L>::IPT;
   constexpr int S = MergeCfg<L>::S;
   const int tid = threadIdx.x;
@@ -441,7 +441,11 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, const i64* __restric
       s_base = base_acc;
     }
   }
-  if (tid == 0 && t == ntiles - 1) *n_out = s_base + tile_total;
+  if (tid == 0 && t == ntiles - 1) {
+    const u64 tot = s_base + tile_total;
+    *n_out = tot;
+    mail_publish(mail, &tot, 1);   // the output count goes straight to the host mailbox
+  }
   __syncthreads();
   const u64 base = s_base;
   for (u32 o = tid; o < tile_total; o += MERGE_THREADS) {
@@ -474,7 +478,7 @@ template <int L>
 __global__ void __launch_bounds__(MERGE_THREADS, MERGE_MIN_CTAS_FOR(L))
 k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __restrict__ wB, u64 nB, Flips f,
               const u64* __restrict__ part, u32 ntiles, u64* status, MCols O, i64* wO, u64* n_out,
-              int use_tma) {
+              int use_tma, Mail mail) {
   constexpr int IPT = MergeCfg<L>::IPT;
   constexpr int TILE = MergeCfg<L>::TILE;
   constexpr int S = MergeCfg<L>::S;
@@ -583,7 +587,7 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
   __syncthreads();
 
   TileScratch sc{&s_base, s_warp, s_lb_first, s_lb_all, s_lb_upto};
-  merge_process_tile<L>(sl, wA + a0, wB + b0, perm, oa, ob, na, nb, has_prev, has_next, t, ntiles, status, O, wO, n_out, f, sc);
+  merge_process_tile<L>(sl, wA + a0, wB + b0, perm, oa, ob, na, nb, has_prev, has_next, t, ntiles, status, O, wO, n_out, f, sc, mail);
 }
 
 
@@ -624,13 +628,14 @@ int32_t merge_launch(Ctx* ctx, const Batch* a, const Batch* b, Batch** out) {
     k_merge_partition<L><<<(ntiles + 1 + 127) / 128, 128, 0, st>>>(a->cols(), a->n, b->cols(), b->n, f, Cfg::TILE, ntiles, part);
   }
   ProfScope* ps = new ProfScope(ctx, KID_MERGE, 0);
+  const Mail mail = mail_begin(ctx);
   k_merge_tiles<L><<<ntiles, MERGE_THREADS, Cfg::SMEM, st>>>(a->cols(), a->w, a->n, b->cols(), b->w, b->n, f, part, ntiles,
-                                                           status, oc, ow, n_out, use_tma);
+                                                           status, oc, ow, n_out, use_tma, mail);
   long ps_idx = ps->idx;
   delete ps;   // records the end event
   ctx->kernel_launches += 2;
   u64 nout;
-  int32_t rc = read_back(ctx, n_out, 1, &nout);
+  int32_t rc = mail_finish(ctx, mail, &nout, 1);
   if (rc != DBSP_OK) { batch_unref(o); return rc; }
   // algorithmic bytes: every input row read once, every output row written once
   if (ps_idx >= 0) ctx->prof[ps_idx].bytes = (total + nout) * (u64)(L + 1) * 8;

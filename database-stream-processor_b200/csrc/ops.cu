@@ -590,9 +590,11 @@ int32_t compact_ordered(Ctx* ctx, const dbsp_schema& s, const Cols& in, const i6
   BufP pbuf;
   TRY(dev_alloc(ctx, (size_t)(n + 1) * 4, &pbuf));
   u32* pos = (u32*)pbuf->p;
-  TRY(exclusive_scan_u32(ctx, keep, pos, n));
-  u32 nout;
-  TRY(read_back32(ctx, pos + n, &nout));
+  const Mail mail = mail_begin(ctx);
+  TRY(exclusive_scan_u32(ctx, keep, pos, n, &mail));
+  u64 nout64;
+  TRY(mail_finish(ctx, mail, &nout64, 1));
+  const u32 nout = (u32)nout64;
   if (nout == 0) { *out = batch_new_empty(ctx, s); return DBSP_OK; }
   Batch* b;
   MCols oc;
@@ -623,9 +625,11 @@ int32_t op_truncate_values(Ctx* ctx, const Batch* b, const u64* val_bound, Batch
     k_vals_ge<<<blocks(n + 1), TB, 0, ctx->stream>>>(b->cols(), n, nk, nv, rb, f, keep);
   }
   LAUNCH_COUNT(ctx);
-  TRY(exclusive_scan_u32(ctx, keep, pos, n));
-  u32 nout;
-  TRY(read_back32(ctx, pos + n, &nout));
+  const Mail mail = mail_begin(ctx);
+  TRY(exclusive_scan_u32(ctx, keep, pos, n, &mail));
+  u64 nout64;
+  TRY(mail_finish(ctx, mail, &nout64, 1));
+  const u32 nout = (u32)nout64;
   if (nout == n) { batch_ref((Batch*)b); *out = (Batch*)b; return DBSP_OK; }
   if (nout == 0) { *out = batch_new_empty(ctx, b->s); return DBSP_OK; }
   Batch* o;
@@ -759,9 +763,11 @@ static int32_t key_segments(Ctx* ctx, const Batch* b, int nk, BufP* kstart, BufP
   u32* pos = (u32*)(*head_ex)->p;
   k_key_heads<<<blocks(b->n + 1), TB, 0, ctx->stream>>>(b->cols(), b->n, nk, flags);
   LAUNCH_COUNT(ctx);
-  TRY(exclusive_scan_u32(ctx, flags, pos, b->n));
-  u32 nkk;
-  TRY(read_back32(ctx, pos + b->n, &nkk));
+  const Mail mail = mail_begin(ctx);
+  TRY(exclusive_scan_u32(ctx, flags, pos, b->n, &mail));
+  u64 nkk64;
+  TRY(mail_finish(ctx, mail, &nkk64, 1));
+  const u32 nkk = (u32)nkk64;
   TRY(dev_alloc(ctx, (size_t)(nkk + 1) * 8, kstart));
   k_scatter_index<<<blocks(b->n), TB, 0, ctx->stream>>>(flags, pos, b->n, (u64*)(*kstart)->p, nkk);
   LAUNCH_COUNT(ctx);
@@ -1237,9 +1243,11 @@ int32_t batch_build_csr(Ctx* ctx, Batch* b) {
   u32* pos = flags + (b->n + 1);
   k_key_heads<<<blocks(b->n + 1), TB, 0, ctx->stream>>>(b->cols(), b->n, nk, flags);
   LAUNCH_COUNT(ctx);
-  TRY(exclusive_scan_u32(ctx, flags, pos, b->n));
-  u32 nkeys;
-  TRY(read_back32(ctx, pos + b->n, &nkeys));
+  const Mail mail = mail_begin(ctx);
+  TRY(exclusive_scan_u32(ctx, flags, pos, b->n, &mail));
+  u64 nkeys64;
+  TRY(mail_finish(ctx, mail, &nkeys64, 1));
+  const u32 nkeys = (u32)nkeys64;
   TRY(dev_alloc(ctx, (size_t)(nkeys + 1) * 8, &pb));
   k_scatter_index<<<blocks(b->n), TB, 0, ctx->stream>>>(flags, pos, b->n, (u64*)pb->p, nkeys);
   LAUNCH_COUNT(ctx);
