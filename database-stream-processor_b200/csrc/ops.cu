@@ -117,11 +117,11 @@ __global__ void k_project_rows(Cols in, int nk_in, int n_in_lanes, unsigned used
 // carrying that key — lower bound by bisection, upper bound by galloping (the
 // `seek_key` of cursor/mod.rs + advance.rs:25-72).  One search per key instead of
 // one per row; all spine batches in one launch.
-__global__ void k_probe_keys(Cols D, const u64* kstart, u64 nkeys, BatchRefs tr, int nk, Flips f, u32* lo_out,
+__global__ void k_probe_keys(Cols D, const u64* kstart, const u32* d_nkeys, BatchRefs tr, int nk, Flips f, u32* lo_out,
                              u32* cnt_out, u32* ktot, unsigned long long* tot64) {
   u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k == 0) *tot64 = 0;   // accumulated by k_row_counts (next kernel on the stream)
-  if (k >= nkeys) return;
+  if (k == 0) { tot64[0] = 0; tot64[1] = 0; }   // match total / finished-block counter of k_row_counts (next kernel on the stream)
+  if (k >= (u64)*d_nkeys) return;   // the grid covers one thread per delta ROW (an upper bound of the key count)
   const u64 row = kstart[k];
   u64 q[MAXL];
   for (int l = 0; l < nk; l++) q[l] = D.c[l][row] ^ f.f[l];
@@ -143,7 +143,7 @@ __global__ void k_probe_keys(Cols D, const u64* kstart, u64 nkeys, BatchRefs tr,
 
 // matches of every delta row = matches of its key; also the row -> key index
 __global__ void k_row_counts(const u32* head_exscan, const u32* ktot, u64 nd, u32* rowcnt, u32* ki,
-                             unsigned long long* tot64) {
+                             unsigned long long* tot64, Mail mail) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long c = 0;
   if (i == nd) rowcnt[nd] = 0;
@@ -157,6 +157,17 @@ __global__ void k_row_counts(const u32* head_exscan, const u32* ktot, u64 nd, u3
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(tot64, c);
+  // the last block to finish publishes the total to the host mailbox
+  __shared__ unsigned s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&tot64[1], 1ull) == (unsigned long long)(gridDim.x - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    const u64 tot = *(volatile unsigned long long*)tot64;
+    mail_publish(mail, &tot, 1);
+  }
 }
 
 // Expand the matches: output slot o -> (delta row i, batch b, trace row).  Slots
@@ -335,6 +346,12 @@ __global__ void k_scatter_index(const u32* keep, const u32* pos, u64 n, u64* out
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && keep[i]) out[pos[i]] = i;
   if (i == 0) out[nout] = n;
+}
+// the same with the number of kept rows read from the scan (pos[n]) instead of the host
+__global__ void k_scatter_index_dev(const u32* keep, const u32* pos, u64 n, u64* out) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && keep[i]) out[pos[i]] = i;
+  if (i == 0) out[pos[n]] = n;
 }
 
 __global__ void k_iota_u32(u32* out, u32 n, u32 mul) {
@@ -754,7 +771,9 @@ int32_t project_and_consolidate(Ctx* ctx, const Cols& in, int nk_in, int n_in_la
 // proj == nullptr: gather the matching trace rows unchanged.
 // key segment starts of the first nk lanes: kstart[nkeys+1] (u64 row indices),
 // plus the exclusive scan of the head flags (u32[n+1]) used for row -> key.
-static int32_t key_segments(Ctx* ctx, const Batch* b, int nk, BufP* kstart, BufP* head_ex, u64* nkeys) {
+static int32_t key_segments(Ctx* ctx, const Batch* b, int nk, BufP* kstart, BufP* head_ex, const u32** d_nkeys) {
+  // No read-back: the key count stays on the device (the scan's total, pos[n]); buffers and grids downstream are
+  // sized by the row count, an upper bound of it.
   ROWS32(b->n, "key_segments");
   BufP fb;
   TRY(dev_alloc(ctx, (size_t)(b->n + 1) * 4, &fb));
@@ -763,15 +782,11 @@ static int32_t key_segments(Ctx* ctx, const Batch* b, int nk, BufP* kstart, BufP
   u32* pos = (u32*)(*head_ex)->p;
   k_key_heads<<<blocks(b->n + 1), TB, 0, ctx->stream>>>(b->cols(), b->n, nk, flags);
   LAUNCH_COUNT(ctx);
-  const Mail mail = mail_begin(ctx);
-  TRY(exclusive_scan_u32(ctx, flags, pos, b->n, &mail));
-  u64 nkk64;
-  TRY(mail_finish(ctx, mail, &nkk64, 1));
-  const u32 nkk = (u32)nkk64;
-  TRY(dev_alloc(ctx, (size_t)(nkk + 1) * 8, kstart));
-  k_scatter_index<<<blocks(b->n), TB, 0, ctx->stream>>>(flags, pos, b->n, (u64*)(*kstart)->p, nkk);
+  TRY(exclusive_scan_u32(ctx, flags, pos, b->n));
+  TRY(dev_alloc(ctx, (size_t)(b->n + 1) * 8, kstart));
+  k_scatter_index_dev<<<blocks(b->n), TB, 0, ctx->stream>>>(flags, pos, b->n, (u64*)(*kstart)->p);
   LAUNCH_COUNT(ctx);
-  *nkeys = nkk;
+  *d_nkeys = pos + b->n;
   return DBSP_OK;
 }
 
@@ -779,12 +794,13 @@ static int32_t key_segments(Ctx* ctx, const Batch* b, int nk, BufP* kstart, BufP
 // proj == nullptr: gather the matching trace rows unchanged.
 static int32_t probe_chunk(Ctx* ctx, const Batch* delta, int nk, Batch* const* tb, int nb, const dbsp_proj* proj,
                            int delta_is_left, const dbsp_schema& out_schema, const u64* kstart, const u32* head_ex,
-                           u64 nkeys, Batch** out) {
+                           const u32* d_nkeys, Batch** out) {
   cudaStream_t st = ctx->stream;
   const u64 nd = delta->n;
   Flips f = delta->flips();
   BatchRefs refs;
   refs.nb = nb;
+  const u64 nkeys = nd;   // upper bound of the distinct keys (the exact count is *d_nkeys)
   u64 trace_rows = 0;
   ROWS32(nd, "join/gather delta");
   for (int b = 0; b < nb; b++) ROWS32(tb[b]->n, "join/gather trace batch");
@@ -810,13 +826,14 @@ static int32_t probe_chunk(Ctx* ctx, const Batch* delta, int nk, Batch* const* t
     u64 lg = 1; while ((1ull << lg) < trace_rows / std::max(nb, 1) + 1) lg++;
     u64 touched = std::min<u64>(nkeys * (u64)nb * 2 * lg, trace_rows) * (u64)std::max(nk, 1) * 8;
     ProfScope ps(ctx, KID_PROBE_RANGES, nkeys * ((u64)nk * 8 + (u64)nb * 8 + 4) + touched);
-    k_probe_keys<<<blocks(nkeys), TB, 0, st>>>(delta->cols(), kstart, nkeys, refs, nk, f, lo, cnt, ktot, tot64);
+    k_probe_keys<<<blocks(nkeys), TB, 0, st>>>(delta->cols(), kstart, d_nkeys, refs, nk, f, lo, cnt, ktot, tot64);
   }
-  k_row_counts<<<blocks(nd + 1), TB, 0, st>>>(head_ex, ktot, nd, rowcnt, ki, tot64);
+  const Mail mail = mail_begin(ctx);
+  k_row_counts<<<blocks(nd + 1), TB, 0, st>>>(head_ex, ktot, nd, rowcnt, ki, tot64, mail);
   ctx->kernel_launches += 2;
   TRY(exclusive_scan_u32(ctx, rowcnt, ex, nd));
   u64 total;
-  TRY(read_back(ctx, tot64, 1, &total));
+  TRY(mail_finish(ctx, mail, &total, 1));
   if (total >= 0xffffffffull) {
     set_error("join/gather: 2^32-1 or more matches in one step (" + std::to_string(total) + "); feed the delta in smaller batches");
     return DBSP_ERR_UNSUPPORTED;
@@ -846,7 +863,7 @@ static int32_t probe_spine(Ctx* ctx, const Batch* delta, int nk, const Spine* tr
   const size_t nb = trace->batches.size();
   if (delta->n == 0 || nb == 0) { *out = batch_new_empty(ctx, out_schema); return DBSP_OK; }
   BufP kstart, head_ex;
-  u64 nkeys;
+  const u32* nkeys = nullptr;   // device count of the distinct delta keys
   TRY(key_segments(ctx, delta, nk, &kstart, &head_ex, &nkeys));
   std::vector<Batch*> parts;
   for (size_t b0 = 0; b0 < nb; b0 += MAX_REFS) {
