@@ -552,6 +552,20 @@ def main():
     if comm is not None:
         line["nvlink_bytes_sent_rank0"] = res.get("nvlink_bytes_sent")
 
+    if not args.no_extras and args.query is None and world == 1:
+        # the circuit step size is DBSP's throughput / latency knob (the reference's --batch-size): q3 at larger steps
+        import copy
+        sweep_steps = []
+        for e_big in (20_000_000, 80_000_000):
+            a2 = copy.copy(args)
+            a2.events_per_step, a2.circuit_steps, a2.steps, a2.warmup = e_big, 1, 6, 3
+            r = run_b200(a2, "q3", rank, world, comm, device)
+            cb = run_reference(a2, "q3", bench_steps=4, warmup=2)
+            sweep_steps.append({"events_per_circuit_step": e_big, "value": r["value"], "unit": UNIT, "ms_per_circuit_step": r["ms_per_circuit_step"],
+                                "e2e": r.get("e2e"), "gpu_launches": r["gpu_launches"],
+                                "cpu_baseline": {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}})
+        line["q3_step_size_sweep"] = sweep_steps
+
     if not args.no_extras and args.query is None:
         extras = {}
         for q in ("q4", "q7"):
