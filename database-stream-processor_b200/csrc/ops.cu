@@ -119,26 +119,28 @@ __global__ void k_project_rows(Cols in, int nk_in, int n_in_lanes, unsigned used
 // one per row; all spine batches in one launch.
 __global__ void k_probe_keys(Cols D, const u64* kstart, const u32* d_nkeys, BatchRefs tr, int nk, Flips f, u32* lo_out,
                              u32* cnt_out, u32* ktot, unsigned long long* tot64) {
-  u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k == 0) { tot64[0] = 0; tot64[1] = 0; }   // match total / finished-block counter of k_row_counts (next kernel on the stream)
-  if (k >= (u64)*d_nkeys) return;   // the grid covers one thread per delta ROW (an upper bound of the key count)
-  const u64 row = kstart[k];
-  u64 q[MAXL];
-  for (int l = 0; l < nk; l++) q[l] = D.c[l][row] ^ f.f[l];
-  u64 tot = 0;
-  for (int b = 0; b < tr.nb; b++) {
-    const Cols& T = tr.b[b].c;
-    const u64 nt = tr.b[b].n;
-    u64 lo = lower_bound_q(T, 0, nt, q, nk, f);
-    u64 hi = lo, step = 1;
-    while (hi + step <= nt && cmp_row_q(T, hi + step - 1, q, nk, f) == 0) { hi += step; step <<= 1; }
-    u64 top = hi + step <= nt ? hi + step : nt;
-    hi = upper_bound_q(T, hi, top, q, nk, f);
-    lo_out[k * tr.nb + b] = (u32)lo;
-    cnt_out[k * tr.nb + b] = (u32)(hi - lo);
-    tot += hi - lo;
+  const u64 gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gtid == 0) { tot64[0] = 0; tot64[1] = 0; }   // match total / finished-block counter of k_row_counts (next kernel on the stream)
+  const u64 nkeys = (u64)*d_nkeys;   // the exact key count lives on the device; the grid is a fixed-size grid-stride loop
+  for (u64 k = gtid; k < nkeys; k += (u64)gridDim.x * blockDim.x) {
+    const u64 row = kstart[k];
+    u64 q[MAXL];
+    for (int l = 0; l < nk; l++) q[l] = D.c[l][row] ^ f.f[l];
+    u64 tot = 0;
+    for (int b = 0; b < tr.nb; b++) {
+      const Cols& T = tr.b[b].c;
+      const u64 nt = tr.b[b].n;
+      u64 lo = lower_bound_q(T, 0, nt, q, nk, f);
+      u64 hi = lo, step = 1;
+      while (hi + step <= nt && cmp_row_q(T, hi + step - 1, q, nk, f) == 0) { hi += step; step <<= 1; }
+      u64 top = hi + step <= nt ? hi + step : nt;
+      hi = upper_bound_q(T, hi, top, q, nk, f);
+      lo_out[k * tr.nb + b] = (u32)lo;
+      cnt_out[k * tr.nb + b] = (u32)(hi - lo);
+      tot += hi - lo;
+    }
+    ktot[k] = tot > 0xffffffffull ? 0xffffffffu : (u32)tot;   // saturate: the 64-bit total below then trips the guard
   }
-  ktot[k] = tot > 0xffffffffull ? 0xffffffffu : (u32)tot;   // saturate: the 64-bit total below then trips the guard
 }
 
 // matches of every delta row = matches of its key; also the row -> key index
@@ -826,7 +828,8 @@ static int32_t probe_chunk(Ctx* ctx, const Batch* delta, int nk, Batch* const* t
     u64 lg = 1; while ((1ull << lg) < trace_rows / std::max(nb, 1) + 1) lg++;
     u64 touched = std::min<u64>(nkeys * (u64)nb * 2 * lg, trace_rows) * (u64)std::max(nk, 1) * 8;
     ProfScope ps(ctx, KID_PROBE_RANGES, nkeys * ((u64)nk * 8 + (u64)nb * 8 + 4) + touched);
-    k_probe_keys<<<blocks(nkeys), TB, 0, st>>>(delta->cols(), kstart, d_nkeys, refs, nk, f, lo, cnt, ktot, tot64);
+    const unsigned pg = (unsigned)std::min<u64>(blocks(nkeys), (u64)ctx->sm_count * 16);
+    k_probe_keys<<<pg, TB, 0, st>>>(delta->cols(), kstart, d_nkeys, refs, nk, f, lo, cnt, ktot, tot64);
   }
   const Mail mail = mail_begin(ctx);
   k_row_counts<<<blocks(nd + 1), TB, 0, st>>>(head_ex, ktot, nd, rowcnt, ki, tot64, mail);
