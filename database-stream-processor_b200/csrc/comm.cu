@@ -288,7 +288,7 @@ int32_t comm_create(Ctx* ctx, int rank, int world, u64 slot_bytes, unsigned char
   c->world = world;
   if (slot_bytes == 0) {
     const char* e = getenv("DBSP_COMM_SLOT_MB");
-    slot_bytes = (u64)(e ? atof(e) : 256.0) << 20;
+    slot_bytes = (u64)(e ? atof(e) : 512.0) << 20;   // default 512 MiB per (source, destination) and parity
   }
   c->slot_bytes = (slot_bytes + 255) & ~255ull;
   c->region_bytes = CTRL_BYTES + (size_t)2 * world * c->slot_bytes;

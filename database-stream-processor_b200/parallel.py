@@ -140,6 +140,7 @@ class Comm:
                 cols = [recv[o + l * n: o + (l + 1) * n] for l in range(schema.nl)]
                 got.append(be.batch_from_flat_tensors(schema, cols, recv[o + schema.nl * n: o + l1 * n], synced=True))
             out.append(got)
+        be.sync()   # the adoption copies run on the backend's stream: finish them before `recv` goes back to torch's allocator
         return out
 
     SORT_THRESHOLD = 1 << 20

@@ -359,7 +359,7 @@ int32_t dbsp_shard_partition(dbsp_ctx* ctx, const dbsp_batch* b,
 #define DBSP_COMM_MAX_RANKS 32
 #define DBSP_COMM_BLOB_BYTES 128
 int32_t dbsp_comm_create(dbsp_ctx* ctx, int32_t rank, int32_t world,
-                         uint64_t slot_bytes /* capacity of one (source,destination) segment per round; 0 = 256 MiB */,
+                         uint64_t slot_bytes /* capacity of one (source,destination) segment per round; 0 = 512 MiB */,
                          uint8_t* blob_out /* DBSP_COMM_BLOB_BYTES */);
 int32_t dbsp_comm_connect(dbsp_ctx* ctx, const uint8_t* blobs /* world * DBSP_COMM_BLOB_BYTES, rank order */);
 int32_t dbsp_comm_destroy(dbsp_ctx* ctx);

@@ -39,7 +39,7 @@ def run_ops(be, comm, rank, world):
     assert comm.native is be, "the CUDA backend must use the in-library exchange"
     for k in range(5):
         assert comm.allreduce_max(1000 * k + 7 * rank) == 1000 * k + 7 * (world - 1)
-    cases = [(Schema("u", "u"), 50_000, 1 << 14), (Schema("ui", "uu"), 5_000_000, 1 << 22), (Schema("u"), 3, 10),
+    cases = [(Schema("u", "u"), 50_000, 1 << 14), (Schema("ui", "uu"), 1_500_000, 1 << 22), (Schema("u"), 3, 10),
              (Schema("uu", "uiu"), 120_000, 300)]
     for ci, (s, n, dom) in enumerate(cases):
         for round_ in range(3):
