@@ -249,7 +249,10 @@ def run_b200(args, query, rank, world, comm, device, do_e2e=True):
                ms_per_circuit_step=ms / K, wall_ms_per_circuit_step=wall * 1e3 / K,
                circuit_step_ms_p50=per_step[K // 2], circuit_step_ms_p99=per_step[min(K - 1, int(K * 0.99))],
                circuit_step_ms_max=per_step[-1], timed_region_ms=ms,
-               gpu_launches=st["kernel_launches"], profile=prof, clocks=clk.summary(), last_step_out_rows=out_rows)
+               gpu_launches=st["kernel_launches"], profile=prof, clocks=clk.summary(), last_step_out_rows=out_rows,
+               launches_per_circuit_step=st["kernel_launches"] / K,
+               host_readbacks_per_circuit_step=st["host_waits"] / K,      # counts the device publishes to the host mailbox
+               host_wait_ms_per_circuit_step=st["host_wait_ms"] / K)      # time the host spent waiting for them
     del c, handles, out, dev_steps
     be.sync()
 
@@ -270,22 +273,41 @@ def run_b200(args, query, rank, world, comm, device, do_e2e=True):
                 else:
                     handles[k].set_upload(ups[k])
 
+        # D2H of a step's output Z-set: flat lanes + weights into pinned host columns on the copy stream, drained
+        # while the next step runs (two buffer sets); the last one is drained inside the timed region
+        import torch as _t
+        host_out = [None, None]
+
+        def start_download(slot):
+            b = out.value
+            n, nl = len(b), b.schema.nk + b.schema.nv
+            if host_out[slot] is None or len(host_out[slot][0]) < n:
+                cap = max(2 * n, 1 << 16)
+                host_out[slot] = [_t.empty(cap, dtype=_t.int64).pin_memory().numpy() for _ in range(nl + 1)]
+            hb = host_out[slot]
+            return be.download_begin(b, [x.view(np.uint64) for x in hb[:nl]], hb[nl])
+
         for s in range(W):
             feed_uploads(start_uploads(steps[s]))
             c.step()
-            out.value.download()
+            start_download(s & 1).finish()
         sync_all(be)
         be.stats(reset=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(ext)
+        pending = None
         nxt = start_uploads(steps[W])             # every step's H2D copy is inside the timed region ...
         for s in range(W, W + K):
             cur = nxt
             nxt = start_uploads(steps[s + 1]) if s + 1 < W + K else None   # ... and overlaps the previous step's kernels
             feed_uploads(cur)
             c.step()
-            out.value.download()                  # D2H of the step's result Z-set
+            dl = start_download(s & 1)            # D2H of the step's result Z-set ...
+            if pending is not None:
+                pending.finish()                  # ... read by the host while the next step runs
+            pending = dl
+        pending.finish()
         e1.record(ext)
         sync_all(be)
         wall2 = time.perf_counter() - t0
@@ -548,7 +570,8 @@ def main():
             "gpu_launches": res["gpu_launches"], "rows_per_s": res["rows_per_s"],
             "ms_per_circuit_step": res["ms_per_circuit_step"], "timed_region_ms": res["timed_region_ms"],
             "circuit_step_latency_ms": {"p50": res["circuit_step_ms_p50"], "p99": res["circuit_step_ms_p99"], "max": res["circuit_step_ms_max"]},
-            "roofline": roofline_from_profile(res["profile"], primary), "kernel_profile": kernel_table(res["profile"])}
+            "roofline": roofline_from_profile(res["profile"], primary), "kernel_profile": kernel_table(res["profile"]),
+            "host_sync": {k: res[k] for k in ("launches_per_circuit_step", "host_readbacks_per_circuit_step", "host_wait_ms_per_circuit_step")}}
     if comm is not None:
         line["nvlink_bytes_sent_rank0"] = res.get("nvlink_bytes_sent")
 
@@ -575,7 +598,8 @@ def main():
                          "circuit_step_latency_ms": {"p50": r["circuit_step_ms_p50"], "p99": r["circuit_step_ms_p99"], "max": r["circuit_step_ms_max"]},
                          "e2e": r.get("e2e"), "gpu_launches": r["gpu_launches"], "roofline": roofline_from_profile(r["profile"]),
                          "kernel_profile": kernel_table(r["profile"]), "config": workload_cfg(q, E, r["circuit_steps_per_bench_step"], W, K, world),
-                         "last_step_out_rows": r["last_step_out_rows"]}
+                         "last_step_out_rows": r["last_step_out_rows"],
+                         "host_sync": {k: r[k] for k in ("launches_per_circuit_step", "host_readbacks_per_circuit_step", "host_wait_ms_per_circuit_step")}}
         line["queries"] = extras
         # configs[4]: every rank merges its own replica (no exchange); rank 0 reports its own and the aggregate
         sweep = []

@@ -93,6 +93,9 @@ _SIGS = {
     "batch_key_count": [_P, _P, _U64P],
     "batch_schema": [_P, C.POINTER(CSchema)],
     "batch_download_csr": [_P, _P, _PP, _P, _PP, _P],
+    "batch_download_begin": [_P, _P, _PP, _P, _PP],
+    "download_finish": [_P],
+    "ctx_sync_stats": [_P, _U64P, C.POINTER(C.c_double), C.c_int32],
     "batch_device_columns": [_P, _PP, _PP],
     "batch_last_key": [_P, _P, _U64P, C.POINTER(C.c_int32)],
     "batch_clone": [_P, _PP],

@@ -351,6 +351,7 @@ int32_t dbsp_ctx_create(int32_t device, dbsp_ctx** out) {
   c->device = device;
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->read_stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaMallocHost(&c->h_scratch, 256 * 8));
   {
     void* hm = nullptr;
@@ -399,6 +400,7 @@ int32_t dbsp_ctx_destroy(dbsp_ctx* c) {
   c->ev_pool.clear();
   cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->copy_stream);
+  cudaStreamDestroy(c->read_stream);
   c->stream = nullptr;
   c->destroyed = true;
   if (c->live_bufs.load() == 0) delete c;   // else the last DevBuf deletes it
@@ -413,6 +415,12 @@ int32_t dbsp_ctx_stats(dbsp_ctx* c, uint64_t* k, uint64_t* h2d, uint64_t* d2h, i
   if (h2d) *h2d = c->h2d_bytes;
   if (d2h) *d2h = c->d2h_bytes;
   if (reset) c->kernel_launches = c->h2d_bytes = c->d2h_bytes = 0;
+  return DBSP_OK;
+}
+int32_t dbsp_ctx_sync_stats(dbsp_ctx* c, uint64_t* n_waits, double* wait_us, int32_t reset) {
+  if (n_waits) *n_waits = c->n_sync;
+  if (wait_us) *wait_us = c->t_sync_us;
+  if (reset) { c->n_sync = 0; c->t_sync_us = 0; }
   return DBSP_OK;
 }
 void* dbsp_ctx_stream(dbsp_ctx* c) { return (void*)c->stream; }
@@ -783,6 +791,50 @@ int32_t dbsp_batch_download_csr(dbsp_ctx* ctx, const dbsp_batch* bb, uint64_t* c
   }
   if (diffs) { CUDA_TRY(cudaMemcpyAsync(diffs, b->w, b->n * 8, cudaMemcpyDeviceToHost, st)); ctx->d2h_bytes += b->n * 8; }
   CUDA_TRY(cudaStreamSynchronize(st));
+  return DBSP_OK;
+}
+
+struct dbsp_download {
+  Ctx* ctx;
+  Batch* b;
+  cudaEvent_t done;
+};
+int32_t dbsp_batch_download_begin(dbsp_ctx* ctx, const dbsp_batch* bb, uint64_t* const* cols, int64_t* diffs,
+                                  dbsp_download** out) { ENTER(ctx);
+  Batch* b = B(bb);
+  dbsp_download* d = new dbsp_download();
+  d->ctx = ctx;
+  d->b = b;
+  batch_ref(b);   // the rows must outlive the copy
+  CUDA_TRY(cudaEventCreateWithFlags(&d->done, cudaEventDisableTiming));
+  if (b->n) {
+    // the read stream picks the batch up once the kernels that produce it have run
+    cudaEvent_t ev;
+    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(ev, ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->read_stream, ev, 0));
+    CUDA_TRY(cudaEventDestroy(ev));
+    for (int l = 0; l < b->nl(); l++) {
+      if (!cols || !cols[l]) continue;
+      CUDA_TRY(cudaMemcpyAsync(cols[l], b->col[l], b->n * 8, cudaMemcpyDeviceToHost, ctx->read_stream));
+      ctx->d2h_bytes += b->n * 8;
+    }
+    if (diffs) {
+      CUDA_TRY(cudaMemcpyAsync(diffs, b->w, b->n * 8, cudaMemcpyDeviceToHost, ctx->read_stream));
+      ctx->d2h_bytes += b->n * 8;
+    }
+  }
+  CUDA_TRY(cudaEventRecord(d->done, ctx->read_stream));
+  *out = d;
+  return DBSP_OK;
+}
+int32_t dbsp_download_finish(dbsp_download* d) {
+  if (!d) return DBSP_OK;
+  cudaError_t e = cudaEventSynchronize(d->done);
+  cudaEventDestroy(d->done);
+  batch_unref(d->b);
+  delete d;
+  if (e != cudaSuccess) { set_error(std::string("download_finish: ") + cudaGetErrorString(e)); return DBSP_ERR_CUDA; }
   return DBSP_OK;
 }
 

@@ -135,6 +135,7 @@ struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // pipelined H2D uploads (dbsp_upload_begin)
+  cudaStream_t read_stream = nullptr;   // asynchronous D2H reads (dbsp_batch_download_begin): PCIe is full duplex
   // pinned scratch for small D2H readbacks (counts, min/max)
   u64* h_scratch = nullptr;   // 256 u64
   // zero-copy mailbox for small read-backs: [0] = sequence flag, [8..] = payload
@@ -220,6 +221,49 @@ __device__ __forceinline__ void mail_publish(const Mail& m, const u64* vals, int
   for (int i = 0; i < count; i++) m.p[8 + i] = vals[i];
   __threadfence_system();
   m.p[0] = m.seq;
+}
+// ---- decoupled look-back over ticket-ordered tiles ----------------------------------------------------------
+// Status word = 2-bit state (0 empty, 1 aggregate, 2 inclusive prefix) | 62-bit value; the status array is zeroed
+// before the launch and tiles take their index from an atomic ticket, so every predecessor a tile waits on is
+// resident or finished.  Relaxed device-scope accesses: flag and value share one word.
+constexpr u64 LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_MASK = (1ull << 62) - 1;
+__device__ __forceinline__ u64 lb_ld(const u64* p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void lb_st(u64* p, u64 v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Called by all 32 lanes of ONE warp of tile t with the tile's total: publishes the aggregate, sums the
+// predecessors (32 status words per round trip), publishes the inclusive prefix and returns the exclusive prefix
+// (the same value in every lane).
+__device__ __forceinline__ u64 lb_exclusive_prefix(u64* status, u32 t, u64 tile_total) {
+  const int lane = threadIdx.x & 31;
+  if (t == 0) {
+    if (lane == 0) lb_st(&status[0], LB_PREFIX | tile_total);
+    return 0;
+  }
+  if (lane == 0) lb_st(&status[t], LB_AGG | tile_total);
+  u64 base = 0;
+  long long p = (long long)t - 1;
+  while (true) {
+    const long long q = p - lane;
+    u64 x = LB_PREFIX;   // tiles before 0 contribute an empty prefix
+    if (q >= 0) {
+      do { x = lb_ld(&status[q]); } while ((x >> 62) == 0);
+    }
+    const unsigned isp = __ballot_sync(0xffffffffu, (x >> 62) == 2);
+    const int first = isp ? (__ffs(isp) - 1) : 32;
+    u64 c = (lane <= first) ? (x & LB_MASK) : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    base += c;
+    if (isp) break;
+    p -= 32;
+  }
+  if (lane == 0) lb_st(&status[t], LB_PREFIX | (base + tile_total));
+  return base;
 }
 // lexicographic compare of row i of A against row j of B over lanes [0,nl)
 __device__ __forceinline__ int cmp_rows_g(const Cols& A, u64 i, const Cols& B, u64 j, int nl, const Flips& f) {

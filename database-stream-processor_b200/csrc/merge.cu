@@ -13,16 +13,18 @@
 // tiles ahead (cp.async.bulk.prefetch.L2), then stages the *lanes* of its A and
 // B segments in shared memory with TMA bulk copies (cp.async.bulk + mbarrier:
 // one thread issues 2*L copies, no registers, no per-thread address
-// arithmetic); the weights never enter shared memory.  Every thread
-// merge-path-searches its own diagonal and serially merges IPT rows with both
-// run heads in registers, then fetches its rows' weights in one batch of
-// independent loads; kept rows are compacted as 16-bit slot ids, gathered and
-// written back coalesced.  Because both inputs are consolidated, an equal pair
+// arithmetic).  Every thread merge-path-searches its own diagonal and serially
+// merges IPT rows with both run heads in registers; kept rows are compacted as
+// 16-bit slot ids, gathered and written back coalesced.  Weights: rows of one or
+// two lanes stage them as one more lane (same TMA copies, partner sums folded in
+// shared memory, coalesced stores); wider rows keep them out of shared memory
+// (more rows in flight per SM) and fetch them in one batch of independent loads
+// after the serial merge.  Because both inputs are consolidated, an equal pair
 // is always (a, b) adjacent in merged order: the A row absorbs its partner's
 // weight, the B row is skipped — also across thread and tile boundaries (one
 // halo row on each side).  The tile's global output offset comes from a
-// decoupled look-back over per-tile status words (tile index = block index:
-// CTAs are dispatched in order, so predecessors are always resident or done).
+// decoupled look-back over per-tile status words (tile index = an arrival
+// ticket, so predecessors are always resident or done).
 // Tile shapes, register caps, look-back width and prefetch distance were swept
 // on the B200 (profiles/README.md).
 #include <algorithm>
@@ -36,7 +38,9 @@ namespace {
 #ifndef MERGE_THREADS_CFG
 #define MERGE_THREADS_CFG 256
 #endif
-constexpr int MERGE_THREADS = MERGE_THREADS_CFG;
+#ifndef MERGE_THREADS_NARROW
+#define MERGE_THREADS_NARROW 128   // threads per CTA for two-lane rows (swept: 128 x 9 rows, weights staged: 63.0 -> 64.9 %)
+#endif
 #ifndef MERGE_NARROW_MAX
 #define MERGE_NARROW_MAX 2   // rows up to this many lanes use the branch-free (select) search and serial merge
 #endif
@@ -54,6 +58,11 @@ constexpr int MERGE_THREADS = MERGE_THREADS_CFG;
 #endif
 #ifndef MERGE_LB_THREADS
 #define MERGE_LB_THREADS 32   // look-back window: predecessor tiles inspected per round trip (measured: 32 > 64 > 128 > 256)
+#endif
+#ifndef MERGE_STAGE_W_MAXL
+#define MERGE_STAGE_W_MAXL 2   // rows up to this many lanes stage their weights in shared memory as one more lane (0 = never;
+                               // swept on the B200: 1 lane 48 -> 60 % of the HBM peak; 2 lanes 63 -> 61 % with 256
+                               // threads, 64.9 % with 128 threads x 9 rows)
 #endif
 constexpr u64 ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62, ST_MASK = (1ull << 62) - 1;
 
@@ -121,11 +130,16 @@ struct MergeCfg {
   // odd rows/thread: the per-thread serial merge walks shared memory with a
   // stride of IPT 64-bit words between lanes of a warp -> bank-conflict free
   static constexpr int IPT = (L <= 2) ? MERGE_IPT_CFG : (L <= 6 ? MERGE_IPT_MID : MERGE_IPT_WIDE);
-  static constexpr int TILE = MERGE_THREADS * IPT;
+  static constexpr int THREADS = (L == 2) ? MERGE_THREADS_NARROW : MERGE_THREADS_CFG;
+  static constexpr int TILE = THREADS * IPT;
   static constexpr int S = TILE + 8;   // staged slots per array (even; room for alignment slack + halos)
-  // shared memory holds the staged lanes and 16-bit slot ids only; the weights
-  // never enter it (read from and written to HBM by the threads that need them)
-  static constexpr size_t SMEM = (size_t)S * L * 8 + (size_t)TILE * 2;
+  // STAGE_W: the weights travel like one more lane — staged by the same TMA copies, summed with their partner in
+  // shared memory, gathered with the kept rows and stored coalesced (no per-thread strided weight loads / stores).
+  // Otherwise shared memory holds the staged lanes and 16-bit slot ids only, and the weights are read from and
+  // written to HBM by the threads that need them (more rows in flight per SM).
+  static constexpr bool STAGE_W = L <= MERGE_STAGE_W_MAXL;
+  static constexpr int LS = L + (STAGE_W ? 1 : 0);   // staged arrays
+  static constexpr size_t SMEM = (size_t)S * LS * 8 + (size_t)TILE * 2;
 };
 
 // a-count of the merge path at diagonal d: number of A rows among the first d
@@ -339,23 +353,41 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, const i64* __restric
   // thread's last row — the B head left over after the loop (possibly the first
   // row of the next thread / tile).  Input weights are never zero (batch
   // invariant), so only a partner sum can cancel.
-  i64 wv[IPT];
+  constexpr bool STAGE_W = MergeCfg<L>::STAGE_W;
+  u64* const sw = sl + (size_t)L * S;   // staged weights (STAGE_W only)
+  i64 wv[STAGE_W ? 1 : IPT];
+  if constexpr (STAGE_W) {
+    // An A row with a partner is owned by this thread and its partner (a B row: the next merged row) is never
+    // written by anyone, so the sum can be folded into the A row's slot in place.
+    if (pmask) {   // rare
 #pragma unroll
-  for (int k = 0; k < IPT; k++) {
-    wv[k] = 0;
-    if (dt + k < n) {
-      const int s = (int)src[k];
-      wv[k] = (s >= ob) ? wBg[s - ob] : wAg[s - oa];
+      for (int k = 0; k < IPT; k++) {
+        if (pmask & (1u << k)) {
+          const u32 ps = (k + 1 < IPT && dt + k + 1 < n) ? src[k + 1 < IPT ? k + 1 : k] : (u32)(ob + bi);
+          const u64 sum = sw[src[k]] + sw[ps];
+          if (sum == 0) keep &= ~(1u << k);
+          else sw[src[k]] = sum;
+        }
+      }
     }
-  }
-  if (pmask) {   // rare
-    const i64 wlast = prev_eq ? wBg[bi] : 0;
+  } else {
 #pragma unroll
     for (int k = 0; k < IPT; k++) {
-      if (pmask & (1u << k)) {
-        const i64 pw = (k + 1 < IPT && dt + k + 1 < n) ? wv[k + 1 < IPT ? k + 1 : k] : wlast;
-        wv[k] = (i64)((u64)wv[k] + (u64)pw);
-        if (wv[k] == 0) keep &= ~(1u << k);
+      wv[k] = 0;
+      if (dt + k < n) {
+        const int s = (int)src[k];
+        wv[k] = (s >= ob) ? wBg[s - ob] : wAg[s - oa];
+      }
+    }
+    if (pmask) {   // rare
+      const i64 wlast = prev_eq ? wBg[bi] : 0;
+#pragma unroll
+      for (int k = 0; k < IPT; k++) {
+        if (pmask & (1u << k)) {
+          const i64 pw = (k + 1 < IPT && dt + k + 1 < n) ? wv[k + 1 < IPT ? k + 1 : k] : wlast;
+          wv[k] = (i64)((u64)wv[k] + (u64)pw);
+          if (wv[k] == 0) keep &= ~(1u << k);
+        }
       }
     }
   }
@@ -372,7 +404,7 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, const i64* __restric
   __syncthreads();
   u32 warp_off = 0, tile_total = 0;
 #pragma unroll
-  for (int wi = 0; wi < MERGE_THREADS / 32; wi++) {
+  for (int wi = 0; wi < MergeCfg<L>::THREADS / 32; wi++) {
     u32 v = s_warp[wi];
     if (wi < (tid >> 5)) warp_off += v;
     tile_total += v;
@@ -396,7 +428,7 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, const i64* __restric
     if (tid == 0) { st_relaxed(&status[0], ST_PREFIX | (u64)tile_total); s_base = 0; }
   } else {
     if (tid == 0) st_relaxed(&status[t], ST_AGG | (u64)tile_total);
-    constexpr int LBT = MERGE_LB_THREADS < MERGE_THREADS ? MERGE_LB_THREADS : MERGE_THREADS;
+    constexpr int LBT = MERGE_LB_THREADS < MergeCfg<L>::THREADS ? MERGE_LB_THREADS : MergeCfg<L>::THREADS;
     constexpr int NW = LBT / 32;
     u64 base_acc = 0;
     long long p = (long long)t - 1;   // window = tiles p, p-1, ..., p-(LBT-1)
@@ -448,12 +480,13 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, const i64* __restric
   }
   __syncthreads();
   const u64 base = s_base;
-  for (u32 o = tid; o < tile_total; o += MERGE_THREADS) {
+  for (u32 o = tid; o < tile_total; o += MergeCfg<L>::THREADS) {
     u32 s = perm[o];
 #pragma unroll
     for (int l = 0; l < L; l++) O.c[l][base + o] = sl[l * S + s] ^ f.f[l];
+    if constexpr (STAGE_W) wO[base + o] = (i64)sw[s];
   }
-  {   // weights: straight from registers to the thread's own (contiguous) output slots
+  if constexpr (!STAGE_W) {   // weights: straight from registers to the thread's own (contiguous) output slots
     u64 wpos = base + (off - cnt);
 #pragma unroll
     for (int k = 0; k < IPT; k++) {
@@ -473,29 +506,38 @@ __device__ __forceinline__ void merge_process_tile(u64* sl, const i64* __restric
 #ifndef MERGE_CTAS_WIDE
 #define MERGE_CTAS_WIDE 4   // 5-8 lanes (5 lanes x 5 rows: 46 -> 61 %; 8 lanes x 3 rows: 57 %)
 #endif
-#define MERGE_MIN_CTAS_FOR(L) ((L) <= 2 ? MERGE_MIN_CTAS : ((L) <= 4 ? MERGE_CTAS_MID : MERGE_CTAS_WIDE))
+#ifndef MERGE_CTAS_L2
+#define MERGE_CTAS_L2 7   // two-lane rows: 128 threads, 30 KB staged per CTA
+#endif
+#define MERGE_MIN_CTAS_FOR(L) ((L) == 1 ? MERGE_MIN_CTAS : ((L) == 2 ? MERGE_CTAS_L2 : ((L) <= 4 ? MERGE_CTAS_MID : MERGE_CTAS_WIDE)))
 template <int L>
-__global__ void __launch_bounds__(MERGE_THREADS, MERGE_MIN_CTAS_FOR(L))
+__global__ void __launch_bounds__(MergeCfg<L>::THREADS, MERGE_MIN_CTAS_FOR(L))
 k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __restrict__ wB, u64 nB, Flips f,
               const u64* __restrict__ part, u32 ntiles, u64* status, MCols O, i64* wO, u64* n_out,
-              int use_tma, Mail mail) {
+              int use_tma, Mail mail, u32* ticket) {
   constexpr int IPT = MergeCfg<L>::IPT;
   constexpr int TILE = MergeCfg<L>::TILE;
   constexpr int S = MergeCfg<L>::S;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   u64* sl = (u64*)smem_raw;                                   // L lanes of S staged slots
-  unsigned short* perm = (unsigned short*)(sl + (size_t)L * S);   // TILE staged-slot ids of kept rows
+  unsigned short* perm = (unsigned short*)(sl + (size_t)MergeCfg<L>::LS * S);   // TILE staged-slot ids of kept rows
   __shared__ __align__(8) u64 s_mbar;
   __shared__ u64 s_base;
-  __shared__ u32 s_warp[MERGE_THREADS / 32];
-  __shared__ int s_lb_first[MERGE_THREADS / 32];
-  __shared__ u64 s_lb_all[MERGE_THREADS / 32], s_lb_upto[MERGE_THREADS / 32];
+  __shared__ u32 s_warp[MergeCfg<L>::THREADS / 32];
+  __shared__ int s_lb_first[MergeCfg<L>::THREADS / 32];
+  __shared__ u64 s_lb_all[MergeCfg<L>::THREADS / 32], s_lb_upto[MergeCfg<L>::THREADS / 32];
 
   const int tid = threadIdx.x;
-  // Tile index = block index: CTAs are dispatched in increasing blockIdx order,
-  // so every predecessor a look-back waits on is resident or finished.
-  const u32 t = blockIdx.x;
-  if (tid == 0) mbar_init(&s_mbar, 1);
+  // Tile index = arrival ticket: every predecessor a look-back waits on has taken its ticket earlier and is
+  // therefore resident or finished — a forward-progress guarantee that does not rely on the order in which the
+  // hardware dispatches blocks (MPS, preemption, compute-sanitizer).
+  __shared__ u32 s_ticket;
+  if (tid == 0) {
+    s_ticket = atomicAdd(ticket, 1u);
+    mbar_init(&s_mbar, 1);
+  }
+  __syncthreads();
+  const u32 t = s_ticket;
   const u64 total = nA + nB;
   const u64 d0 = (u64)t * TILE;
   const u64 d1 = (d0 + TILE < total) ? d0 + TILE : total;
@@ -520,7 +562,6 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
     l2_prefetch(wB + pb0, (pb1 - pb0) * 8);
   }
 #endif
-  __syncthreads();   // s_mbar initialised
   bool any_flip = false;
 #pragma unroll
   for (int l = 0; l < L; l++) any_flip = any_flip || (f.f[l] != 0);
@@ -544,16 +585,18 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
     const int cb = (eb > (long long)b0) ? (int)(((eb - gb) + 1) & ~1ll) : 0;
     ob = sb + (int)((long long)b0 - gb);
     if (tid == 0) {
-      const unsigned bytes = (unsigned)(ca + cb) * 8u * L;
+      const unsigned bytes = (unsigned)(ca + cb) * 8u * MergeCfg<L>::LS;
       if (bytes) {
         mbar_expect_tx(&s_mbar, bytes);
         if (ca) {
 #pragma unroll
           for (int l = 0; l < L; l++) tma_bulk_g2s(sl + l * S, A.c[l] + ga, (unsigned)ca * 8u, &s_mbar);
+          if constexpr (MergeCfg<L>::STAGE_W) tma_bulk_g2s(sl + L * S, wA + ga, (unsigned)ca * 8u, &s_mbar);
         }
         if (cb) {
 #pragma unroll
           for (int l = 0; l < L; l++) tma_bulk_g2s(sl + l * S + sb, B.c[l] + gb, (unsigned)cb * 8u, &s_mbar);
+          if constexpr (MergeCfg<L>::STAGE_W) tma_bulk_g2s(sl + L * S + sb, wB + gb, (unsigned)cb * 8u, &s_mbar);
         }
       }
     }
@@ -564,7 +607,7 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
     const int nslots = na + nb + 2;
 #pragma unroll
     for (int k = 0; k < IPT + 1; k++) {
-      const int x = tid + k * MERGE_THREADS;
+      const int x = tid + k * MergeCfg<L>::THREADS;
       if (x < nslots) {
         const bool from_a = x <= na;
         const bool skip = (x == 0 && !has_prev) || (x == nslots - 1 && !has_next);
@@ -572,6 +615,7 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
           const u64 g = from_a ? (a0 + x - 1) : (b0 + (x - 1 - na));
 #pragma unroll
           for (int l = 0; l < L; l++) cp_async8(&sl[l * S + x], (from_a ? A.c[l] : B.c[l]) + g);
+          if constexpr (MergeCfg<L>::STAGE_W) cp_async8(&sl[L * S + x], (from_a ? wA : wB) + g);
         }
       }
     }
@@ -579,7 +623,7 @@ k_merge_tiles(Cols A, const i64* __restrict__ wA, u64 nA, Cols B, const i64* __r
   }
   if (any_flip) {   // i64 lanes: stage the order-preserving image
     __syncthreads();
-    for (int x = tid; x < S; x += MERGE_THREADS) {
+    for (int x = tid; x < S; x += MergeCfg<L>::THREADS) {
 #pragma unroll
       for (int l = 0; l < L; l++) sl[l * S + x] ^= f.f[l];
     }
@@ -597,7 +641,8 @@ bool uniform_phase(const Batch* b) {
   size_t ph = ((size_t)b->col[0] >> 3) & 1;
   for (int l = 1; l < b->nl(); l++)
     if ((((size_t)b->col[l] >> 3) & 1) != ph) return false;
-  return true;   // the weights are not staged
+  // the weights ride along with the lanes when they are staged
+  return b->nl() > MERGE_STAGE_W_MAXL || (((size_t)b->w >> 3) & 1) == ph;
 }
 
 template <int L>
@@ -607,13 +652,13 @@ int32_t merge_launch(Ctx* ctx, const Batch* a, const Batch* b, Batch** out) {
   u64 total = a->n + b->n;
   u32 ntiles = (u32)((total + Cfg::TILE - 1) / Cfg::TILE);
   BufP aux;
-  // part[ntiles+1] u64 | status[ntiles] u64 | n_out u64
-  size_t aux_u64 = (size_t)(ntiles + 1) + ntiles + 1;
+  // part[ntiles+1] u64 | status[ntiles] u64 | n_out u64 | ticket u64
+  size_t aux_u64 = (size_t)(ntiles + 1) + ntiles + 2;
   TRY(dev_alloc(ctx, aux_u64 * 8, &aux));
   u64* part = (u64*)aux->p;
   u64* status = part + (ntiles + 1);
   u64* n_out = status + ntiles;
-  CUDA_TRY(cudaMemsetAsync(status, 0, (size_t)(ntiles + 1) * 8, st));
+  CUDA_TRY(cudaMemsetAsync(status, 0, (size_t)(ntiles + 2) * 8, st));
   Batch* o;
   MCols oc;
   i64* ow;
@@ -629,8 +674,8 @@ int32_t merge_launch(Ctx* ctx, const Batch* a, const Batch* b, Batch** out) {
   }
   ProfScope* ps = new ProfScope(ctx, KID_MERGE, 0);
   const Mail mail = mail_begin(ctx);
-  k_merge_tiles<L><<<ntiles, MERGE_THREADS, Cfg::SMEM, st>>>(a->cols(), a->w, a->n, b->cols(), b->w, b->n, f, part, ntiles,
-                                                           status, oc, ow, n_out, use_tma, mail);
+  k_merge_tiles<L><<<ntiles, MergeCfg<L>::THREADS, Cfg::SMEM, st>>>(a->cols(), a->w, a->n, b->cols(), b->w, b->n, f, part, ntiles,
+                                                           status, oc, ow, n_out, use_tma, mail, (u32*)(n_out + 1));
   long ps_idx = ps->idx;
   delete ps;   // records the end event
   ctx->kernel_launches += 2;

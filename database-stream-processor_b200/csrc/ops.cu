@@ -24,16 +24,30 @@ struct Env {
   const u64* key;
   const u64* lv;
   const u64* rv;
+  __device__ __forceinline__ u64 k(int i) const { return key[i]; }
+  __device__ __forceinline__ u64 l(int i) const { return lv[i]; }
+  __device__ __forceinline__ u64 r(int i) const { return rv[i]; }
 };
-__device__ __forceinline__ u64 src_val(const dbsp_src& s, const Env& e) {
+// one row of a column table / batch, read in place: only the lanes the closure names are ever loaded
+struct ColEnv {
+  const Cols& c;
+  int nk;
+  u64 row;
+  __device__ __forceinline__ u64 k(int i) const { return c.c[i][row]; }
+  __device__ __forceinline__ u64 l(int i) const { return c.c[nk + i][row]; }
+  __device__ __forceinline__ u64 r(int i) const { return c.c[nk + i][row]; }
+};
+template <class E>
+__device__ __forceinline__ u64 src_val(const dbsp_src& s, const E& e) {
   switch (s.kind) {
-    case DBSP_SRC_KEY: return e.key[s.idx];
-    case DBSP_SRC_LVAL: return e.lv[s.idx];
-    case DBSP_SRC_RVAL: return e.rv[s.idx];
+    case DBSP_SRC_KEY: return e.k(s.idx);
+    case DBSP_SRC_LVAL: return e.l(s.idx);
+    case DBSP_SRC_RVAL: return e.r(s.idx);
     default: return (u64)s.cst;
   }
 }
-__device__ __forceinline__ u64 expr_val(const dbsp_expr& x, const Env& e) {
+template <class E>
+__device__ __forceinline__ u64 expr_val(const dbsp_expr& x, const E& e) {
   u64 a = src_val(x.a, e);
   switch (x.op) {
     case DBSP_OP_COPY: return a;
@@ -48,7 +62,8 @@ __device__ __forceinline__ u64 expr_val(const dbsp_expr& x, const Env& e) {
   }
   return a;
 }
-__device__ __forceinline__ bool pred_ok(const dbsp_pred& p, const Env& e) {
+template <class E>
+__device__ __forceinline__ bool pred_ok(const dbsp_pred& p, const E& e) {
   u64 a = src_val(p.a, e), b = src_val(p.b, e);
   if (p.cmp == DBSP_CMP_IN) return a < 64 && ((b >> a) & 1);
   int c = p.is_signed ? (((i64)a < (i64)b) ? -1 : ((i64)a > (i64)b)) : ((a < b) ? -1 : (a > b));
@@ -73,42 +88,81 @@ __device__ __forceinline__ bool project(const dbsp_proj& p, const Env& e, u64* r
 }
 
 // flat_map_index over a raw table (filter_map.rs:700-724) / map_index over a
-// batch.  Order preserving: phase 0 counts the surviving rows per CTA, a scan
-// of the CTA counts gives each CTA its output base, phase 1 re-evaluates the
-// closure and writes the survivors in input order — so inputs that are already
-// ordered on the output key (id-ordered event tables, monotone projections)
-// reach the sort-free path of consolidate_rows.
-constexpr int PROJ_ROWS = TB * 4;
-__global__ void k_project_rows(Cols in, int nk_in, int n_in_lanes, unsigned used_mask, const i64* w, u64 n,
-                               dbsp_proj proj, int phase, u32* blk_cnt, const u32* blk_base, MCols out, i64* out_w) {
-  __shared__ u32 s_warp[TB / 32];
-  u64 base = (u64)blockIdx.x * PROJ_ROWS;
-  u32 run = phase ? blk_base[blockIdx.x] : 0;
-  for (int it = 0; it < 4; it++) {
-    u64 i = base + (u64)it * TB + threadIdx.x;
-    u64 lanes[MAXL], row[MAXL];
+// batch, in one pass and order preserving: a CTA evaluates the predicates of its PROJ_ROWS rows, a decoupled
+// look-back over the CTA totals gives it its output base, and the survivors' output rows are evaluated and written
+// in input order — so inputs that are already ordered on the output key (id-ordered event tables, monotone
+// projections) reach the sort-free path of consolidate_rows.  The surviving-row count stays on the device
+// (*d_m): the census of consolidate_rows returns it.  identity != 0 (no predicates): output slot = input row.
+constexpr int PROJ_IT = 4;
+constexpr int PROJ_ROWS = TB * PROJ_IT;
+__global__ void __launch_bounds__(TB)
+k_project_rows(Cols in, int nk_in, const i64* w, u64 n, dbsp_proj proj, int identity, u32 ntiles, u32* ticket,
+               u64* status, MCols out, i64* out_w, u32* d_m) {
+  static_assert(PROJ_IT * (TB / 32) == 32, "one warp scans the per-(round, warp) counts");
+  __shared__ u32 s_tile;
+  __shared__ u32 s_cnt[32], s_off[32];
+  __shared__ u64 s_base;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nl = proj.out_schema.n_key_lanes + proj.out_schema.n_val_lanes;
+  if (identity) {
+    const u64 base = (u64)blockIdx.x * PROJ_ROWS;
+    for (int it = 0; it < PROJ_IT; it++) {
+      const u64 i = base + (u64)it * TB + tid;
+      if (i < n) {
+        const ColEnv e{in, nk_in, i};
+        for (int l = 0; l < nl; l++) out.c[l][i] = expr_val(proj.out[l], e);
+        out_w[i] = w ? w[i] : 1;
+      }
+    }
+    return;
+  }
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const u32 t = s_tile;
+  const u64 base_row = (u64)t * PROJ_ROWS;
+  unsigned okbits = 0, rk = 0;   // rk: 8 bits per round = number of surviving rows before this lane in its warp
+  for (int it = 0; it < PROJ_IT; it++) {
+    const u64 i = base_row + (u64)it * TB + tid;
     bool ok = false;
     if (i < n) {
-      for (int l = 0; l < n_in_lanes; l++) lanes[l] = ((used_mask >> l) & 1) ? in.c[l][i] : 0;   // untouched columns are never read
-      Env e{lanes, lanes + nk_in, lanes + nk_in};
-      ok = project(proj, e, row);
+      const ColEnv e{in, nk_in, i};
+      ok = true;
+      for (int q = 0; q < proj.n_pred; q++) ok = ok && pred_ok(proj.pred[q], e);
     }
-    unsigned m = __ballot_sync(0xffffffffu, ok);
-    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) s_warp[wid] = __popc(m);
-    __syncthreads();
-    u32 before = 0, tot = 0;
-    for (int k = 0; k < TB / 32; k++) { u32 v = s_warp[k]; if (k < wid) before += v; tot += v; }
-    if (phase && ok) {
-      u64 pos = (u64)run + before + __popc(m & ((1u << lane) - 1));
-      int nl = proj.out_schema.n_key_lanes + proj.out_schema.n_val_lanes;
-      for (int l = 0; l < nl; l++) out.c[l][pos] = row[l];
-      out_w[pos] = w ? w[i] : 1;
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_cnt[it * (TB / 32) + wid] = __popc(m);
+    if (ok) {
+      okbits |= 1u << it;
+      rk |= (unsigned)__popc(m & ((1u << lane) - 1)) << (8 * it);
     }
-    run += tot;
-    __syncthreads();
   }
-  if (!phase && threadIdx.x == 0) blk_cnt[blockIdx.x] = run;
+  __syncthreads();
+  if (wid == 0) {
+    const u32 c = s_cnt[lane];
+    u32 incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+    s_off[lane] = incl - c;
+    const u64 base = lb_exclusive_prefix(status, t, (u64)total);
+    if (lane == 0) {
+      s_base = base;
+      if (t == ntiles - 1) *d_m = (u32)(base + total);
+    }
+  }
+  __syncthreads();
+  const u64 base = s_base;
+  for (int it = 0; it < PROJ_IT; it++) {
+    if (!((okbits >> it) & 1)) continue;
+    const u64 i = base_row + (u64)it * TB + tid;
+    const u64 pos = base + s_off[it * (TB / 32) + wid] + ((rk >> (8 * it)) & 0xffu);
+    const ColEnv e{in, nk_in, i};
+    for (int l = 0; l < nl; l++) out.c[l][pos] = expr_val(proj.out[l], e);
+    out_w[pos] = w ? w[i] : 1;
+  }
 }
 
 // ---------------- delta x trace probes -----------------------------------------
@@ -118,9 +172,8 @@ __global__ void k_project_rows(Cols in, int nk_in, int n_in_lanes, unsigned used
 // `seek_key` of cursor/mod.rs + advance.rs:25-72).  One search per key instead of
 // one per row; all spine batches in one launch.
 __global__ void k_probe_keys(Cols D, const u64* kstart, const u32* d_nkeys, BatchRefs tr, int nk, Flips f, u32* lo_out,
-                             u32* cnt_out, u32* ktot, unsigned long long* tot64) {
+                             u32* cnt_out, u32* ktot) {
   const u64 gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gtid == 0) { tot64[0] = 0; tot64[1] = 0; }   // match total / finished-block counter of k_row_counts (next kernel on the stream)
   const u64 nkeys = (u64)*d_nkeys;   // the exact key count lives on the device; the grid is a fixed-size grid-stride loop
   for (u64 k = gtid; k < nkeys; k += (u64)gridDim.x * blockDim.x) {
     const u64 row = kstart[k];
@@ -143,32 +196,124 @@ __global__ void k_probe_keys(Cols D, const u64* kstart, const u32* d_nkeys, Batc
   }
 }
 
-// matches of every delta row = matches of its key; also the row -> key index
-__global__ void k_row_counts(const u32* head_exscan, const u32* ktot, u64 nd, u32* rowcnt, u32* ki,
-                             unsigned long long* tot64, Mail mail) {
-  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long c = 0;
-  if (i == nd) rowcnt[nd] = 0;
-  if (i < nd) {
-    u32 k = head_exscan[i + 1] - 1;   // inclusive head count - 1
-    ki[i] = k;
-    c = ktot[k];
-    rowcnt[i] = (u32)c;
-  }
-  // 64-bit total of the matches: the 32-bit scan below wraps silently on a skewed join, this does not
+// Key segments of a sorted batch in one pass: a row is a head when it differs from its predecessor over the
+// first nk lanes.  Each thread owns SEG_IPT consecutive rows; block scan of the head counts + decoupled look-back
+// over the tiles give every head its key index: kstart[key] = row, ki[row] = key of the row, kstart[nkeys] = n
+// and *d_nkeys = nkeys (the key count never leaves the device).
+constexpr int SEG_IPT = 4, SEG_TILE = TB * SEG_IPT;
+__global__ void __launch_bounds__(TB)
+k_key_segments(Cols C, u64 n, int nk, u32 ntiles, u32* ticket, u64* status, u64* kstart, u32* ki, u32* d_nkeys) {
+  __shared__ u32 s_tile, s_warp[TB / 32];
+  __shared__ u64 s_base;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const u32 t = s_tile;
+  const u64 i0 = (u64)t * SEG_TILE + (u64)tid * SEG_IPT;
+  unsigned heads = 0;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd(tot64, c);
-  // the last block to finish publishes the total to the host mailbox
-  __shared__ unsigned s_last;
-  __threadfence();
+  for (int k = 0; k < SEG_IPT; k++) {
+    const u64 i = i0 + k;
+    if (i < n) {
+      bool head = i == 0;
+      if (!head)
+        for (int l = 0; l < nk; l++)
+          if (C.c[l][i] != C.c[l][i - 1]) { head = true; break; }
+      heads |= (head ? 1u : 0u) << k;
+    }
+  }
+  const u32 cnt = __popc(heads);
+  u32 incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[wid] = incl;
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&tot64[1], 1ull) == (unsigned long long)(gridDim.x - 1);
+  u32 woff = 0, tile_total = 0;
+#pragma unroll
+  for (int k = 0; k < TB / 32; k++) {
+    const u32 v = s_warp[k];
+    if (k < wid) woff += v;
+    tile_total += v;
+  }
+  if (wid == 0) {
+    const u64 base = lb_exclusive_prefix(status, t, (u64)tile_total);
+    if (lane == 0) {
+      s_base = base;
+      if (t == ntiles - 1) {
+        *d_nkeys = (u32)(base + tile_total);
+        kstart[base + tile_total] = n;
+      }
+    }
+  }
   __syncthreads();
-  if (s_last && threadIdx.x == 0) {
-    __threadfence();
-    const u64 tot = *(volatile unsigned long long*)tot64;
-    mail_publish(mail, &tot, 1);
+  u32 run = (u32)s_base + woff + incl - cnt;   // heads before this thread's first row
+#pragma unroll
+  for (int k = 0; k < SEG_IPT; k++) {
+    const u64 i = i0 + k;
+    if (i < n) {
+      if ((heads >> k) & 1) { kstart[run] = i; run++; }
+      ki[i] = run - 1;
+    }
+  }
+}
+
+// matches of every delta row = matches of its key, and their exclusive running sum (the output slot of the row's
+// first match) in the same pass: ex[i] for i < nd, ex[nd] = total.  The total is carried in 64 bits through the
+// look-back (a skewed join can exceed 2^32 matches; the 32-bit ex[] wraps then, and the host rejects the step on
+// the exact total, which the last tile publishes to the host mailbox).
+__global__ void __launch_bounds__(TB)
+k_row_counts_scan(const u32* __restrict__ ki, const u32* __restrict__ ktot, u64 nd, u32 ntiles, u32* ticket, u64* status,
+                  u32* ex, Mail mail) {
+  __shared__ u32 s_tile;
+  __shared__ u64 s_warp[TB / 32];
+  __shared__ u64 s_base;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const u32 t = s_tile;
+  const u64 i0 = (u64)t * SEG_TILE + (u64)tid * SEG_IPT;
+  u32 c[SEG_IPT];
+  u64 sum = 0;
+#pragma unroll
+  for (int k = 0; k < SEG_IPT; k++) {
+    c[k] = (i0 + k < nd) ? ktot[ki[i0 + k]] : 0u;
+    sum += c[k];
+  }
+  u64 incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u64 v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  u64 woff = 0, tile_total = 0;
+#pragma unroll
+  for (int k = 0; k < TB / 32; k++) {
+    const u64 v = s_warp[k];
+    if (k < wid) woff += v;
+    tile_total += v;
+  }
+  if (wid == 0) {
+    const u64 base = lb_exclusive_prefix(status, t, tile_total);
+    if (lane == 0) {
+      s_base = base;
+      if (t == ntiles - 1) {
+        const u64 tot = base + tile_total;
+        ex[nd] = (u32)tot;
+        mail_publish(mail, &tot, 1);
+      }
+    }
+  }
+  __syncthreads();
+  u64 run = s_base + woff + incl - sum;
+#pragma unroll
+  for (int k = 0; k < SEG_IPT; k++) {
+    if (i0 + k < nd) ex[i0 + k] = (u32)run;
+    run += c[k];
   }
 }
 
@@ -349,18 +494,6 @@ __global__ void k_scatter_index(const u32* keep, const u32* pos, u64 n, u64* out
   if (i < n && keep[i]) out[pos[i]] = i;
   if (i == 0) out[nout] = n;
 }
-// the same with the number of kept rows read from the scan (pos[n]) instead of the host
-__global__ void k_scatter_index_dev(const u32* keep, const u32* pos, u64 n, u64* out) {
-  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && keep[i]) out[pos[i]] = i;
-  if (i == 0) out[pos[n]] = n;
-}
-
-__global__ void k_iota_u32(u32* out, u32 n, u32 mul) {
-  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = i * mul;
-}
-
 __global__ void k_fill_i64(i64* out, u64 n, i64 v) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = v;
@@ -733,69 +866,64 @@ int32_t project_and_consolidate(Ctx* ctx, const Cols& in, int nk_in, int n_in_la
   int Lo = os.n_key_lanes + os.n_val_lanes;
   if (n == 0) { *out = batch_new_empty(ctx, os); return DBSP_OK; }
   ROWS32(n, "map_index / flat_map_index");
-  unsigned g = (unsigned)((n + PROJ_ROWS - 1) / PROJ_ROWS);
-  const unsigned umask = proj_used_mask(proj, nk_in);
+  const unsigned g = (unsigned)((n + PROJ_ROWS - 1) / PROJ_ROWS);
+  const bool filtered = proj.n_pred > 0;
+  const u64 m = n;   // upper bound when a filter is present
+  u64* status = nullptr;
+  u32* ticket = nullptr;
+  u32* d_mw = nullptr;
   BufP cb;
-  TRY(dev_alloc(ctx, (size_t)(g + 1) * 4 * 2, &cb));
-  u32* blk_cnt = (u32*)cb->p;
-  u32* blk_base = blk_cnt + (g + 1);
-  u64 m = n;   // upper bound when a filter is present
-  const u32* d_m = nullptr;
-  MCols none;
-  for (int l = 0; l < MAXL; l++) none.c[l] = nullptr;
-  long pidx;
-  {
-    ProfScope ps(ctx, KID_PROJECT, 0);
-    pidx = ps.idx;
-    if (proj.n_pred > 0) {
-      k_project_rows<<<g, TB, 0, ctx->stream>>>(in, nk_in, n_in_lanes, umask, w, n, proj, 0, blk_cnt, nullptr, none, nullptr);
-      LAUNCH_COUNT(ctx);
-      CUDA_TRY(cudaMemsetAsync(blk_cnt + g, 0, 4, ctx->stream));
-      TRY(exclusive_scan_u32(ctx, blk_cnt, blk_base, g));
-      d_m = blk_base + g;   // surviving-row count stays on the device; the census of consolidate_rows returns it
-    } else {
-      k_iota_u32<<<(g + TB - 1) / TB, TB, 0, ctx->stream>>>(blk_base, g, PROJ_ROWS);
-      LAUNCH_COUNT(ctx);
-    }
+  if (filtered) {
+    // status[g] u64 | ticket u32, surviving-row count u32
+    TRY(dev_alloc(ctx, (size_t)(g + 1) * 8, &cb));
+    CUDA_TRY(cudaMemsetAsync(cb->p, 0, (size_t)(g + 1) * 8, ctx->stream));
+    status = (u64*)cb->p;
+    ticket = (u32*)(status + g);
+    d_mw = ticket + 1;   // stays on the device; the census of consolidate_rows returns it
   }
+  const u32* d_m = d_mw;
   TmpRows t;
   TRY(tmp_alloc(ctx, Lo, m, &t));
   {
+    // the lanes the closure names read once, the output rows written once (bound: every row survives)
     ProfScope ps(ctx, KID_PROJECT, n * (u64)(used_lanes(proj, n_in_lanes, nk_in) + (w ? 1 : 0)) * 8 + m * (u64)(Lo + 1) * 8);
-    k_project_rows<<<g, TB, 0, ctx->stream>>>(in, nk_in, n_in_lanes, umask, w, n, proj, 1, nullptr, blk_base, t.c, t.w);
+    k_project_rows<<<g, TB, 0, ctx->stream>>>(in, nk_in, w, n, proj, filtered ? 0 : 1, g, ticket, status, t.c, t.w, d_mw);
   }
   LAUNCH_COUNT(ctx);
-  if (pidx >= 0) ctx->prof[pidx].bytes = proj.n_pred > 0 ? n * (u64)used_lanes(proj, n_in_lanes, nk_in) * 8 : 0;
   return consolidate_rows(ctx, os, t.cc(), t.w, m, &t.buf, out, d_m);
 }
 
 // Probe `delta` against every batch of `trace` and expand the matches.
 // proj == nullptr: gather the matching trace rows unchanged.
 // key segment starts of the first nk lanes: kstart[nkeys+1] (u64 row indices),
-// plus the exclusive scan of the head flags (u32[n+1]) used for row -> key.
-static int32_t key_segments(Ctx* ctx, const Batch* b, int nk, BufP* kstart, BufP* head_ex, const u32** d_nkeys) {
-  // No read-back: the key count stays on the device (the scan's total, pos[n]); buffers and grids downstream are
-  // sized by the row count, an upper bound of it.
+// plus the key index of every row (u32[n]).
+static int32_t key_segments(Ctx* ctx, const Batch* b, int nk, BufP* kstart, BufP* ki, const u32** d_nkeys) {
+  // No read-back: the key count stays on the device; buffers and grids downstream are sized by the row count, an
+  // upper bound of it.  kstart: u64[n+1] (+ aux words behind it), ki: u32[n].
   ROWS32(b->n, "key_segments");
-  BufP fb;
-  TRY(dev_alloc(ctx, (size_t)(b->n + 1) * 4, &fb));
-  TRY(dev_alloc(ctx, (size_t)(b->n + 1) * 4, head_ex));
-  u32* flags = (u32*)fb->p;
-  u32* pos = (u32*)(*head_ex)->p;
-  k_key_heads<<<blocks(b->n + 1), TB, 0, ctx->stream>>>(b->cols(), b->n, nk, flags);
+  const u64 n = b->n;
+  const u32 ntiles = (u32)((n + SEG_TILE - 1) / SEG_TILE);
+  // kstart[n+1] u64 | status[ntiles] u64 | ticket u32, nkeys u32
+  TRY(dev_alloc(ctx, (size_t)(n + 1 + ntiles + 1) * 8, kstart));
+  TRY(dev_alloc(ctx, (size_t)(n + 1) * 4, ki));
+  u64* ks = (u64*)(*kstart)->p;
+  u64* status = ks + (n + 1);
+  u32* ticket = (u32*)(status + ntiles);
+  u32* nkeys = ticket + 1;
+  CUDA_TRY(cudaMemsetAsync(status, 0, (size_t)(ntiles + 1) * 8, ctx->stream));
+  {
+    ProfScope ps(ctx, KID_PROBE_RANGES, n * (u64)nk * 8 + n * 12);
+    k_key_segments<<<ntiles, TB, 0, ctx->stream>>>(b->cols(), n, nk, ntiles, ticket, status, ks, (u32*)(*ki)->p, nkeys);
+  }
   LAUNCH_COUNT(ctx);
-  TRY(exclusive_scan_u32(ctx, flags, pos, b->n));
-  TRY(dev_alloc(ctx, (size_t)(b->n + 1) * 8, kstart));
-  k_scatter_index_dev<<<blocks(b->n), TB, 0, ctx->stream>>>(flags, pos, b->n, (u64*)(*kstart)->p);
-  LAUNCH_COUNT(ctx);
-  *d_nkeys = pos + b->n;
+  *d_nkeys = nkeys;
   return DBSP_OK;
 }
 
 // Probe `delta` against (up to MAX_REFS) batches of `trace` and expand the matches.
 // proj == nullptr: gather the matching trace rows unchanged.
 static int32_t probe_chunk(Ctx* ctx, const Batch* delta, int nk, Batch* const* tb, int nb, const dbsp_proj* proj,
-                           int delta_is_left, const dbsp_schema& out_schema, const u64* kstart, const u32* head_ex,
+                           int delta_is_left, const dbsp_schema& out_schema, const u64* kstart, const u32* ki,
                            const u32* d_nkeys, Batch** out) {
   cudaStream_t st = ctx->stream;
   const u64 nd = delta->n;
@@ -817,11 +945,14 @@ static int32_t probe_chunk(Ctx* ctx, const Batch* delta, int nk, Batch* const* t
   u32* lo = (u32*)kb->p;
   u32* cnt = lo + (size_t)nkeys * nb;
   u32* ktot = cnt + (size_t)nkeys * nb;
-  TRY(dev_alloc(ctx, (size_t)(nd + 1) * 4 * 3, &rb));
-  u32* rowcnt = (u32*)rb->p;
-  u32* ex = rowcnt + (nd + 1);
-  u32* ki = ex + (nd + 1);
-  unsigned long long* tot64 = (unsigned long long*)(ctx->d_scratch + 24);
+  // ex[nd+1] u32 (padded to u64) | status[ntiles] u64 | ticket u64
+  const u32 ntiles = (u32)((nd + SEG_TILE - 1) / SEG_TILE);
+  const size_t ex_u64 = (size_t)(nd + 2) / 2 + 1;
+  TRY(dev_alloc(ctx, (ex_u64 + ntiles + 1) * 8, &rb));
+  u32* ex = (u32*)rb->p;
+  u64* status = (u64*)rb->p + ex_u64;
+  u32* ticket = (u32*)(status + ntiles);
+  CUDA_TRY(cudaMemsetAsync(status, 0, (size_t)(ntiles + 1) * 8, st));
   {
     // delta keys read once, ranges written once; every bisection step touches one
     // trace key row (bounded by the trace's key bytes)
@@ -829,12 +960,14 @@ static int32_t probe_chunk(Ctx* ctx, const Batch* delta, int nk, Batch* const* t
     u64 touched = std::min<u64>(nkeys * (u64)nb * 2 * lg, trace_rows) * (u64)std::max(nk, 1) * 8;
     ProfScope ps(ctx, KID_PROBE_RANGES, nkeys * ((u64)nk * 8 + (u64)nb * 8 + 4) + touched);
     const unsigned pg = (unsigned)std::min<u64>(blocks(nkeys), (u64)ctx->sm_count * 16);
-    k_probe_keys<<<pg, TB, 0, st>>>(delta->cols(), kstart, d_nkeys, refs, nk, f, lo, cnt, ktot, tot64);
+    k_probe_keys<<<pg, TB, 0, st>>>(delta->cols(), kstart, d_nkeys, refs, nk, f, lo, cnt, ktot);
   }
   const Mail mail = mail_begin(ctx);
-  k_row_counts<<<blocks(nd + 1), TB, 0, st>>>(head_ex, ktot, nd, rowcnt, ki, tot64, mail);
+  {
+    ProfScope ps(ctx, KID_SCAN, nd * 16);
+    k_row_counts_scan<<<ntiles, TB, 0, st>>>(ki, ktot, nd, ntiles, ticket, status, ex, mail);
+  }
   ctx->kernel_launches += 2;
-  TRY(exclusive_scan_u32(ctx, rowcnt, ex, nd));
   u64 total;
   TRY(mail_finish(ctx, mail, &total, 1));
   if (total >= 0xffffffffull) {
@@ -865,15 +998,15 @@ static int32_t probe_spine(Ctx* ctx, const Batch* delta, int nk, const Spine* tr
                            int delta_is_left, const dbsp_schema& out_schema, Batch** out) {
   const size_t nb = trace->batches.size();
   if (delta->n == 0 || nb == 0) { *out = batch_new_empty(ctx, out_schema); return DBSP_OK; }
-  BufP kstart, head_ex;
+  BufP kstart, ki;
   const u32* nkeys = nullptr;   // device count of the distinct delta keys
-  TRY(key_segments(ctx, delta, nk, &kstart, &head_ex, &nkeys));
+  TRY(key_segments(ctx, delta, nk, &kstart, &ki, &nkeys));
   std::vector<Batch*> parts;
   for (size_t b0 = 0; b0 < nb; b0 += MAX_REFS) {
     int cnt = (int)std::min<size_t>(MAX_REFS, nb - b0);
     Batch* part = nullptr;
     int32_t rc = probe_chunk(ctx, delta, nk, trace->batches.data() + b0, cnt, proj, delta_is_left, out_schema,
-                             (const u64*)kstart->p, (const u32*)head_ex->p, nkeys, &part);
+                             (const u64*)kstart->p, (const u32*)ki->p, nkeys, &part);
     if (rc) { for (Batch* p : parts) batch_unref(p); return rc; }
     parts.push_back(part);
   }

@@ -301,6 +301,28 @@ class Upload:
             pass
 
 
+class Download:
+    """In-flight D2H copy of a batch's flat rows (keeps the destination arrays alive)."""
+
+    def __init__(self, be, handle, n, cols, diffs):
+        self.be, self.h, self.n, self.cols, self.diffs = be, handle, n, cols, diffs
+
+    def finish(self):
+        """Wait for the copy; returns (cols trimmed to n rows, diffs trimmed)."""
+        if self.h:
+            h, self.h = self.h, None
+            self.be.api.call("download_finish", h)
+        return [None if c is None else c[: self.n] for c in self.cols], None if self.diffs is None else self.diffs[: self.n]
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.be.api._download_finish(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
 class Spine:
     """Owning handle of a trace (trace/spine_fueled.rs:107-119)."""
 
@@ -480,7 +502,24 @@ class Backend:
     def stats(self, reset=False):
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self.api.call("ctx_stats", self.ctx, C.byref(a), C.byref(b), C.byref(c), int(reset))
-        return {"kernel_launches": a.value, "h2d_bytes": b.value, "d2h_bytes": c.value}
+        n, us = C.c_uint64(), C.c_double()
+        self.api.call("ctx_sync_stats", self.ctx, C.byref(n), C.byref(us), int(reset))
+        return {"kernel_launches": a.value, "h2d_bytes": b.value, "d2h_bytes": c.value,
+                "host_waits": n.value, "host_wait_ms": us.value / 1e3}
+
+    def download_begin(self, batch: "Batch", cols: Sequence, diffs):
+        """Queue the D2H copy of `batch`'s flat rows into caller-owned (pinned) arrays: cols[l] takes lane l,
+        diffs the weights, each with room for len(batch) entries.  Returns a Download; .finish() waits."""
+        cols = [None if c is None else as_u64(c) for c in cols]
+        n = len(batch)
+        for c in cols:
+            assert c is None or len(c) >= n
+        assert diffs is None or len(diffs) >= n
+        ptrs = col_ptrs(cols)
+        h = C.c_void_p()
+        self.api.call("batch_download_begin", self.ctx, batch.h, ptrs, diffs.ctypes.data if diffs is not None else None,
+                      C.byref(h))
+        return Download(self, h.value, n, cols, diffs)
 
     def profile(self, enable=True):
         self.api.call("ctx_profile", self.ctx, int(enable))

@@ -249,6 +249,24 @@ int32_t dbsp_batch_schema(const dbsp_batch* b, dbsp_schema* out);
 int32_t dbsp_batch_download_csr(dbsp_ctx* ctx, const dbsp_batch* b,
                                 uint64_t* const* keys, uint64_t* offs,
                                 uint64_t* const* vals, int64_t* diffs);
+/* Asynchronous read of a batch's flat rows (the output handle of a circuit
+ * drained while the next step runs — the reference's OutputHandle is read by
+ * the client thread between steps, operator/output.rs:20-75).  _begin queues,
+ * on the context's read stream (its own: PCIe is full duplex, uploads are not
+ * delayed) and ordered after the work already queued on the compute stream, the copy of lane l (n_tuples u64) into cols[l] and of
+ * the weights into diffs (NULL entries are skipped); the destinations should
+ * be pinned host memory and must stay valid until _finish, which waits for
+ * the copy and releases the handle (and its reference on the batch). */
+typedef struct dbsp_download dbsp_download;
+int32_t dbsp_batch_download_begin(dbsp_ctx* ctx, const dbsp_batch* b,
+                                  uint64_t* const* cols, int64_t* diffs,
+                                  dbsp_download** out);
+int32_t dbsp_download_finish(dbsp_download* d);
+/* Host synchronisation counters: how many times the host waited for a count
+ * published by the device (mailbox read-backs) and for how long in total,
+ * since the last reset. */
+int32_t dbsp_ctx_sync_stats(dbsp_ctx* ctx, uint64_t* n_waits, double* wait_us,
+                            int32_t reset);
 /* Device pointers of the flat column-major rows (lane l, weights). */
 int32_t dbsp_batch_device_columns(const dbsp_batch* b, const uint64_t** cols,
                                   const int64_t** weights);

@@ -908,6 +908,11 @@ int32_t orc_batch_download_csr(orc_ctx*, const orc_batch* bb, u64* const* keys, 
 }
 
 int32_t orc_batch_device_columns(const orc_batch*, const u64**, const i64**) { return DBSP_ERR_UNSUPPORTED; }
+// no device, no asynchronous reads: the oracle's outputs are compared through download_csr
+struct orc_download;
+int32_t orc_batch_download_begin(orc_ctx*, const orc_batch*, u64* const*, i64*, orc_download**) { return DBSP_ERR_UNSUPPORTED; }
+int32_t orc_download_finish(orc_download*) { return DBSP_OK; }
+int32_t orc_ctx_sync_stats(orc_ctx*, u64* n, double* us, int32_t) { if (n) *n = 0; if (us) *us = 0; return DBSP_OK; }
 
 // fast_forward_keys + get_key (operator/time_series/watermark.rs:38-45).
 int32_t orc_batch_last_key(orc_ctx*, const orc_batch* b, u64* key, int32_t* valid) {
