@@ -7,8 +7,10 @@ kernel of interest can be profiled in isolation, e.g.
 what:  sort   Batch::from_tuples of 4.6 M unsorted 3-lane rows (q4's bids_by_auction shape): k_props, k_pack12,
               k_sample, k_rs_hist_all, k_rs_pass, k_bucket_ids, k_chunk_sort, k_reduce_emit
        sort2  the same with 6-lane rows (two key words, q7's bids_by_price shape)
-       join   a 4.6 M-row delta against a 3-batch trace of 30 M rows: k_probe_keys, k_row_counts, k_probe_fill
+       join   a 4.6 M-row delta against a 3-batch trace of 30 M rows: k_key_segments, k_probe_keys, k_row_counts_scan, k_probe_fill
        merge  2 x 20 M-row OrdIndexedZSet<u64,u64,i64> merge: k_merge_partition, k_merge_tiles
+       merge1 the same with OrdZSet<u64,i64> rows (one lane + staged weights)
+       project  flat_map_index of a 40 M-row table with a 50 % filter, output ordered on arrival: k_project_rows, k_props
 """
 import os
 import sys
@@ -56,10 +58,21 @@ def main():
             o = be.join_delta_trace(d, tr, proj, delta_is_left=True)
         be.sync()
         print(what, len(o), tr.stats())
-    elif what == "merge":
+    elif what in ("merge", "merge1"):
         import bench
 
-        print(bench.merge_sweep(0, rows=20_000_000, n_val_lanes=1, reps=reps))
+        print(bench.merge_sweep(0, rows=20_000_000, n_val_lanes=1 if what == "merge" else 0, reps=reps))
+    elif what == "project":
+        from dbsp_b200 import col
+
+        m = 40_000_000   # bid-table shape: (auction, bidder, price, date_time), filter on price, key by auction
+        cols = [rng.integers(1000, 300_000, m).astype(np.uint64), rng.integers(1000, 100_000, m).astype(np.uint64),
+                rng.integers(0, 1 << 24, m).astype(np.uint64), np.arange(m, dtype=np.uint64)]
+        proj = Proj(Schema("u", "uu"), [col(3), col(0), col(2)], where=[col(2).lt(1 << 23)])
+        for _ in range(reps):
+            b = be.batch_from_table(cols, proj)
+        be.sync()
+        print(what, len(b))
     else:
         raise SystemExit("unknown " + what)
 
