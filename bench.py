@@ -498,6 +498,10 @@ def run_reference(args, query, bench_steps=None, warmup=None, n_workers=None, gp
     E, S = args.events_per_step * gpus, args.circuit_steps or CIRCUIT_STEPS[query]
     Kb = args.steps if bench_steps is None else bench_steps
     Wb = args.warmup if warmup is None else warmup
+    # bounded sample: the whole CPU run stays below ~2.4 G generated events (minutes, a few GB of host columns) by
+    # running fewer circuit steps per bench step — the circuit step itself (E events) is never shrunk
+    S_full = S
+    S = max(1, min(S, 2_400_000_000 // max(1, (Wb + Kb) * E)))
     W, K = Wb * S, Kb * S
     steps = gen_steps(query, 0, 1, W + K, E, pinned=False)
     secs, rows, fps, how = nw.run(query, T, steps, native=True)
@@ -505,7 +509,7 @@ def run_reference(args, query, bench_steps=None, warmup=None, n_workers=None, gp
     in_rows = rows_in(steps, W, W + K)
     return {"value": E * K / timed, "rows_per_s": in_rows / timed, "cores": T, "kind": "port", "ms_per_step": 1e3 * timed / Kb,
             "bench_steps": Kb, "warmup": Wb, "build": how, "last_step_out_rows": rows[-1],
-            "sample": f"{query}: {Wb}+{Kb} bench steps x {S} circuit steps of {E} events on {T} native oracle worker threads "
+            "sample": f"{query}: {Wb}+{Kb} bench steps x {S} circuit steps{'' if S == S_full else f' (of {S_full}: bounded sample)'} of {E} events on {T} native oracle worker threads "
                       f"(C++ port of the reference's algorithms, hash-shard + in-process exchange, {how})"}
 
 
