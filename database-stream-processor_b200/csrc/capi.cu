@@ -802,29 +802,42 @@ struct dbsp_download {
 int32_t dbsp_batch_download_begin(dbsp_ctx* ctx, const dbsp_batch* bb, uint64_t* const* cols, int64_t* diffs,
                                   dbsp_download** out) { ENTER(ctx);
   Batch* b = B(bb);
+  cudaEvent_t done;
+  CUDA_TRY(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+  auto queue = [&]() -> int32_t {
+    if (b->n) {
+      // the read stream picks the batch up once the kernels that produce it have run
+      cudaEvent_t ev;
+      CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      cudaError_t e1 = cudaEventRecord(ev, ctx->stream);
+      cudaError_t e2 = cudaStreamWaitEvent(ctx->read_stream, ev, 0);
+      cudaEventDestroy(ev);
+      CUDA_TRY(e1);
+      CUDA_TRY(e2);
+      for (int l = 0; l < b->nl(); l++) {
+        if (!cols || !cols[l]) continue;
+        CUDA_TRY(cudaMemcpyAsync(cols[l], b->col[l], b->n * 8, cudaMemcpyDeviceToHost, ctx->read_stream));
+        ctx->d2h_bytes += b->n * 8;
+      }
+      if (diffs) {
+        CUDA_TRY(cudaMemcpyAsync(diffs, b->w, b->n * 8, cudaMemcpyDeviceToHost, ctx->read_stream));
+        ctx->d2h_bytes += b->n * 8;
+      }
+    }
+    CUDA_TRY(cudaEventRecord(done, ctx->read_stream));
+    return DBSP_OK;
+  };
+  const int32_t rc = queue();
+  if (rc != DBSP_OK) {   // whatever was queued must not outlive the caller's buffers
+    cudaStreamSynchronize(ctx->read_stream);
+    cudaEventDestroy(done);
+    return rc;
+  }
   dbsp_download* d = new dbsp_download();
   d->ctx = ctx;
   d->b = b;
+  d->done = done;
   batch_ref(b);   // the rows must outlive the copy
-  CUDA_TRY(cudaEventCreateWithFlags(&d->done, cudaEventDisableTiming));
-  if (b->n) {
-    // the read stream picks the batch up once the kernels that produce it have run
-    cudaEvent_t ev;
-    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventRecord(ev, ctx->stream));
-    CUDA_TRY(cudaStreamWaitEvent(ctx->read_stream, ev, 0));
-    CUDA_TRY(cudaEventDestroy(ev));
-    for (int l = 0; l < b->nl(); l++) {
-      if (!cols || !cols[l]) continue;
-      CUDA_TRY(cudaMemcpyAsync(cols[l], b->col[l], b->n * 8, cudaMemcpyDeviceToHost, ctx->read_stream));
-      ctx->d2h_bytes += b->n * 8;
-    }
-    if (diffs) {
-      CUDA_TRY(cudaMemcpyAsync(diffs, b->w, b->n * 8, cudaMemcpyDeviceToHost, ctx->read_stream));
-      ctx->d2h_bytes += b->n * 8;
-    }
-  }
-  CUDA_TRY(cudaEventRecord(d->done, ctx->read_stream));
   *out = d;
   return DBSP_OK;
 }
