@@ -426,6 +426,7 @@ int32_t dbsp_ctx_sync_stats(dbsp_ctx* c, uint64_t* n_waits, double* wait_us, int
 void* dbsp_ctx_stream(dbsp_ctx* c) { return (void*)c->stream; }
 
 int32_t dbsp_ctx_profile(dbsp_ctx* c, int32_t enable) { ENTER(c);
+  if (enable == 2) { c->prof_on = false; return DBSP_OK; }   // pause: keep what was collected, record nothing more
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   for (auto& r : c->prof) { c->ev_pool.push_back(r.a); c->ev_pool.push_back(r.b); }
   c->prof.clear();

@@ -524,6 +524,10 @@ class Backend:
     def profile(self, enable=True):
         self.api.call("ctx_profile", self.ctx, int(enable))
 
+    def profile_pause(self):
+        """Stop recording per-kernel events; what was collected stays readable (a sampling window)."""
+        self.api.call("ctx_profile", self.ctx, 2)
+
     def profile_read(self):
         """{kernel name: dict(launches, ms, alg_bytes)} since profile(True)."""
         out, i = {}, 0

@@ -138,7 +138,9 @@ const char* dbsp_last_error(void);
 int32_t dbsp_ctx_stats(dbsp_ctx* ctx, uint64_t* kernel_launches,
                        uint64_t* h2d_bytes, uint64_t* d2h_bytes, int32_t reset);
 /* Optional per-kernel timing (CUDA events on the context's stream around the
- * library's own kernels).  enable != 0 starts a fresh collection.  _read
+ * library's own kernels).  enable == 1 starts a fresh collection, enable == 2
+ * pauses it (what was collected stays readable, nothing more is recorded —
+ * a sampling window inside a longer timed region), enable == 0 ends it.  _read
  * returns, for kernel class `kernel_id` (0,1,2,... until DBSP_ERR_INVALID),
  * its name, launch count, summed device time and algorithmic bytes (the
  * per-kernel byte formulas of DESIGN.md). */
