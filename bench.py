@@ -515,6 +515,7 @@ def run_reference(args, query, bench_steps=None, warmup=None, n_workers=None, gp
     in_rows = rows_in(steps, W, W + K)
     return {"value": E * K / timed, "rows_per_s": in_rows / timed, "cores": T, "kind": "port", "ms_per_step": 1e3 * timed / Kb,
             "bench_steps": Kb, "warmup": Wb, "build": how, "last_step_out_rows": rows[-1],
+            "circuit_steps_per_bench_step": S, "circuit_steps_per_bench_step_full": S_full, "timed_events": E * K,
             "sample": f"{query}: {Wb}+{Kb} bench steps x {S} circuit steps{'' if S == S_full else f' (of {S_full}: bounded sample)'} of {E} events on {T} native oracle worker threads "
                       f"(C++ port of the reference's algorithms, hash-shard + in-process exchange, {how})"}
 
@@ -548,6 +549,11 @@ def main():
         # same workload as the GPU arm at --gpus N: N x E events per circuit step, all on this host's cores
         r = run_reference(args, primary, gpus=max(args.gpus, 1))
         cfg = workload_cfg(primary, E, S, W, K, max(args.gpus, 1))
+        if r["circuit_steps_per_bench_step"] != r["circuit_steps_per_bench_step_full"]:
+            # same circuit steps (events per step, query, generator) as the GPU arm, fewer of them per bench step
+            cfg["reference_sample"] = {"circuit_steps_per_bench_step_run": r["circuit_steps_per_bench_step"],
+                                       "timed_circuit_steps_run": r["circuit_steps_per_bench_step"] * K,
+                                       "timed_events_run": r["timed_events"]}
         line = {"impl_note": f"CPU arm: every circuit step's {max(args.gpus, 1) * E} events on one host, {r['cores']} worker threads; the Rust "
                              "reference cannot be built here (no rustc): this is the C++ port under oracle/ (kind: port)",
                 "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
