@@ -4,3 +4,7 @@ import recursion_cases as rc
 
 def test_oracle_join_trace_test(oracle):
     rc.run_join_trace_test(oracle)
+
+
+def test_oracle_propagate_test(oracle):
+    rc.run_propagate_test(oracle)
