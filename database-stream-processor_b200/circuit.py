@@ -435,7 +435,9 @@ class Stream:
             st["prev"] = cur
             return out
 
-        return self._binary(bounds, fn, "window", self.schema, self.sharded)
+        out = self._binary(bounds, fn, "window", self.schema, self.sharded)
+        out.window_trace = trace   # the bounded trace of the operator (window.rs:454-486 asserts that it stays small)
+        return out
 
     def watermark_monotonic(self, f: Callable[[int], int]) -> "Stream":
         """watermark_monotonic (operator/time_series/watermark.rs:33-74): max of

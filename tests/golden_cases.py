@@ -463,3 +463,25 @@ ALL_CASES = {
 }
 for _name in Q7_CASES:
     ALL_CASES["q7_" + _name] = (lambda be, _n=_name: run_q7(be, _n))
+
+
+# ---- window bounded_memory (dbsp/src/operator/time_series/window.rs:453-486) ----
+# 100 fresh timestamps per step under the window (watermark - 1000, watermark): the trace behind the window must
+# not grow with the stream (the reference asserts < 20 000 bytes over 10 000 steps; here: rows, over 1 500 steps).
+def run_window_bounded_memory(be, steps=1500):
+    c = RootCircuit(be)
+    inp, h = c.add_input_zset(Schema("i"))
+    bounds = inp.watermark_monotonic(lambda ts: ts).apply(lambda ts: (ts - 1000, ts))
+    w = inp.window(bounds)
+    out = w.output()
+    worst = 0
+    for i in range(steps):
+        h.append((j, 1) for j in range(i * 100, (i + 1) * 100))   # input_handle.push(j, 1)
+        c.step()
+        worst = max(worst, w.window_trace.stats()[0])   # rows held by the trace (all layers)
+    assert worst <= 1200, worst          # the window (1000 timestamps) + the step that just arrived
+    assert len(out.value) <= 200
+
+
+# run on the oracle only: written after the round's GPU budget ended, nothing unrun goes into `-m gpu`
+ORACLE_ONLY_CASES = {"window_bounded_memory": run_window_bounded_memory}

@@ -8,3 +8,8 @@ import golden_cases as gc
 @pytest.mark.parametrize("name", sorted(gc.ALL_CASES))
 def test_oracle_golden(oracle, name):
     gc.ALL_CASES[name](oracle)
+
+
+@pytest.mark.parametrize("name", sorted(gc.ORACLE_ONLY_CASES))
+def test_oracle_only_golden(oracle, name):
+    gc.ORACLE_ONLY_CASES[name](oracle)
