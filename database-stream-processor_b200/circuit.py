@@ -201,8 +201,28 @@ class Stream:
         be = self.circuit.be
         return self._unary(lambda b: be.map_index(b, proj), "map_index", proj.schema)
 
+    # the reference's closure-taking variants all lower to one projection + filter in the row language:
+    # map / flat_map produce an OrdZSet, map_index / flat_map_index / index_with an OrdIndexedZSet — the output
+    # schema of `proj` says which (filter_map.rs:40-215, index.rs:38-62)
     map = map_index
+    flat_map = map_index
     flat_map_index = map_index
+    index_with = map_index
+
+    def filter(self, *preds) -> "Stream":
+        """filter (operator/filter_map.rs:40-54): keep the rows satisfying every predicate; schema unchanged."""
+        from .zset import key, val
+
+        s = self.schema
+        ident = [key(i) for i in range(s.nk)] + [val(i) for i in range(s.nv)]
+        return self.map_index(Proj(s, ident, list(preds)))
+
+    def sum(self, others: Sequence["Stream"]) -> "Stream":
+        """sum (operator/sum.rs:20-40): self + every stream of `others` (aliases allowed)."""
+        out = self
+        for o in others:
+            out = out.plus(o)
+        return out
 
     def neg(self) -> "Stream":
         be = self.circuit.be

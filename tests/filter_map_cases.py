@@ -98,3 +98,65 @@ def run_sum_zero(be, steps=100):
             total = be.merge(total, x)
         assert len(total) == 0, total.rows()
         s1, s2, s3 = be.merge(s1, d1), be.merge(s2, d2), be.merge(s3, d3)
+
+
+# ---- the same test through the circuit API, shaped like the reference's (one circuit, every operator inspected) ----
+def run_filter_map_circuit(be):
+    from dbsp_b200 import RootCircuit
+
+    c = RootCircuit(be)
+    it = iter([be.batch_from_rows(Schema("iu"), [(a, CODE[b], 1) for a, b in INPUT])])
+    inp = c.add_source(lambda: next(it), Schema("iu"))
+    input_indexed = inp.index(1)
+    input_ints = input_indexed.map(Proj(INTS, [key(0)]))
+    streams = {
+        "filter_pos": input_ints.filter(pos),
+        "indexed": input_ints.map_index(Proj(Schema("i", "i"), [n, n])),
+        "times2": input_ints.map(Proj(INTS, [n * 2])),
+        "times2_pos": input_ints.flat_map(Proj(INTS, [n * 2], [pos])),
+        "neg": input_ints.map(Proj(INTS, [-n])),
+        "neg_pos": input_ints.flat_map(Proj(INTS, [-n], [pos])),
+        "sqr": input_ints.map(Proj(INTS, [n * n])),
+        "sqr_pos": input_ints.flat_map(Proj(INTS, [n * n], [pos])),
+        "sqr_pos_indexed": input_ints.flat_map_index(Proj(Schema("i", "i"), [n * n, n], [pos])),
+        "i_filter_pos": input_indexed.filter(pos, foo),
+        "i_indexed": input_indexed.map_index(Proj(IDX, [n * 2, s])),
+        "i_times2": input_indexed.map(Proj(INTS, [n * 2])),
+        "i_times2_pos": input_indexed.flat_map(Proj(INTS, [n * 2], [pos, foo])),
+        "i_neg": input_indexed.map(Proj(INTS, [-n])),
+        "i_neg_pos": input_indexed.flat_map(Proj(INTS, [-n], [pos, foo])),
+        "i_sqr": input_indexed.map(Proj(INTS, [n * n])),
+        "i_sqr_pos": input_indexed.flat_map(Proj(INTS, [n * n], [pos, foo])),
+        "i_sqr_pos_indexed": input_indexed.flat_map_index(Proj(IDX, [n * n, s], [pos])),
+    }
+    assert set(streams) == set(CASES)
+    seen = {}
+    for name, st in streams.items():
+        st.inspect(lambda b, name=name: seen.__setitem__(name, {tuple(int(x) for x in r[:-1]): int(r[-1]) for r in b.rows()}))
+    c.step()
+    for name, (_, _, want) in CASES.items():
+        assert seen[name] == want, (name, seen[name])
+
+
+def run_sum_circuit(be, steps=20):
+    """zset_sum of sum.rs through Stream.sum, source3 supplied twice."""
+    from dbsp_b200 import RootCircuit
+
+    sch = Schema("u")
+    c = RootCircuit(be)
+    state = {"s1": be.batch_empty(sch), "s2": be.batch_empty(sch), "s3": be.batch_empty(sch)}
+    deltas = {"s1": [(5, 1), (6, 2)], "s2": [(5, -1)], "s3": [(6, -1)]}
+
+    def gen(k):
+        def g():
+            res = state[k]
+            state[k] = be.merge(res, be.batch_from_rows(sch, deltas[k]))
+            return res
+        return g
+
+    s1, s2, s3 = (c.add_source(gen(k), sch) for k in ("s1", "s2", "s3"))
+    sizes = []
+    s3.sum([s2, s1, s3]).inspect(lambda b: sizes.append(len(b)))
+    for _ in range(steps):
+        c.step()
+    assert sizes == [0] * steps

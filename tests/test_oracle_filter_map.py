@@ -19,3 +19,12 @@ def test_oracle_neg_plus_and_sum_are_zero(oracle):
     """zset_sum (operator/neg.rs:85-110, operator/sum.rs:138-200)."""
     fc.run_neg_plus_zero(oracle)
     fc.run_sum_zero(oracle)
+
+
+def test_oracle_filter_map_circuit(oracle):
+    """filter_map_test as one circuit over Stream.{filter,map,flat_map,map_index,flat_map_index}."""
+    fc.run_filter_map_circuit(oracle)
+
+
+def test_oracle_sum_circuit(oracle):
+    fc.run_sum_circuit(oracle)

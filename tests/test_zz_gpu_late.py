@@ -33,3 +33,11 @@ def test_cuda_propagate_test(cuda):
 @pytest.mark.parametrize("name", sorted(gc.ORACLE_ONLY_CASES))
 def test_cuda_late_golden(cuda, name):
     gc.ORACLE_ONLY_CASES[name](cuda)
+
+
+def test_cuda_filter_map_circuit(cuda):
+    fc.run_filter_map_circuit(cuda)
+
+
+def test_cuda_sum_circuit(cuda):
+    fc.run_sum_circuit(cuda)
