@@ -58,6 +58,14 @@ class InputHandle:
         """rows: iterable of (lane.., weight)."""
         self.pending.extend(rows)
 
+    def push(self, *row):
+        """push(k.., w) (operator/input.rs:676-681): one (lane.., weight) update."""
+        self.pending.append(tuple(row))
+
+    def clear_input(self):
+        """clear_input (operator/input.rs:697-703): drop the updates buffered since the last step."""
+        self.pending = []
+
     def _take(self) -> Batch:
         rows, self.pending = self.pending, []
         return self.circuit.be.batch_from_rows(self.schema, rows)

@@ -160,3 +160,32 @@ def run_sum_circuit(be, steps=20):
     for _ in range(steps):
         c.step()
     assert sizes == [0] * steps
+
+
+# ---- zset_test_st (operator/input.rs:1058-1100): append / push (with a cancelling pair) / clear_input on the
+# add_input_zset handle; the stream sees input_batches(), input_batches() again, then the empty Z-set.
+INPUT_BATCHES = [{1: 1, 2: 1, 3: 1}, {5: -1, 10: 2, 11: 11}, {}]
+
+
+def run_input_zset_test(be):
+    from dbsp_b200 import RootCircuit
+
+    c = RootCircuit(be)
+    stream, handle = c.add_input_zset(Schema("u"))
+    seen = []
+    stream.inspect(lambda b: seen.append({int(r[0]): int(r[1]) for r in b.rows()}))
+    vecs = [sorted(d.items()) for d in INPUT_BATCHES]
+    for v in vecs:
+        handle.append(list(v))
+        c.step()
+    for v in vecs:
+        for k, w in v:
+            handle.push(k, w)
+        handle.push(5, 1)
+        handle.push(5, -1)
+        c.step()
+    for v in vecs:
+        handle.append(list(v))
+    handle.clear_input()
+    c.step()
+    assert seen == INPUT_BATCHES + INPUT_BATCHES + [{}], seen

@@ -28,3 +28,8 @@ def test_oracle_filter_map_circuit(oracle):
 
 def test_oracle_sum_circuit(oracle):
     fc.run_sum_circuit(oracle)
+
+
+def test_oracle_input_zset(oracle):
+    """zset_test_st (operator/input.rs:1058-1100)."""
+    fc.run_input_zset_test(oracle)

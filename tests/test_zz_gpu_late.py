@@ -41,3 +41,7 @@ def test_cuda_filter_map_circuit(cuda):
 
 def test_cuda_sum_circuit(cuda):
     fc.run_sum_circuit(cuda)
+
+
+def test_cuda_input_zset(cuda):
+    fc.run_input_zset_test(cuda)
